@@ -1,0 +1,124 @@
+/* speechcatcher_b200 -- C ABI of the B200-native multi-stream streaming decode path.
+ *
+ * Drop-in boundary for speechcatcher's `Speech2TextStreaming` native decoder.  The reference is pure
+ * Python (no FFI of its own), so every entry point below cites the Python interface it replaces
+ * (paths relative to the reference checkout).  A maintainer binds these with ctypes; the binding the
+ * repo ships is speechcatcher_b200/_lib.py and the reference-side stub is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only, no torch types; `stream` is a cudaStream_t passed as void*
+ *   - the caller owns every device buffer (including the engine workspace); the library allocates no
+ *     per-engine device memory and keeps no global mutable state besides small constant tables
+ *   - every function returns 0 on success and a negative code on failure; sc_last_error() explains
+ *   - functions never throw across the boundary; one driver thread per engine handle
+ */
+#ifndef SPEECHCATCHER_B200_H
+#define SPEECHCATCHER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_OK 0
+#define SC_ERR_CUDA (-1)
+#define SC_ERR_ARG (-2)
+#define SC_ERR_CAPACITY (-3)
+#define SC_ERR_STATE (-4)
+
+/* Architecture + capacity of one engine (one GPU, many streams).
+ * Mirrors what Speech2TextStreaming.__init__/_load_model read from config.yaml
+ * (speech2text_streaming.py:43-51, 210-232) plus batching capacities. */
+typedef struct ScConfig {
+  int32_t d_model;       /* encoder_conf.output_size (256) */
+  int32_t enc_heads;     /* encoder_conf.attention_heads */
+  int32_t enc_layers;    /* encoder_conf.num_blocks */
+  int32_t dec_heads;     /* decoder_conf.attention_heads */
+  int32_t dec_layers;    /* decoder_conf.num_blocks */
+  int32_t vocab;         /* rows of decoder.embed.0.weight (1024) */
+  int32_t ffn;           /* linear_units (2048; not configurable in the reference) */
+  int32_t n_streams;     /* concurrent streams S held by this engine */
+  int32_t beam;          /* beam_size (<= 20) */
+  int32_t max_chunk;     /* largest number of samples one stream may push per call */
+  int32_t max_frames;    /* capacity of the per-stream encoder buffer (frames of 40 ms) */
+  int32_t use_bbd;       /* Speech2TextStreaming(use_bbd=...) */
+  int32_t precision;     /* 0 = fp32 (parity mode), 1 = bf16 tensor-core GEMMs */
+  float ctc_weight;      /* 0.3; decoder weight is 1 - ctc_weight (speech2text_streaming.py:143-150) */
+} ScConfig;
+
+typedef struct ScPushStats {
+  int32_t n_feature_frames;   /* feature frames emitted by the frontend over all streams */
+  int32_t n_encoder_blocks;   /* encoder blocks processed */
+  int32_t n_encoder_frames;   /* encoder output frames appended */
+  int32_t n_decode_steps;     /* search iterations launched (max over streams, incl. the probe step) */
+  int32_t n_kernel_launches;  /* CUDA kernels launched by this call */
+  int32_t reserved[3];
+} ScPushStats;
+
+typedef struct ScStreamPlan {     /* host-side shape plan of one stream for one push (debug / tests) */
+  int32_t called;             /* 1 if process_block would be called (frontend emitted features) */
+  int32_t n_feat;             /* emitted feature frames */
+  int32_t n_sub;              /* new sub-sampled frames */
+  int32_t n_blocks;           /* encoder blocks formed */
+  int32_t n_enc_out;          /* encoder output frames appended */
+  int32_t enc_len;            /* encoder buffer length after the push */
+  int32_t n_decode_blocks;    /* decode blocks queued */
+  int32_t last_T;             /* memory length of the last queued decode block (0 if none) */
+} ScStreamPlan;
+
+const char* sc_version(void);
+const char* sc_last_error(void);
+
+/* ---- engine (replaces Speech2TextStreaming + BlockwiseSynchronousBeamSearch state, batched) ---- */
+/* Bytes of caller-owned device workspace the engine needs for `cfg`. */
+int sc_engine_workspace_bytes(const ScConfig* cfg, size_t* bytes);
+/* Create an engine over `workspace` (device memory, 256-byte aligned, zero-initialised by the caller). */
+int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** handle);
+int sc_engine_destroy(void* handle);
+/* Register one packed weight tensor by name (device pointer, caller keeps it alive).
+ * Names/layouts: see speechcatcher_b200/weights.py (built from the reference state_dict keys). */
+int sc_engine_set_weight(void* handle, const char* name, const void* dev_ptr, size_t n_elem);
+/* Host tables: hann(400), mel_fb[257*80] (model.frontend buffers, stft_frontend.py:68-85) and the
+ * global MVN statistics mean/std[80] in fp64 (checkpoint_loader.py:210-237); mean may be NULL. */
+int sc_engine_set_frontend(void* handle, const float* window400, const float* mel_fb, const double* mean,
+                           const double* std_);
+int sc_engine_finalize(void* handle);
+/* Speech2TextStreaming.reset() for the listed streams (speech2text_streaming.py:252-263). */
+int sc_engine_reset(void* handle, const int32_t* streams, int32_t n, void* stream);
+/* One Speech2TextStreaming.__call__ per listed stream (speech2text_streaming.py:402-464):
+ * wave_dev[i*ld_wave ...] holds n_samples[i] new samples of stream streams[i]. */
+int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const int32_t* streams,
+                   const int32_t* n_samples, const int32_t* is_final, int32_t n, void* stream,
+                   ScPushStats* stats);
+/* Current beam of one stream (beam_state.hypotheses): copies to host buffers and synchronises.
+ * yseq/xpos: [beam][max_len] int32, score: [beam] fp64. */
+int sc_engine_read_beam(void* handle, int32_t stream_id, int32_t max_len, int32_t* n_hyp, int32_t* len,
+                        int32_t* process_idx, int32_t* yseq, int32_t* xpos, double* score, void* stream);
+/* Host plan of the last push for stream `stream_id`. */
+int sc_engine_last_plan(void* handle, int32_t stream_id, ScStreamPlan* plan);
+/* Named internal device buffer (tests / debugging): pointer, element count and row pitch. */
+int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem);
+
+/* ---- host-only shape planner (no CUDA calls; CPU-testable) ---- */
+int sc_planner_create(int32_t n_streams, void** planner);
+int sc_planner_destroy(void* planner);
+int sc_planner_reset(void* planner, int32_t stream_id);
+int sc_planner_push(void* planner, int32_t stream_id, int32_t n_samples, int32_t is_final, ScStreamPlan* plan);
+
+/* ---- single operators over raw device pointers (used by the parity tests) ---- */
+/* LayerNorm eps=1e-12 (model/layers/normalization.py:23) */
+int sc_layernorm_f32(const float* x, const float* w, const float* b, float* y, int32_t rows, int32_t d,
+                     void* stream);
+/* y = act(x W^T + bias) + residual  (torch.nn.functional.linear; fp32 CUDA-core path) */
+int sc_linear_f32(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                  int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
+/* same contract on the tcgen05 tensor-core path: bf16 operands, fp32 accumulate */
+int sc_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual,
+                   float* y_f32, void* y_bf16, int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

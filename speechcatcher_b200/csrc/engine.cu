@@ -1,0 +1,664 @@
+// Host engine + C ABI: one engine per GPU holds the device state of S independent streams and
+// advances all of them through frontend -> encoder -> block-synchronous beam search per push.
+//
+// Replaces (batched, on device): speechcatcher/speech2text_streaming.py:402-464 (__call__),
+//   speechcatcher/beam_search/beam_search.py:507-653 (process_block) and everything below them.
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/speechcatcher_b200.h"
+#include "kernels.h"
+#include "planner.h"
+
+namespace scb {
+
+int launch_gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
+                     int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int K, int relu,
+                     const int* n_rows_dev, cudaStream_t st);
+
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Caps {
+  int feat_cap, t1_cap, t2_cap, sub_cap, nb_cap, qcap, Tcap, Lcap, nb_max, rows_max, sub_rows_max, R;
+};
+
+static Caps make_caps(const ScConfig& c) {
+  Caps k;
+  const int fmax = 1 + (c.max_chunk + 400) / 160 + 1;   // STFT frames of the largest slab
+  const int tmax = 12 + fmax;                            // + carried feature frames
+  k.feat_cap = tmax + 4;
+  k.t1_cap = (tmax - 3) / 2 + 1;
+  k.t2_cap = std::max(1, (k.t1_cap - 3) / 2 + 1);
+  k.sub_cap = 40 + k.t2_cap + 1;
+  k.nb_cap = std::max(1, (k.sub_cap - 24 + 15) / 16);
+  k.qcap = k.nb_cap + 2;
+  k.Tcap = c.max_frames;
+  k.Lcap = 512;                                          // > max_length (500) + sos + 1
+  k.nb_max = c.n_streams * k.nb_cap;
+  k.rows_max = k.nb_max * kSlots;
+  k.sub_rows_max = c.n_streams * k.t2_cap;
+  k.R = c.n_streams * c.beam;
+  return k;
+}
+
+struct EncLayerW { const float *ln1w, *ln1b, *qkvw, *qkvb, *ow, *ob, *ln2w, *ln2b, *f1w, *f1b, *f2w, *f2b;
+                   const __nv_bfloat16 *qkvw16, *ow16, *f1w16, *f2w16; };
+struct DecLayerW { const float *ln1w, *ln1b, *sqkvw, *sqkvb, *sow, *sob, *ln2w, *ln2b, *cqw, *cqb, *ckvw, *ckvb,
+                   *cow, *cob, *ln3w, *ln3b, *f1w, *f1b, *f2w, *f2b;
+                   const __nv_bfloat16 *sqkvw16, *sow16, *cqw16, *ckvw16, *cow16, *f1w16, *f2w16; };
+
+struct Engine {
+  ScConfig cfg;
+  Caps cap;
+  Planner planner;
+  std::unordered_map<std::string, const void*> wmap;
+  bool finalized = false;
+  // weights
+  const float *pe = nullptr, *c1w = nullptr, *c1b = nullptr, *c2w = nullptr, *c2b = nullptr, *eow = nullptr, *eob = nullptr;
+  const float *eaw = nullptr, *eab = nullptr, *ctcw = nullptr, *ctcb = nullptr, *demb = nullptr, *daw = nullptr, *dab = nullptr,
+              *doutw = nullptr, *doutb = nullptr;
+  const __nv_bfloat16 *c2w16 = nullptr, *eow16 = nullptr, *ctcw16 = nullptr, *doutw16 = nullptr;
+  std::vector<EncLayerW> enc;
+  std::vector<DecLayerW> dec;
+  // frontend stats (device, inside workspace)
+  double *d_mean = nullptr, *d_std = nullptr;
+  bool has_stats = false;
+  // device buffers
+  float *wbuf, *featbuf, *h1, *h2, *subbuf, *prev_addin, *enc_ctx, *addin, *X, *Nrm, *QKV, *Att, *FF, *encbuf, *ctcx;
+  float *dx, *dn, *dqkv, *dq, *dattn, *dffn, *dlogp;
+  __nv_bfloat16 *Nrm16, *Att16, *FF16, *h2_16, *dn16, *dattn16, *dffn16, *encnew16;
+  SearchBuffers sb;
+  // device descriptor arrays
+  FrontendDesc* d_fd; SubDesc* d_sd; BlockDesc* d_blk;
+  int *d_carry_f, *d_carry_s;       // 3 x S each: stream, src, n
+  int64_t *d_c2_a, *d_c2_c, *d_en_a, *d_en_ctc, *d_en_kv;
+  int *d_en_flag, *d_c2_seg, *d_q, *d_reset;
+  // pinned host staging
+  unsigned char* h_stage = nullptr; size_t h_stage_bytes = 0;
+  int* h_flag = nullptr;            // [2] n_active probe
+  cudaEvent_t ev[2];
+  std::unordered_map<std::string, std::pair<void*, size_t>> named;
+  std::vector<ScStreamPlan> last_plan;
+  int launches = 0;
+
+  explicit Engine(const ScConfig& c) : cfg(c), cap(make_caps(c)), planner(c.n_streams), last_plan(c.n_streams) {}
+};
+
+// ---------------------------------------------------------------- workspace carving
+struct Carver {
+  unsigned char* base; size_t off = 0; bool dry;
+  Carver(void* b, bool d) : base((unsigned char*)b), dry(d) {}
+  template <typename T> T* take(size_t n) {
+    off = align_up(off);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static void carve(Engine& e, Carver& cv) {
+  const ScConfig& c = e.cfg; const Caps& k = e.cap;
+  const size_t S = c.n_streams, D = c.d_model, F = c.ffn, V = c.vocab, B = c.beam, R = k.R;
+  auto reg = [&](const char* name, void* p, size_t n) { if (!cv.dry) e.named[name] = {p, n}; };
+  e.d_mean = cv.take<double>(80); e.d_std = cv.take<double>(80);
+  e.wbuf = cv.take<float>(S * 512); reg("wbuf", e.wbuf, S * 512);
+  e.featbuf = cv.take<float>(S * k.feat_cap * 80); reg("featbuf", e.featbuf, S * k.feat_cap * 80);
+  e.h1 = cv.take<float>(S * k.t1_cap * 39 * D);
+  e.h2 = cv.take<float>((size_t)k.sub_rows_max * 19 * D);
+  e.subbuf = cv.take<float>(S * k.sub_cap * D); reg("subbuf", e.subbuf, S * k.sub_cap * D);
+  e.prev_addin = cv.take<float>(S * D);
+  e.enc_ctx = cv.take<float>(S * c.enc_layers * D);
+  e.addin = cv.take<float>((size_t)k.nb_max * D);
+  e.X = cv.take<float>((size_t)k.rows_max * D); reg("X", e.X, (size_t)k.rows_max * D);
+  e.Nrm = cv.take<float>((size_t)k.rows_max * D);
+  e.QKV = cv.take<float>((size_t)k.rows_max * 3 * D);
+  e.Att = cv.take<float>((size_t)k.rows_max * D);
+  e.FF = cv.take<float>((size_t)k.rows_max * F);
+  e.encbuf = cv.take<float>(S * k.Tcap * D); reg("encbuf", e.encbuf, S * k.Tcap * D);
+  e.ctcx = cv.take<float>(S * k.Tcap * V); reg("ctcx", e.ctcx, S * k.Tcap * V);
+  e.dx = cv.take<float>(R * D); e.dn = cv.take<float>(R * D); e.dqkv = cv.take<float>(R * 3 * D);
+  e.dq = cv.take<float>(R * D); e.dattn = cv.take<float>(R * D); e.dffn = cv.take<float>(R * F);
+  e.dlogp = cv.take<float>(R * V); reg("dlogp", e.dlogp, R * V);
+  if (c.precision == 1) {
+    e.Nrm16 = cv.take<__nv_bfloat16>((size_t)k.rows_max * D);
+    e.Att16 = cv.take<__nv_bfloat16>((size_t)k.rows_max * D);
+    e.FF16 = cv.take<__nv_bfloat16>((size_t)k.rows_max * F);
+    e.h2_16 = cv.take<__nv_bfloat16>((size_t)k.sub_rows_max * 19 * D);
+    e.dn16 = cv.take<__nv_bfloat16>(R * D); e.dattn16 = cv.take<__nv_bfloat16>(R * D);
+    e.dffn16 = cv.take<__nv_bfloat16>(R * F);
+    e.encnew16 = cv.take<__nv_bfloat16>(S * k.sub_cap * D);
+  }
+  SearchBuffers& sb = e.sb;
+  sb.S = c.n_streams; sb.B = c.beam; sb.V = c.vocab; sb.D = c.d_model; sb.H = c.dec_heads; sb.Ld = c.dec_layers;
+  sb.Tcap = k.Tcap; sb.Lcap = k.Lcap; sb.use_bbd = c.use_bbd; sb.qcap = k.qcap;
+  sb.w_dec = (float)(1.0 - (double)c.ctc_weight); sb.w_ctc = c.ctc_weight;
+  sb.ctcx = e.ctcx;
+  sb.xkv = cv.take<float>((size_t)c.dec_layers * S * k.Tcap * 2 * D);
+  sb.skv = cv.take<float>((size_t)c.dec_layers * S * k.Lcap * B * 2 * D);
+  sb.yseq = cv.take<int>(2 * S * B * k.Lcap); reg("yseq", sb.yseq, 2 * S * B * k.Lcap);
+  sb.xpos = cv.take<int>(2 * S * B * k.Lcap);
+  sb.anc = cv.take<unsigned char>(2 * S * B * k.Lcap);
+  sb.score = cv.take<double>(2 * S * B); sb.sc_dec = cv.take<double>(2 * S * B); sb.sc_ctc = cv.take<double>(2 * S * B);
+  sb.ctc_r = cv.take<float>(2 * S * B * (size_t)k.Tcap * 2);
+  sb.ctc_s = cv.take<float>(2 * S * B);
+  sb.ctl = cv.take<StreamCtl>(S); reg("ctl", sb.ctl, S * sizeof(StreamCtl) / sizeof(int));
+  sb.blkq_T = cv.take<int>(S * k.qcap); sb.blkq_final = cv.take<int>(S * k.qcap);
+  sb.row_sh = cv.take<int>(R); sb.row_base = cv.take<int>(S); sb.act_streams = cv.take<int>(S);
+  sb.n_rows = cv.take<int>(1); sb.n_active = cv.take<int>(1);
+  sb.logp = e.dlogp;
+  sb.pre_ids = cv.take<int>(R * kPreBeam); reg("pre_ids", sb.pre_ids, R * kPreBeam);
+  sb.psi = cv.take<float>(R * kPreBeam); reg("psi", sb.psi, R * kPreBeam);
+  sb.psi_eos = cv.take<float>(R);
+  sb.cand_val = cv.take<float>(R * B); sb.cand_tok = cv.take<int>(R * B); sb.cand_dec = cv.take<float>(R * B);
+  sb.cand_ctc = cv.take<float>(R * B); sb.cand_psi = cv.take<float>(R * B); sb.cand_col = cv.take<int>(R * B);
+  sb.new_parent = cv.take<int>(S * B); sb.new_col = cv.take<int>(S * B); sb.upd_flag = cv.take<int>(S);
+  // descriptors
+  e.d_fd = cv.take<FrontendDesc>(S); e.d_sd = cv.take<SubDesc>(S); e.d_blk = cv.take<BlockDesc>(k.nb_max);
+  e.d_carry_f = cv.take<int>(3 * S); e.d_carry_s = cv.take<int>(3 * S);
+  e.d_c2_a = cv.take<int64_t>((size_t)k.sub_rows_max * 19); e.d_c2_c = cv.take<int64_t>(k.sub_rows_max);
+  e.d_en_a = cv.take<int64_t>(S * k.sub_cap); e.d_en_ctc = cv.take<int64_t>(S * k.sub_cap);
+  e.d_en_kv = cv.take<int64_t>(S * k.sub_cap); e.d_en_flag = cv.take<int>(S * k.sub_cap);
+  e.d_c2_seg = cv.take<int>(16);
+  e.d_q = cv.take<int>(2 * S + 2 * S * k.qcap);
+  e.d_reset = cv.take<int>(S);
+}
+
+// ---------------------------------------------------------------- linear dispatch (fp32 SIMT / bf16 tcgen05)
+struct Lin {
+  const float* A; int lda; const __nv_bfloat16* A16; const float* W; const __nv_bfloat16* W16; const float* bias;
+  const float* R; int ldr; float* C; int ldc; __nv_bfloat16* C16; int M, N, K, relu; const int* n_rows_dev;
+};
+
+static int linear(Engine& e, const Lin& l, cudaStream_t st) {
+  e.launches++;
+  if (e.cfg.precision == 1 && l.A16 && l.W16) {
+    return launch_gemm_bf16(l.A16, l.lda, l.W16, l.bias, l.R, l.ldr, l.C, l.ldc, l.C16, l.ldc, l.M, l.N, l.K,
+                            l.relu, l.n_rows_dev, st);
+  }
+  GemmArgs g;
+  g.A = l.A; g.lda = l.lda; g.W = l.W; g.bias = l.bias; g.R = l.R; g.ldr = l.ldr; g.C = l.C; g.ldc = l.ldc;
+  g.M = l.M; g.N = l.N; g.K = l.K; g.relu = l.relu; g.n_rows_dev = l.n_rows_dev;
+  return launch_gemm_f32(g, st);
+}
+
+#define TRY(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
+
+// ---------------------------------------------------------------- encoder layers over all blocks of the push
+static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
+  const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, rows = n_blk * kSlots;
+  const bool tc = c.precision == 1;
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const EncLayerW& w = e.enc[l];
+    if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln1w, w.ln1b, e.Nrm16, D, rows, D, nullptr, st));
+    else TRY(launch_layernorm(e.X, D, w.ln1w, w.ln1b, e.Nrm, D, rows, D, nullptr, st));
+    TRY(linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
+    TRY(launch_enc_attention(e.QKV, e.Att, e.d_blk, n_blk, c.enc_heads, D, st));
+    TRY(linear(e, Lin{e.Att, D, nullptr, w.ow, nullptr, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
+    if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
+    else TRY(launch_layernorm(e.X, D, w.ln2w, w.ln2b, e.Nrm, D, rows, D, nullptr, st));
+    TRY(linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
+    TRY(linear(e, Lin{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr}, st));
+    TRY(launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, st));
+    e.launches += 5;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- one search iteration for all active streams
+static int run_decode_step(Engine& e, cudaStream_t st) {
+  const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, V = c.vocab, R = e.cap.R;
+  const SearchBuffers& sb = e.sb;
+  const int* nr = sb.n_rows;
+  const bool tc = c.precision == 1;
+  TRY(launch_dec_embed(sb, e.demb, e.pe, e.dx, st));
+  for (int l = 0; l < c.dec_layers; ++l) {
+    const DecLayerW& w = e.dec[l];
+    if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
+    else TRY(launch_layernorm(e.dx, D, w.ln1w, w.ln1b, e.dn, D, R, D, nr, st));
+    TRY(linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
+    TRY(launch_dec_attention(sb, 0, l, e.dqkv, 3 * D, e.dqkv + D, 3 * D, e.dattn, st));
+    TRY(linear(e, Lin{e.dattn, D, nullptr, w.sow, nullptr, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
+    if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln2w, w.ln2b, e.dn16, D, R, D, nr, st));
+    else TRY(launch_layernorm(e.dx, D, w.ln2w, w.ln2b, e.dn, D, R, D, nr, st));
+    TRY(linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
+    TRY(launch_dec_attention(sb, 1, l, e.dq, D, nullptr, 0, e.dattn, st));
+    TRY(linear(e, Lin{e.dattn, D, nullptr, w.cow, nullptr, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
+    if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
+    else TRY(launch_layernorm(e.dx, D, w.ln3w, w.ln3b, e.dn, D, R, D, nr, st));
+    TRY(linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
+    TRY(linear(e, Lin{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr}, st));
+    e.launches += 5;
+  }
+  if (tc) TRY(launch_layernorm_bf16(e.dx, D, e.daw, e.dab, e.dn16, D, R, D, nr, st));
+  else TRY(launch_layernorm(e.dx, D, e.daw, e.dab, e.dn, D, R, D, nr, st));
+  TRY(linear(e, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
+  TRY(launch_logsoftmax_prebeam(sb, e.dlogp, st));
+  TRY(launch_ctc_prefix(sb, st));
+  TRY(launch_combine_topk(sb, e.dlogp, st));
+  TRY(launch_beam_prune(sb, st));
+  TRY(launch_ctc_state_update(sb, st));
+  TRY(launch_step_finish(sb, st));
+  e.launches += 9;
+  return 0;
+}
+
+}  // namespace scb
+
+using namespace scb;
+
+// ================================================================== C ABI
+extern "C" {
+
+const char* sc_version(void) { return "speechcatcher_b200 0.1 (sm_100a)"; }
+const char* sc_last_error(void) { return get_last_error(); }
+
+static int check_cfg(const ScConfig* c) {
+  if (!c) { set_last_error("null config"); return SC_ERR_ARG; }
+  if (c->d_model != 256 || c->vocab != 1024 || c->ffn % 16 != 0) {
+    set_last_error("unsupported architecture: d_model=%d vocab=%d ffn=%d (kernels are specialised for 256/1024)",
+                   c->d_model, c->vocab, c->ffn);
+    return SC_ERR_ARG;
+  }
+  if (c->beam < 1 || c->beam > 20) { set_last_error("beam %d out of range [1, 20]", c->beam); return SC_ERR_ARG; }
+  if (c->n_streams < 1 || c->max_chunk < 1 || c->max_frames < 32) { set_last_error("bad capacities"); return SC_ERR_ARG; }
+  int dk_e = c->d_model / c->enc_heads, dk_d = c->d_model / c->dec_heads;
+  if ((dk_e != 32 && dk_e != 64) || (dk_d != 32 && dk_d != 64)) { set_last_error("head dim must be 32 or 64"); return SC_ERR_ARG; }
+  return SC_OK;
+}
+
+int sc_engine_workspace_bytes(const ScConfig* cfg, size_t* bytes) {
+  int r = check_cfg(cfg); if (r) return r;
+  Engine e(*cfg);
+  Carver cv(nullptr, true);
+  carve(e, cv);
+  *bytes = align_up(cv.off) + 256;
+  return SC_OK;
+}
+
+int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** handle) {
+  int r = check_cfg(cfg); if (r) return r;
+  size_t need = 0; sc_engine_workspace_bytes(cfg, &need);
+  if (!workspace || bytes < need || ((uintptr_t)workspace & 255)) {
+    set_last_error("workspace too small or misaligned: have %zu need %zu", bytes, need);
+    return SC_ERR_ARG;
+  }
+  Engine* e = new Engine(*cfg);
+  Carver cv(workspace, false);
+  carve(*e, cv);
+  const Caps& k = e->cap;
+  const size_t S = cfg->n_streams;
+  e->h_stage_bytes = sizeof(FrontendDesc) * S + sizeof(SubDesc) * S + sizeof(BlockDesc) * k.nb_max + sizeof(int) * (6 * S) +
+                     (sizeof(int64_t) * 3 + sizeof(int)) * S * k.sub_cap + sizeof(int) * (2 * S + 2 * S * k.qcap) + sizeof(int) * S + 4096;
+  if (cudaMallocHost(&e->h_stage, e->h_stage_bytes) != cudaSuccess || cudaMallocHost(&e->h_flag, 2 * sizeof(int)) != cudaSuccess) {
+    set_last_error("pinned host allocation failed"); delete e; return SC_ERR_CUDA;
+  }
+  cudaEventCreateWithFlags(&e->ev[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev[1], cudaEventDisableTiming);
+  e->enc.resize(cfg->enc_layers); e->dec.resize(cfg->dec_layers);
+  *handle = e;
+  return SC_OK;
+}
+
+int sc_engine_destroy(void* handle) {
+  Engine* e = (Engine*)handle;
+  if (!e) return SC_OK;
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->h_flag) cudaFreeHost(e->h_flag);
+  cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
+  delete e;
+  return SC_OK;
+}
+
+int sc_engine_set_weight(void* handle, const char* name, const void* dev_ptr, size_t /*n_elem*/) {
+  Engine* e = (Engine*)handle;
+  if (!e || !name || !dev_ptr) { set_last_error("set_weight: null argument"); return SC_ERR_ARG; }
+  e->wmap[name] = dev_ptr;
+  return SC_OK;
+}
+
+int sc_engine_set_frontend(void* handle, const float* window400, const float* mel_fb, const double* mean, const double* std_) {
+  Engine* e = (Engine*)handle;
+  if (!e || !window400 || !mel_fb) { set_last_error("set_frontend: null argument"); return SC_ERR_ARG; }
+  if (frontend_upload_tables(window400, mel_fb)) return SC_ERR_CUDA;
+  e->has_stats = mean && std_;
+  if (e->has_stats) {
+    SCB_CUDA_CHECK(cudaMemcpy(e->d_mean, mean, 80 * sizeof(double), cudaMemcpyHostToDevice));
+    SCB_CUDA_CHECK(cudaMemcpy(e->d_std, std_, 80 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return SC_OK;
+}
+
+int sc_engine_finalize(void* handle) {
+  Engine* e = (Engine*)handle;
+  if (!e) return SC_ERR_ARG;
+  std::string missing;
+  const bool tc = e->cfg.precision == 1;
+  auto getf = [&](const std::string& n) -> const float* {
+    auto it = e->wmap.find(n);
+    if (it == e->wmap.end()) { missing += n + " "; return nullptr; }
+    return (const float*)it->second;
+  };
+  auto geth = [&](const std::string& n) -> const __nv_bfloat16* {
+    if (!tc) return nullptr;
+    auto it = e->wmap.find(n + ".bf16");
+    if (it == e->wmap.end()) { missing += n + ".bf16 "; return nullptr; }
+    return (const __nv_bfloat16*)it->second;
+  };
+  e->pe = getf("pe");
+  e->c1w = getf("enc.conv1.w"); e->c1b = getf("enc.conv1.b");
+  e->c2w = getf("enc.conv2.w"); e->c2b = getf("enc.conv2.b");
+  e->eow = getf("enc.out.w"); e->eob = getf("enc.out.b");
+  e->eaw = getf("enc.after.w"); e->eab = getf("enc.after.b");
+  e->ctcw = getf("ctc.w"); e->ctcb = getf("ctc.b");
+  e->demb = getf("dec.emb"); e->daw = getf("dec.after.w"); e->dab = getf("dec.after.b");
+  e->doutw = getf("dec.out.w"); e->doutb = getf("dec.out.b");
+  e->eow16 = geth("enc.out.w"); e->ctcw16 = geth("ctc.w"); e->doutw16 = geth("dec.out.w");
+  for (int l = 0; l < e->cfg.enc_layers; ++l) {
+    std::string p = "enc." + std::to_string(l) + ".";
+    EncLayerW& w = e->enc[l];
+    w.ln1w = getf(p + "ln1.w"); w.ln1b = getf(p + "ln1.b"); w.qkvw = getf(p + "qkv.w"); w.qkvb = getf(p + "qkv.b");
+    w.ow = getf(p + "o.w"); w.ob = getf(p + "o.b"); w.ln2w = getf(p + "ln2.w"); w.ln2b = getf(p + "ln2.b");
+    w.f1w = getf(p + "ff1.w"); w.f1b = getf(p + "ff1.b"); w.f2w = getf(p + "ff2.w"); w.f2b = getf(p + "ff2.b");
+    w.qkvw16 = geth(p + "qkv.w"); w.ow16 = geth(p + "o.w"); w.f1w16 = geth(p + "ff1.w"); w.f2w16 = geth(p + "ff2.w");
+  }
+  for (int l = 0; l < e->cfg.dec_layers; ++l) {
+    std::string p = "dec." + std::to_string(l) + ".";
+    DecLayerW& w = e->dec[l];
+    w.ln1w = getf(p + "ln1.w"); w.ln1b = getf(p + "ln1.b"); w.sqkvw = getf(p + "self_qkv.w"); w.sqkvb = getf(p + "self_qkv.b");
+    w.sow = getf(p + "self_o.w"); w.sob = getf(p + "self_o.b"); w.ln2w = getf(p + "ln2.w"); w.ln2b = getf(p + "ln2.b");
+    w.cqw = getf(p + "src_q.w"); w.cqb = getf(p + "src_q.b"); w.ckvw = getf(p + "src_kv.w"); w.ckvb = getf(p + "src_kv.b");
+    w.cow = getf(p + "src_o.w"); w.cob = getf(p + "src_o.b"); w.ln3w = getf(p + "ln3.w"); w.ln3b = getf(p + "ln3.b");
+    w.f1w = getf(p + "ff1.w"); w.f1b = getf(p + "ff1.b"); w.f2w = getf(p + "ff2.w"); w.f2b = getf(p + "ff2.b");
+    w.sqkvw16 = geth(p + "self_qkv.w"); w.sow16 = geth(p + "self_o.w"); w.cqw16 = geth(p + "src_q.w");
+    w.ckvw16 = geth(p + "src_kv.w"); w.cow16 = geth(p + "src_o.w"); w.f1w16 = geth(p + "ff1.w"); w.f2w16 = geth(p + "ff2.w");
+  }
+  if (!missing.empty()) { set_last_error("missing weights: %.400s", missing.c_str()); return SC_ERR_STATE; }
+  // conv2 implicit-GEMM segment offsets: K = (kt, kf, c) -> ((kt * 39) + kf) * D
+  int seg[9];
+  for (int kt = 0; kt < 3; ++kt) for (int kf = 0; kf < 3; ++kf) seg[kt * 3 + kf] = (kt * 39 + kf) * e->cfg.d_model;
+  SCB_CUDA_CHECK(cudaMemcpy(e->d_c2_seg, seg, sizeof(seg), cudaMemcpyHostToDevice));
+  // all streams start reset
+  std::vector<int> all(e->cfg.n_streams);
+  for (int i = 0; i < e->cfg.n_streams; ++i) all[i] = i;
+  SCB_CUDA_CHECK(cudaMemcpy(e->d_reset, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (launch_search_reset(e->sb, e->d_reset, e->cfg.n_streams, 0)) return SC_ERR_CUDA;
+  SCB_CUDA_CHECK(cudaDeviceSynchronize());
+  e->finalized = true;
+  return SC_OK;
+}
+
+int sc_engine_reset(void* handle, const int32_t* streams, int32_t n, void* stream) {
+  Engine* e = (Engine*)handle;
+  if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n; ++i) {
+    if (streams[i] < 0 || streams[i] >= e->cfg.n_streams) { set_last_error("bad stream id %d", streams[i]); return SC_ERR_ARG; }
+    e->planner.reset(streams[i]);
+  }
+  int* hs = (int*)e->h_stage;
+  memcpy(hs, streams, n * sizeof(int));
+  SCB_CUDA_CHECK(cudaMemcpyAsync(e->d_reset, hs, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (launch_search_reset(e->sb, e->d_reset, n, st)) return SC_ERR_CUDA;
+  SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SC_OK;
+}
+
+int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const int32_t* streams,
+                   const int32_t* n_samples, const int32_t* is_final, int32_t n, void* stream, ScPushStats* stats) {
+  Engine* e = (Engine*)handle;
+  if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
+  const ScConfig& c = e->cfg; const Caps& k = e->cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = c.n_streams, D = c.d_model, V = c.vocab;
+  e->launches = 0;
+  if (n < 0 || n > S) { set_last_error("push: n=%d out of range", n); return SC_ERR_ARG; }
+  // ---------------- plan on the host
+  std::vector<StreamPush> plans(n);
+  for (int i = 0; i < n; ++i) {
+    const int s = streams[i];
+    if (s < 0 || s >= S) { set_last_error("bad stream id %d", s); return SC_ERR_ARG; }
+    if (n_samples[i] < 0 || n_samples[i] > c.max_chunk) {
+      set_last_error("stream %d: chunk of %d samples exceeds max_chunk %d", s, n_samples[i], c.max_chunk);
+      return SC_ERR_CAPACITY;
+    }
+    if (n_samples[i] > ld_wave) { set_last_error("ld_wave too small"); return SC_ERR_ARG; }
+    const StreamHost before = e->planner.state(s);
+    plans[i] = e->planner.push(s, n_samples[i], is_final[i] != 0);
+    StreamPush& p = plans[i];
+    if (p.error) {
+      set_last_error("stream %d: input shape the reference cannot process (code %d)", s, p.error);
+      return SC_ERR_STATE;
+    }
+    if (e->planner.state(s).enc_len > k.Tcap) {
+      set_last_error("stream %d: encoder buffer overflow (%d > max_frames %d)", s, e->planner.state(s).enc_len, k.Tcap);
+      return SC_ERR_CAPACITY;
+    }
+    ScStreamPlan& lp = e->last_plan[s];
+    lp.called = p.called; lp.n_feat = p.n_feat; lp.n_sub = p.run_sub ? p.sd.t2 : 0; lp.n_blocks = (int)p.blocks.size();
+    lp.n_enc_out = p.n_enc_out; lp.enc_len = e->planner.state(s).enc_len; lp.n_decode_blocks = (int)p.dq_T.size();
+    lp.last_T = p.dq_T.empty() ? 0 : p.dq_T.back();
+    (void)before;
+  }
+  // ---------------- flatten into pinned staging
+  unsigned char* hp = e->h_stage;
+  auto stage = [&](size_t bytes) { unsigned char* r = hp; hp += align_up(bytes, 16); return r; };
+  FrontendDesc* h_fd = (FrontendDesc*)stage(sizeof(FrontendDesc) * S);
+  SubDesc* h_sd = (SubDesc*)stage(sizeof(SubDesc) * S);
+  BlockDesc* h_blk = (BlockDesc*)stage(sizeof(BlockDesc) * k.nb_max);
+  int* h_cf = (int*)stage(sizeof(int) * 3 * S);
+  int* h_cs = (int*)stage(sizeof(int) * 3 * S);
+  int64_t* h_en_a = (int64_t*)stage(sizeof(int64_t) * S * k.sub_cap);
+  int64_t* h_en_ctc = (int64_t*)stage(sizeof(int64_t) * S * k.sub_cap);
+  int64_t* h_en_kv = (int64_t*)stage(sizeof(int64_t) * S * k.sub_cap);
+  int* h_en_flag = (int*)stage(sizeof(int) * S * k.sub_cap);
+  int* h_q = (int*)stage(sizeof(int) * (2 * S + 2 * S * k.qcap));
+  int n_fd = 0, n_fd_all = 0, n_sd = 0, n_blk = 0, n_cf = 0, n_cs = 0, n_en = 0, n_q = 0, frame_base = 0, sub_rows = 0;
+  int n_feat_total = 0;
+  // frontend descriptors: emitting ones first (frame_base indexing), buffer-only ones after
+  std::vector<FrontendDesc> buf_only;
+  for (int i = 0; i < n; ++i) {
+    StreamPush& p = plans[i];
+    if (!p.has_fd) continue;
+    if (p.fd.emit1 > p.fd.emit0) { p.fd.frame_base = frame_base; frame_base += p.fd.n_frames; h_fd[n_fd++] = p.fd; n_feat_total += p.n_feat; }
+    else buf_only.push_back(p.fd);
+  }
+  n_fd_all = n_fd;
+  for (auto& f : buf_only) { f.frame_base = frame_base; h_fd[n_fd_all++] = f; }
+  for (int i = 0; i < n; ++i) {
+    StreamPush& p = plans[i];
+    const int s = streams[i];
+    if (p.run_sub) {
+      p.sd.row0 = sub_rows; sub_rows += p.sd.t2;
+      h_sd[n_sd++] = p.sd;
+    }
+    if (p.feat_carry_move) { h_cf[n_cf] = s; h_cf[S + n_cf] = p.sd.carry_src; h_cf[2 * S + n_cf] = p.sd.carry_n; n_cf++; }
+    if (p.sub_carry_move) { h_cs[n_cs] = s; h_cs[S + n_cs] = p.sub_carry_src; h_cs[2 * S + n_cs] = p.sub_carry_n; n_cs++; }
+    const int blk0 = n_blk;
+    for (auto b : p.blocks) {
+      if ((int)n_blk >= k.nb_max) { set_last_error("block capacity exceeded"); return SC_ERR_CAPACITY; }
+      if (b.prev_blk >= 0) b.prev_blk += blk0;
+      h_blk[n_blk++] = b;
+    }
+    for (int t = 0; t < p.n_enc_out; ++t) {
+      const int tt = p.enc_t0 + t;
+      h_en_a[n_en] = ((int64_t)s * k.Tcap + tt) * D;
+      h_en_ctc[n_en] = ((int64_t)s * k.Tcap + tt) * V;
+      h_en_kv[n_en] = ((int64_t)s * k.Tcap + tt) * 2 * D;
+      h_en_flag[n_en] = tt < (kBlock - kLook) ? 1 : 0;      // rows of the first decode block are log-softmaxed (Q1)
+      n_en++;
+    }
+    if (!p.dq_T.empty()) {
+      if ((int)p.dq_T.size() > k.qcap) { set_last_error("decode queue capacity exceeded"); return SC_ERR_CAPACITY; }
+      h_q[n_q] = s; h_q[S + n_q] = (int)p.dq_T.size();
+      for (size_t j = 0; j < p.dq_T.size(); ++j) {
+        h_q[2 * S + n_q * k.qcap + j] = p.dq_T[j];
+        h_q[2 * S + S * k.qcap + n_q * k.qcap + j] = p.dq_final[j];
+      }
+      n_q++;
+    }
+  }
+  // ---------------- upload descriptors
+  auto up = [&](void* dst, const void* src, size_t bytes) -> int {
+    if (bytes == 0) return 0;
+    SCB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  };
+  TRY(up(e->d_fd, h_fd, sizeof(FrontendDesc) * n_fd_all));
+  TRY(up(e->d_sd, h_sd, sizeof(SubDesc) * n_sd));
+  TRY(up(e->d_blk, h_blk, sizeof(BlockDesc) * n_blk));
+  if (n_cf) TRY(up(e->d_carry_f, h_cf, sizeof(int) * 3 * S));
+  if (n_cs) TRY(up(e->d_carry_s, h_cs, sizeof(int) * 3 * S));
+  TRY(up(e->d_en_a, h_en_a, sizeof(int64_t) * n_en));
+  TRY(up(e->d_en_ctc, h_en_ctc, sizeof(int64_t) * n_en));
+  TRY(up(e->d_en_kv, h_en_kv, sizeof(int64_t) * n_en));
+  TRY(up(e->d_en_flag, h_en_flag, sizeof(int) * n_en));
+  if (n_q) TRY(up(e->d_q, h_q, sizeof(int) * (2 * S + 2 * S * k.qcap)));
+  // ---------------- frontend
+  TRY(launch_frontend(wave_dev, ld_wave, e->wbuf, 512, e->d_fd, n_fd, frame_base, e->has_stats ? e->d_mean : nullptr,
+                      e->has_stats ? e->d_std : nullptr, e->featbuf, k.feat_cap, st));
+  TRY(launch_wavebuf_update(wave_dev, ld_wave, e->wbuf, 512, e->d_fd, n_fd_all, st));
+  e->launches += 2;
+  // ---------------- conv2d sub-sampling
+  const bool tc = c.precision == 1;
+  if (n_sd > 0) {
+    TRY(launch_conv1(e->featbuf, k.feat_cap, e->c1w, e->c1b, e->h1, k.t1_cap, e->d_sd, n_sd, D, st));
+    TRY(launch_conv2_rows(e->d_sd, n_sd, k.t1_cap, k.sub_cap, D, e->d_c2_a, e->d_c2_c, st));
+    GemmArgs g;
+    g.A = e->h1; g.a_row_off = e->d_c2_a; g.a_seg_off = e->d_c2_seg; g.seg_len = D; g.W = e->c2w; g.bias = e->c2b;
+    g.C = e->h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
+    TRY(launch_gemm_f32(g, st));
+    GemmArgs o;
+    o.A = e->h2; o.lda = 19 * D; o.W = e->eow; o.bias = e->eob; o.C = e->subbuf; o.c_row_off = e->d_c2_c;
+    o.M = sub_rows; o.N = D; o.K = 19 * D;
+    TRY(launch_gemm_f32(o, st));
+    e->launches += 4;
+  }
+  if (n_cf) { TRY(launch_carry_rows(e->featbuf, k.feat_cap, 80, e->d_carry_f, e->d_carry_f + S, e->d_carry_f + 2 * S, n_cf, st)); e->launches++; }
+  // ---------------- encoder blocks
+  if (n_blk > 0) {
+    TRY(launch_block_assemble(e->subbuf, k.sub_cap, e->pe, e->d_blk, n_blk, e->addin, e->prev_addin, e->X, D, st));
+    TRY(run_encoder_layers(*e, n_blk, st));
+    TRY(launch_stitch_norm(e->X, e->d_blk, n_blk, e->eaw, e->eab, e->encbuf, k.Tcap, D, st));
+    e->launches += 4;
+  }
+  if (n_cs) { TRY(launch_carry_rows(e->subbuf, k.sub_cap, D, e->d_carry_s, e->d_carry_s + S, e->d_carry_s + 2 * S, n_cs, st)); e->launches++; }
+  // ---------------- CTC head + cross-attention K|V for the new encoder frames
+  if (n_en > 0) {
+    GemmArgs g;
+    g.A = e->encbuf; g.a_row_off = e->d_en_a; g.W = e->ctcw; g.bias = e->ctcb; g.C = e->ctcx; g.c_row_off = e->d_en_ctc;
+    g.M = n_en; g.N = V; g.K = D;
+    TRY(launch_gemm_f32(g, st));
+    TRY(launch_logsoftmax_rows(e->ctcx, e->d_en_ctc, e->d_en_flag, n_en, V, st));
+    for (int l = 0; l < c.dec_layers; ++l) {
+      GemmArgs kv;
+      kv.A = e->encbuf; kv.a_row_off = e->d_en_a; kv.W = e->dec[l].ckvw; kv.bias = e->dec[l].ckvb;
+      kv.C = e->sb.xkv + (size_t)l * S * k.Tcap * 2 * D; kv.c_row_off = e->d_en_kv; kv.M = n_en; kv.N = 2 * D; kv.K = D;
+      TRY(launch_gemm_f32(kv, st));
+    }
+    e->launches += 2 + c.dec_layers;
+  }
+  (void)tc;
+  // ---------------- block-synchronous beam search
+  int steps = 0;
+  TRY(launch_search_begin(e->sb, e->d_q, e->d_q + S, e->d_q + 2 * S, e->d_q + 2 * S + S * k.qcap, n_q, st));
+  e->launches += 2;
+  SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[0], e->sb.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaEventRecord(e->ev[0], st));
+  if (n_q == 0) {
+    SCB_CUDA_CHECK(cudaEventSynchronize(e->ev[0]));
+  } else {
+    // one step is always in flight ahead of the host's view of n_active (kernels of an empty step exit at once)
+    for (int i = 0;; ++i) {
+      TRY(run_decode_step(*e, st));
+      steps++;
+      SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[(i + 1) & 1], e->sb.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SCB_CUDA_CHECK(cudaEventRecord(e->ev[(i + 1) & 1], st));
+      SCB_CUDA_CHECK(cudaEventSynchronize(e->ev[i & 1]));
+      if (e->h_flag[i & 1] == 0) break;
+      if (steps > 4 * kMaxLength + 64) { set_last_error("decode loop did not terminate"); return SC_ERR_STATE; }
+    }
+    SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_feature_frames = n_feat_total; stats->n_encoder_blocks = n_blk; stats->n_encoder_frames = n_en;
+    stats->n_decode_steps = steps; stats->n_kernel_launches = e->launches;
+  }
+  return SC_OK;
+}
+
+int sc_engine_read_beam(void* handle, int32_t s, int32_t max_len, int32_t* n_hyp, int32_t* len, int32_t* process_idx,
+                        int32_t* yseq, int32_t* xpos, double* score, void* stream) {
+  Engine* e = (Engine*)handle;
+  if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
+  if (s < 0 || s >= e->cfg.n_streams) { set_last_error("bad stream id %d", s); return SC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const SearchBuffers& sb = e->sb;
+  StreamCtl ctl;
+  SCB_CUDA_CHECK(cudaMemcpyAsync(&ctl, sb.ctl + s, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+  *n_hyp = ctl.n_hyp; *len = ctl.len; *process_idx = ctl.process_idx;
+  if (ctl.len > max_len) { set_last_error("read_beam: max_len %d < len %d", max_len, ctl.len); return SC_ERR_ARG; }
+  for (int h = 0; h < ctl.n_hyp; ++h) {
+    const size_t o = (((size_t)ctl.cur * sb.S + s) * sb.B + h);
+    SCB_CUDA_CHECK(cudaMemcpyAsync(yseq + (size_t)h * max_len, sb.yseq + o * sb.Lcap, ctl.len * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCB_CUDA_CHECK(cudaMemcpyAsync(xpos + (size_t)h * max_len, sb.xpos + o * sb.Lcap, ctl.len * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  SCB_CUDA_CHECK(cudaMemcpyAsync(score, sb.score + (((size_t)ctl.cur * sb.S + s) * sb.B), ctl.n_hyp * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SC_OK;
+}
+
+int sc_engine_last_plan(void* handle, int32_t s, ScStreamPlan* plan) {
+  Engine* e = (Engine*)handle;
+  if (!e || s < 0 || s >= e->cfg.n_streams || !plan) { set_last_error("last_plan: bad argument"); return SC_ERR_ARG; }
+  *plan = e->last_plan[s];
+  return SC_OK;
+}
+
+int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem) {
+  Engine* e = (Engine*)handle;
+  if (!e || !name) return SC_ERR_ARG;
+  auto it = e->named.find(name);
+  if (it == e->named.end()) { set_last_error("unknown buffer %s", name); return SC_ERR_ARG; }
+  *ptr = it->second.first; *n_elem = it->second.second;
+  return SC_OK;
+}
+
+// ---------------- host-only planner
+int sc_planner_create(int32_t n_streams, void** planner) {
+  if (n_streams < 1 || !planner) return SC_ERR_ARG;
+  *planner = new Planner(n_streams);
+  return SC_OK;
+}
+int sc_planner_destroy(void* planner) { delete (Planner*)planner; return SC_OK; }
+int sc_planner_reset(void* planner, int32_t s) { ((Planner*)planner)->reset(s); return SC_OK; }
+int sc_planner_push(void* planner, int32_t s, int32_t n_samples, int32_t is_final, ScStreamPlan* plan) {
+  Planner* p = (Planner*)planner;
+  StreamPush r = p->push(s, n_samples, is_final != 0);
+  if (r.error) { set_last_error("planner: unsupported shape (code %d)", r.error); return SC_ERR_STATE; }
+  plan->called = r.called; plan->n_feat = r.n_feat; plan->n_sub = r.run_sub ? r.sd.t2 : 0; plan->n_blocks = (int)r.blocks.size();
+  plan->n_enc_out = r.n_enc_out; plan->enc_len = p->state(s).enc_len; plan->n_decode_blocks = (int)r.dq_T.size();
+  plan->last_T = r.dq_T.empty() ? 0 : r.dq_T.back();
+  return SC_OK;
+}
+
+// ---------------- single operators
+int sc_layernorm_f32(const float* x, const float* w, const float* b, float* y, int32_t rows, int32_t d, void* stream) {
+  return launch_layernorm(x, d, w, b, y, d, rows, d, nullptr, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+int sc_linear_f32(const float* x, const float* w, const float* bias, const float* residual, float* y, int32_t m, int32_t n,
+                  int32_t k, int32_t relu, void* stream) {
+  GemmArgs g;
+  g.A = x; g.lda = k; g.W = w; g.bias = bias; g.R = residual; g.ldr = n; g.C = y; g.ldc = n; g.M = m; g.N = n; g.K = k; g.relu = relu;
+  return launch_gemm_f32(g, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+int sc_linear_bf16(const void* x, const void* w, const float* bias, const float* residual, float* y, void* y16, int32_t m,
+                   int32_t n, int32_t k, int32_t relu, void* stream) {
+  return launch_gemm_bf16((const __nv_bfloat16*)x, k, (const __nv_bfloat16*)w, bias, residual, n, y, n, (__nv_bfloat16*)y16, n,
+                          m, n, k, relu, nullptr, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+// Launcher declarations for every CUDA kernel of the streaming decode path.
+// All launchers return 0 on success, -1 on failure (message via scb::get_last_error()).
+#pragma once
+#include "common.cuh"
+
+namespace scb {
+
+// ---------------------------------------------------------------- descriptors
+// One entry per stream that receives samples in this push (frontend plan).
+struct FrontendDesc {
+  int stream;      // stream slot
+  int n_prev;      // samples already buffered
+  int n_new;       // samples in this chunk
+  int slab;        // samples framed this call (>= n_prev + n_new only when zero padded)
+  int n_frames;    // STFT frames of the slab (1 + slab / 160)
+  int emit0;       // first emitted frame
+  int emit1;       // one past the last emitted frame
+  int feat_off;    // row in featbuf[stream] where the first emitted frame goes
+  int new_buf;     // samples kept for the next call (0 when final)
+  int frame_base;  // prefix sum of n_frames over descriptors (for flat frame indexing)
+};
+
+// One entry per encoder block formed in this push.
+struct BlockDesc {
+  int stream;
+  int sub_start;     // first sub-sampled frame of the block inside subbuf[stream]
+  int clen;          // frames present (40 except the last block of a final call)
+  int pe_frame_off;  // positional offset of the block's first frame
+  int pe_ctx_off;    // positional offset of its context vector
+  int prev_blk;      // previous block of the same stream in this push, or -1
+  int has_prev_addin;  // prev_blk < 0: 1 -> use the stream's stored prev_addin, 0 -> own addin
+  int is_last;       // last block of this stream in this push
+  int out_slot0;     // first slot emitted to the encoder buffer
+  int out_count;     // number of slots emitted
+  int out_t0;        // destination frame index in encbuf[stream]
+  int n_rows;        // rows that take part in attention: 42, or T for the short path
+  int short_path;    // 1: no mask, no context slots
+  int has_past_ctx;  // stream carries past_encoder_ctx from an earlier call
+};
+
+// ---------------------------------------------------------------- elementwise
+// y = LayerNorm(x) (eps 1e-12) over rows of width D (D % 32 == 0, D <= 512).
+int launch_layernorm(const float* x, int ldx, const float* w, const float* b, float* y, int ldy,
+                     int rows, int D, const int* n_rows_dev, cudaStream_t st);
+int launch_layernorm_bf16(const float* x, int ldx, const float* w, const float* b, __nv_bfloat16* y,
+                          int ldy, int rows, int D, const int* n_rows_dev, cudaStream_t st);
+
+// ---------------------------------------------------------------- GEMM (fp32 SIMT)
+struct GemmArgs {
+  const float* A = nullptr;       // [M][lda] unless a_row_off is given
+  int lda = 0;
+  const int64_t* a_row_off = nullptr;  // element offset of row m (gather-A)
+  const int* a_seg_off = nullptr;      // element offset added per K segment (implicit-GEMM conv)
+  int seg_len = 0;                     // K segment length (multiple of 16) when a_seg_off != null
+  const float* W = nullptr;       // [N][K] row-major (torch Linear layout)
+  const float* bias = nullptr;    // [N] or null
+  const float* R = nullptr;       // residual [M][ldr] or null (may alias C)
+  int ldr = 0;
+  float* C = nullptr;             // [M][ldc] unless c_row_off is given
+  int ldc = 0;
+  const int64_t* c_row_off = nullptr;  // element offset of output row m
+  int M = 0, N = 0, K = 0;
+  int relu = 0;
+  const int* n_rows_dev = nullptr;     // optional dynamic M (device scalar)
+};
+int launch_gemm_f32(const GemmArgs& g, cudaStream_t st);
+
+// ---------------------------------------------------------------- frontend
+int frontend_upload_tables(const float* window400, const float* mel_fb_257x80);
+int launch_frontend(const float* wave_in, int ld_wave, const float* wbuf, int ld_wbuf, const FrontendDesc* desc,
+                    int n_desc, int total_frames, const double* mean, const double* std_, float* featbuf,
+                    int feat_cap, cudaStream_t st);
+int launch_wavebuf_update(const float* wave_in, int ld_wave, float* wbuf, int ld_wbuf,
+                          const FrontendDesc* desc, int n_desc, cudaStream_t st);
+
+// ---------------------------------------------------------------- encoder
+struct SubDesc {       // one per stream that runs conv2d subsampling in this push
+  int stream;
+  int t_in;            // feature frames convolved (from featbuf[stream][0 : t_in])
+  int t1;              // conv1 output frames
+  int t2;              // conv2 output frames (= new sub-sampled frames)
+  int row0;            // prefix sum of t2 (dense row of the first new frame)
+  int sub_off;         // destination row in subbuf[stream]
+  int carry_src;       // featbuf row where the carried frames start
+  int carry_n;         // frames carried to the next call
+};
+int launch_conv1(const float* featbuf, int feat_cap, const float* w1, const float* b1, float* h1, int t1_cap,
+                 const SubDesc* desc, int n_desc, int D, cudaStream_t st);
+int launch_conv2_rows(const SubDesc* desc, int n_desc, int t1_cap, int sub_cap, int D, int64_t* a_row_off,
+                      int64_t* c_row_off, cudaStream_t st);
+// move rows [src, src+n) of buf[stream] (row width `width`, `cap` rows per stream) to the front
+int launch_carry_rows(float* buf, int cap, int width, const int* stream, const int* src, const int* n,
+                      int n_desc, cudaStream_t st);
+int launch_block_assemble(const float* subbuf, int sub_cap, const float* pe, const BlockDesc* blk, int n_blk,
+                          float* addin, float* prev_addin, float* X, int D, cudaStream_t st);
+int launch_enc_attention(const float* qkv, float* out, const BlockDesc* blk, int n_blk, int n_head, int d_model,
+                         cudaStream_t st);
+int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const BlockDesc* blk, int n_blk,
+                        int D, cudaStream_t st);
+int launch_stitch_norm(const float* X, const BlockDesc* blk, int n_blk, const float* w, const float* b,
+                       float* encbuf, int t_cap, int D, cudaStream_t st);
+
+// ---------------------------------------------------------------- decoder / search
+struct StreamCtl {     // per-stream search state that lives on the device
+  int cur;             // beam buffer (0/1) holding the current hypotheses
+  int n_hyp;           // hypotheses in the current beam (1 before the first step, then B)
+  int len;             // tokens per hypothesis (all equal: block-synchronous)
+  int process_idx;     // global step counter (beam_search.py:326)
+  int has_ctc;         // hypotheses carry a CTC forward state
+  int ctc_T;           // rows of that state
+  int active;          // still iterating in the current block
+  int Tb;              // memory length of the current block
+  int is_final;        // current block is the final one
+  int iters_done;      // iterations completed in the current block
+  int blk_next;        // next entry of the per-push decode-block queue (SearchBuffers::blkq_*)
+  int blk_count;       // entries in the queue
+  int outcome;         // decision of the current iteration (set by beam_prune, applied by step_commit)
+  int steps_total;     // statistics: iterations executed for this stream
+  int pad_[2];
+};
+
+struct SearchBuffers {
+  // configuration
+  int S, B, V, D, H, Ld, Tcap, Lcap, use_bbd;
+  float w_dec, w_ctc;
+  // model memory
+  const float* ctcx;      // [S][Tcap][V]
+  float* xkv;             // [Ld][S][Tcap][2D]  cross-attention K|V
+  float* skv;             // [Ld][S][Lcap][B][2D] self-attention K|V (tree storage)
+  // beam (ping-pong)
+  int* yseq;              // [2][S][B][Lcap]
+  int* xpos;              // [2][S][B][Lcap]
+  unsigned char* anc;     // [2][S][B][Lcap] slot of the ancestor at each position
+  double* score;          // [2][S][B]
+  double* sc_dec;         // [2][S][B]
+  double* sc_ctc;         // [2][S][B]
+  float* ctc_r;           // [2][S][B][Tcap][2]
+  float* ctc_s;           // [2][S][B]
+  StreamCtl* ctl;         // [S]
+  int* blkq_T;            // [S][qcap] memory length of each queued decode block
+  int* blkq_final;        // [S][qcap] 1 for the final block
+  int qcap;
+  // per-step scratch (compact rows)
+  int* row_sh;            // [S*B] compact row -> s*B+h
+  int* row_base;          // [S] first compact row of the stream, -1 if inactive
+  int* act_streams;       // [S] compact list of active streams
+  int* n_rows;            // device scalar: active rows
+  int* n_active;          // device scalar: active streams
+  float* logp;            // [S*B][V] decoder log-probs
+  int* pre_ids;           // [S*B][40]
+  float* psi;             // [S*B][40]
+  float* psi_eos;         // [S*B]
+  float* cand_val;        // [S*B][B]
+  int* cand_tok;          // [S*B][B]
+  float* cand_dec;        // [S*B][B] unweighted decoder score of the candidate
+  float* cand_ctc;        // [S*B][B] unweighted ctc score of the candidate
+  float* cand_psi;        // [S*B][B] log_psi of the candidate (new CTC prefix score)
+  int* cand_col;          // [S*B][B] token whose forward column is inherited (select_state)
+  int* new_parent;        // [S][B] parent slot of each new hypothesis (this step)
+  int* new_col;           // [S][B]
+  int* upd_flag;          // [S] 1 -> the CTC state of the new beam must be written this step
+};
+
+int launch_search_reset(const SearchBuffers& sb, const int* streams, int n, cudaStream_t st);
+// q_T / q_final: [n_q][qcap]
+int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int* q_n, const int* q_T,
+                        const int* q_final, int n_q, cudaStream_t st);
+int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, cudaStream_t st);
+// mode 0: self attention over the tree KV store (appends this step's K|V first); mode 1: cross attention
+int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
+                         const float* kv_new, int ldkv, float* out, cudaStream_t st);
+int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st);
+int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st);
+int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st);
+int launch_beam_prune(const SearchBuffers& sb, cudaStream_t st);
+int launch_ctc_state_update(const SearchBuffers& sb, cudaStream_t st);
+int launch_step_finish(const SearchBuffers& sb, cudaStream_t st);
+// in-place log-softmax of the rows x + row_off[r] whose row_flag[r] != 0
+int launch_logsoftmax_rows(float* x, const int64_t* row_off, const int* row_flag, int rows, int V, cudaStream_t st);
+
+}  // namespace scb

@@ -1,0 +1,737 @@
+// Block-synchronous beam search on the device: decoder-step attention over a tree-structured self-KV
+// store and a per-stream cross-KV cache, log-softmax + pre-beam top-40, the batched CTC prefix scorer,
+// score combination + per-hypothesis top-k, global pruning and all hypothesis / endpoint bookkeeping
+// (EOS stop, BBD rollback, rewind, global step cap, per-push block queue).
+//
+// Replaces: speechcatcher/beam_search/beam_search.py:71-185, 403-505, 655-838
+//           speechcatcher/beam_search/ctc_prefix_score_full.py:88-368
+//           speechcatcher/beam_search/scorers.py:238-431
+//           speechcatcher/beam_search/hypothesis.py:132-168
+//           speechcatcher/model/decoder/transformer_decoder.py:210-251 (attention part)
+#include "kernels.h"
+
+namespace scb {
+
+enum { OUT_CONTINUE = 0, OUT_BREAK_NEW = 1, OUT_BREAK_OLD = 2 };
+
+// ---------------------------------------------------------------- indexing helpers
+__device__ __forceinline__ size_t beam_off(const SearchBuffers& sb, int buf, int s, int h) {
+  return (((size_t)buf * sb.S + s) * sb.B + h);
+}
+
+// ---------------------------------------------------------------- reset
+__global__ void search_reset_kernel(SearchBuffers sb, const int* __restrict__ streams, int n) {
+  int i = blockIdx.x;
+  if (i >= n) return;
+  int s = streams[i];
+  if (threadIdx.x == 0) {
+    StreamCtl c;
+    memset(&c, 0, sizeof(c));
+    c.cur = 0; c.n_hyp = 1; c.len = 1;
+    sb.ctl[s] = c;
+    size_t o = beam_off(sb, 0, s, 0);
+    sb.yseq[o * sb.Lcap] = sb.V - 1;          // [sos]
+    sb.xpos[o * sb.Lcap] = 0;
+    sb.score[o] = 0.0; sb.sc_dec[o] = 0.0; sb.sc_ctc[o] = 0.0;
+    sb.ctc_s[o] = 0.f;
+  }
+}
+
+int launch_search_reset(const SearchBuffers& sb, const int* streams, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  search_reset_kernel<<<n, 32, 0, st>>>(sb, streams, n);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- block start / end (device functions)
+// extend_state (ctc_prefix_score_full.py:326-368) for every hypothesis of the current beam, or the
+// initial state r^b = cumsum(blank) for the start hypothesis (ctc_prefix_score_full.py:121-134).
+__device__ void start_block_ctc(const SearchBuffers& sb, int s, StreamCtl& c, int tid, int nthreads) {
+  const float* x = sb.ctcx + (size_t)s * sb.Tcap * sb.V;      // blank id 0 -> column 0
+  for (int h = tid; h < c.n_hyp; h += nthreads) {
+    float* r = sb.ctc_r + beam_off(sb, c.cur, s, h) * sb.Tcap * 2;
+    if (!c.has_ctc) {
+      float acc = 0.f;
+      for (int t = 0; t < c.Tb; ++t) {
+        acc = (t == 0) ? x[0] : acc + x[(size_t)t * sb.V];
+        r[2 * t] = kLogZero;
+        r[2 * t + 1] = acc;
+      }
+      sb.ctc_s[beam_off(sb, c.cur, s, h)] = 0.f;
+    } else {
+      int start = min(max(c.ctc_T, 1), c.Tb);
+      for (int t = start; t < c.Tb; ++t) {
+        r[2 * t] = kLogZero;
+        r[2 * t + 1] = r[2 * (t - 1) + 1] + x[(size_t)t * sb.V];
+      }
+    }
+  }
+}
+
+// Runs with the whole CTA; thread 0 owns the control word in shared memory (`c`).
+__device__ void advance_blocks(const SearchBuffers& sb, int s, StreamCtl& c) {
+  // pops queue entries until one can iterate (process_idx < max_length) or the queue is empty
+  while (true) {
+    __syncthreads();
+    if (c.blk_next >= c.blk_count) {
+      if (threadIdx.x == 0) c.active = 0;
+      __syncthreads();
+      return;
+    }
+    if (threadIdx.x == 0) {
+      c.Tb = sb.blkq_T[s * sb.qcap + c.blk_next];
+      c.is_final = sb.blkq_final[s * sb.qcap + c.blk_next];
+      c.blk_next++;
+      c.iters_done = 0;
+    }
+    __syncthreads();
+    start_block_ctc(sb, s, c, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) { c.has_ctc = 1; c.ctc_T = c.Tb; }
+    __syncthreads();
+    if (c.process_idx < kMaxLength) {
+      if (threadIdx.x == 0) c.active = 1;
+      __syncthreads();
+      return;
+    }
+    // loop exhausted before the first iteration: nothing to rewind (iters_done == 0)
+  }
+}
+
+// Queue the decode blocks of this push and start the first one.  One CTA per queued stream.
+__global__ void search_begin_kernel(SearchBuffers sb, const int* __restrict__ q_stream, const int* __restrict__ q_n,
+                                    const int* __restrict__ q_T, const int* __restrict__ q_final) {
+  __shared__ StreamCtl c;
+  const int s = q_stream[blockIdx.x];
+  if (threadIdx.x == 0) {
+    c = sb.ctl[s];
+    c.blk_count = q_n[blockIdx.x];
+    c.blk_next = 0;
+    for (int i = 0; i < c.blk_count; ++i) {
+      sb.blkq_T[s * sb.qcap + i] = q_T[blockIdx.x * sb.qcap + i];
+      sb.blkq_final[s * sb.qcap + i] = q_final[blockIdx.x * sb.qcap + i];
+    }
+  }
+  __syncthreads();
+  advance_blocks(sb, s, c);
+  if (threadIdx.x == 0) sb.ctl[s] = c;
+}
+
+// ---------------------------------------------------------------- compaction of active rows
+__global__ void compact_rows_kernel(SearchBuffers sb) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_base, s_nact;
+  if (threadIdx.x == 0) { s_base = 0; s_nact = 0; }
+  __syncthreads();
+  for (int s0 = 0; s0 < sb.S; s0 += blockDim.x) {
+    int s = s0 + threadIdx.x;
+    int n = 0;
+    if (s < sb.S && sb.ctl[s].active) n = sb.ctl[s].n_hyp;
+    s_scan[threadIdx.x] = n;
+    __syncthreads();
+    for (int off = 1; off < blockDim.x; off <<= 1) {          // Hillis-Steele inclusive scan
+      int v = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    int incl = s_scan[threadIdx.x];
+    int base = s_base + incl - n;
+    if (s < sb.S) {
+      sb.row_base[s] = n > 0 ? base : -1;
+      for (int h = 0; h < n; ++h) sb.row_sh[base + h] = s * sb.B + h;
+    }
+    // active stream list (order of stream ids)
+    int flag = n > 0 ? 1 : 0;
+    __syncthreads();
+    s_scan[threadIdx.x] = flag;
+    __syncthreads();
+    for (int off = 1; off < blockDim.x; off <<= 1) {
+      int v = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (flag) sb.act_streams[s_nact + s_scan[threadIdx.x] - 1] = s;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) { s_base += incl; s_nact += s_scan[threadIdx.x]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *sb.n_rows = s_base; *sb.n_active = s_nact; }
+}
+
+int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int* q_n, const int* q_T,
+                        const int* q_final, int n_q, cudaStream_t st) {
+  if (n_q > 0) {
+    search_begin_kernel<<<n_q, 64, 0, st>>>(sb, q_stream, q_n, q_T, q_final);
+    SCB_LAUNCH_CHECK();
+  }
+  compact_rows_kernel<<<1, 1024, 0, st>>>(sb);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- decoder input: sqrt(D)*Emb[y_last] + pe[len-1]
+__global__ void dec_embed_kernel(SearchBuffers sb, const float* __restrict__ emb, const float* __restrict__ pe,
+                                 float* __restrict__ x) {
+  const int r = blockIdx.x;
+  if (r >= *sb.n_rows) return;
+  const int sh = sb.row_sh[r], s = sh / sb.B, h = sh % sb.B;
+  const StreamCtl& c = sb.ctl[s];
+  const int tok = sb.yseq[beam_off(sb, c.cur, s, h) * sb.Lcap + c.len - 1];
+  const float scale = sqrtf((float)sb.D);
+  for (int d = threadIdx.x; d < sb.D; d += blockDim.x)
+    x[(size_t)r * sb.D + d] = emb[(size_t)tok * sb.D + d] * scale + pe[(size_t)(c.len - 1) * sb.D + d];
+}
+
+int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, cudaStream_t st) {
+  dec_embed_kernel<<<sb.S * sb.B, 128, 0, st>>>(sb, emb, pe, x);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- decoder attention (self over the KV tree / cross over memory)
+// One CTA per (active stream, head) serves all hypotheses of the stream so that keys/values shared by
+// the beam are read once.  Flash-style online softmax over tiles of 128 positions.
+//   mode 0 (self):  position j of hypothesis b lives in skv[layer][s][j][anc_b[j]]; this step's K|V
+//                   (columns D..3D of the fused QKV GEMM output) is first appended at [len-1][b].
+//   mode 1 (cross): position j lives in xkv[layer][s][j]; all hypotheses see frames [0, Tb).
+constexpr int ATILE = 128;
+constexpr int AMAXB = 20;     // beam capacity of the attention kernel
+
+template <int DK>
+__global__ void __launch_bounds__(128) dec_attention_kernel(SearchBuffers sb, int mode, int layer,
+                                                            const float* __restrict__ q, int ldq,
+                                                            const float* __restrict__ kv_new, int ldkv,
+                                                            float* __restrict__ out) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  const int head = blockIdx.y;
+  const StreamCtl& c = sb.ctl[s];
+  const int nb = c.n_hyp, row0 = sb.row_base[s], D = sb.D;
+  const int npos = mode == 0 ? c.len : c.Tb;
+  const int tid = threadIdx.x;
+
+  extern __shared__ unsigned char smem_raw[];
+  float* qs = reinterpret_cast<float*>(smem_raw);            // [AMAXB][DK]
+  float* sc = qs + AMAXB * DK;                               // [AMAXB][ATILE]
+  float* sm_m = sc + AMAXB * ATILE;                          // [AMAXB] running max
+  float* sm_l = sm_m + AMAXB;                                // [AMAXB] running sum
+  float* sm_f = sm_l + AMAXB;                                // [AMAXB] rescale factor of the tile
+  unsigned char* ancs = reinterpret_cast<unsigned char*>(sm_f + AMAXB);   // [AMAXB][Lcap] (self only)
+
+  for (int i = tid; i < nb * DK; i += blockDim.x) qs[i] = q[(size_t)(row0 + i / DK) * ldq + head * DK + i % DK];
+  if (tid < AMAXB) { sm_m[tid] = -INFINITY; sm_l[tid] = 0.f; }
+  const size_t row_stride = 2 * (size_t)D;                  // K|V row
+  const float* base;
+  if (mode == 0) {
+    float* store = sb.skv + ((size_t)layer * sb.S + s) * sb.Lcap * sb.B * row_stride;
+    // append this step's K|V for every hypothesis (this head's slice)
+    for (int i = tid; i < nb * 2 * DK; i += blockDim.x) {
+      int b = i / (2 * DK), rem = i % (2 * DK), which = rem / DK, cc = rem % DK;
+      store[((size_t)(c.len - 1) * sb.B + b) * row_stride + which * D + head * DK + cc] =
+          kv_new[(size_t)(row0 + b) * ldkv + which * D + head * DK + cc];
+    }
+    for (int i = tid; i < nb * npos; i += blockDim.x) {
+      int b = i / npos, j = i % npos;
+      ancs[b * sb.Lcap + j] = (j == npos - 1) ? (unsigned char)b
+                                              : sb.anc[beam_off(sb, c.cur, s, b) * sb.Lcap + j];
+    }
+    base = store;
+  } else {
+    base = sb.xkv + ((size_t)layer * sb.S + s) * sb.Tcap * row_stride;
+  }
+  __syncthreads();
+
+  const float sqrt_dk = sqrtf((float)DK);
+  // accumulators: thread (g, cdim) owns hypotheses b = g, g+G, ... for output dim cdim
+  constexpr int G = 128 / DK;                 // 4 for DK=32, 2 for DK=64
+  constexpr int NACC = (AMAXB + G - 1) / G;
+  const int g = tid / DK, cdim = tid % DK;
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+  for (int t0 = 0; t0 < npos; t0 += ATILE) {
+    // ---- scores for position j = t0 + tid
+    const int j = t0 + tid;
+    if (j < npos) {
+      float kreg[DK];
+      int loaded = -1;
+      for (int b = 0; b < nb; ++b) {
+        int slot = mode == 0 ? (int)ancs[b * sb.Lcap + j] : 0;
+        if (slot != loaded) {
+          const float* kp = mode == 0 ? base + ((size_t)j * sb.B + slot) * row_stride + head * DK
+                                      : base + (size_t)j * row_stride + head * DK;
+#pragma unroll
+          for (int i = 0; i < DK; i += 4) {
+            float4 v = *reinterpret_cast<const float4*>(kp + i);
+            kreg[i] = v.x; kreg[i + 1] = v.y; kreg[i + 2] = v.z; kreg[i + 3] = v.w;
+          }
+          loaded = slot;
+        }
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < DK; ++i) d = fmaf(qs[b * DK + i], kreg[i], d);
+        sc[b * ATILE + tid] = d / sqrt_dk;
+      }
+    } else {
+      for (int b = 0; b < nb; ++b) sc[b * ATILE + tid] = -INFINITY;
+    }
+    __syncthreads();
+    // ---- online softmax bookkeeping: warp w handles hypotheses w, w+4, ...
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int b = warp; b < nb; b += 4) {
+        float m = -INFINITY;
+        for (int i = lane; i < ATILE; i += 32) m = fmaxf(m, sc[b * ATILE + i]);
+        m = warp_max(m);
+        float m_old = sm_m[b];
+        float m_new = fmaxf(m_old, m);
+        float ssum = 0.f;
+        for (int i = lane; i < ATILE; i += 32) {
+          float e = expf(sc[b * ATILE + i] - m_new);
+          sc[b * ATILE + i] = e;
+          ssum += e;
+        }
+        ssum = warp_sum(ssum);
+        if (lane == 0) {
+          float f = expf(m_old - m_new);       // 0 on the first tile (m_old = -inf)
+          sm_f[b] = f;
+          sm_l[b] = sm_l[b] * f + ssum;
+          sm_m[b] = m_new;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- P * V for the tile
+    {
+      const int jn = min(ATILE, npos - t0);
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        int b = g + i * G;
+        if (b < nb) acc[i] *= sm_f[b];
+      }
+      for (int jj = 0; jj < jn; ++jj) {
+        const int jp = t0 + jj;
+        float vreg = 0.f;
+        int loaded = -1;
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+          int b = g + i * G;
+          if (b < nb) {
+            int slot = mode == 0 ? (int)ancs[b * sb.Lcap + jp] : 0;
+            if (slot != loaded) {
+              vreg = mode == 0 ? base[((size_t)jp * sb.B + slot) * row_stride + D + head * DK + cdim]
+                               : base[(size_t)jp * row_stride + D + head * DK + cdim];
+              loaded = slot;
+            }
+            acc[i] = fmaf(sc[b * ATILE + jj], vreg, acc[i]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    int b = g + i * G;
+    if (b < nb) out[(size_t)(row0 + b) * D + head * DK + cdim] = acc[i] / sm_l[b];
+  }
+}
+
+int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
+                         const float* kv_new, int ldkv, float* out, cudaStream_t st) {
+  if (sb.B > AMAXB) { set_last_error("dec_attention: beam %d > %d", sb.B, AMAXB); return -1; }
+  const int dk = sb.D / sb.H;
+  dim3 grid(sb.S, sb.H);
+  size_t smem = sizeof(float) * (AMAXB * dk + AMAXB * ATILE + 3 * AMAXB) + (mode == 0 ? (size_t)AMAXB * sb.Lcap : 0);
+  if (dk == 32) dec_attention_kernel<32><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out);
+  else if (dk == 64) dec_attention_kernel<64><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out);
+  else { set_last_error("dec_attention: unsupported head dim %d", dk); return -1; }
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- log-softmax + pre-beam top-40
+// One warp per row (V = 1024 -> 32 values per lane).  Writes log-probs in place and the 40 best ids of
+// w_dec * logp in descending order (lowest index first on ties).   (beam_search.py:121-154)
+constexpr int VMAX_PER_LANE = 32;
+
+__global__ void __launch_bounds__(128) logsoftmax_prebeam_kernel(SearchBuffers sb, float* __restrict__ logits) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= *sb.n_rows) return;
+  const int lane = threadIdx.x & 31, V = sb.V;
+  float* row = logits + (size_t)r * V;
+  float v[VMAX_PER_LANE];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < VMAX_PER_LANE; ++i) { v[i] = row[lane + 32 * i]; m = fmaxf(m, v[i]); }
+  m = warp_max(m);
+  float ssum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VMAX_PER_LANE; ++i) ssum += expf(v[i] - m);
+  ssum = warp_sum(ssum);
+  const float lse = logf(ssum);
+#pragma unroll
+  for (int i = 0; i < VMAX_PER_LANE; ++i) {
+    v[i] = (v[i] - m) - lse;
+    row[lane + 32 * i] = v[i];
+    v[i] = __fmul_rn(sb.w_dec, v[i]);             // full-scorer score used for the pre-beam
+  }
+  // 40 rounds of warp arg-max
+  float lbest = -INFINITY; int lidx = 0;
+  auto rescan = [&]() {
+    lbest = -INFINITY; lidx = 0;
+#pragma unroll
+    for (int i = 0; i < VMAX_PER_LANE; ++i) if (v[i] > lbest) { lbest = v[i]; lidx = i; }
+  };
+  rescan();
+  for (int k = 0; k < kPreBeam; ++k) {
+    float bv = lbest; int bi = lane + 32 * lidx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) sb.pre_ids[(size_t)r * kPreBeam + k] = bi;
+    if ((bi & 31) == lane) {
+      const int slot = bi >> 5;
+#pragma unroll
+      for (int i = 0; i < VMAX_PER_LANE; ++i) if (i == slot) v[i] = -INFINITY;
+      rescan();
+    }
+  }
+}
+
+int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st) {
+  if (sb.V != 1024) { set_last_error("logsoftmax_prebeam: V=%d unsupported (1024 only)", sb.V); return -1; }
+  logsoftmax_prebeam_kernel<<<cdiv(sb.S * sb.B, 4), 128, 0, st>>>(sb, logits);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// rows with row_flag != 0 get an in-place log-softmax (CTC store rows t < 24)
+__global__ void __launch_bounds__(128) logsoftmax_rows_kernel(float* __restrict__ x, const int64_t* __restrict__ row_off,
+                                                              const int* __restrict__ row_flag, int rows, int V) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows || !row_flag[r]) return;
+  const int lane = threadIdx.x & 31;
+  float* row = x + row_off[r];
+  float m = -INFINITY;
+  for (int i = lane; i < V; i += 32) m = fmaxf(m, row[i]);
+  m = warp_max(m);
+  float ssum = 0.f;
+  for (int i = lane; i < V; i += 32) ssum += expf(row[i] - m);
+  const float lse = logf(warp_sum(ssum));
+  for (int i = lane; i < V; i += 32) row[i] = (row[i] - m) - lse;
+}
+
+int launch_logsoftmax_rows(float* x, const int64_t* row_off, const int* row_flag, int rows, int V, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  logsoftmax_rows_kernel<<<cdiv(rows, 4), 128, 0, st>>>(x, row_off, row_flag, rows, V);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- CTC prefix scorer (ctc_prefix_score_full.py:88-291)
+// 64 threads per row, thread k < 40 owns candidate ids[row][k].  The forward variables r are NOT
+// materialised for all 40 candidates (the reference writes a (T,2,n_bh,40) tensor every step); only the
+// column each surviving hypothesis inherits is rebuilt after pruning (ctc_state_update_kernel).
+struct CtcRec { float rn, rb; };
+
+__device__ __forceinline__ void ctc_forward_column(const float* __restrict__ x, int V, const float* __restrict__ rprev,
+                                                   int T, int L, int c, bool same_as_last, float* __restrict__ r_out,
+                                                   float& psi) {
+  // r_out (if non-null): [T][2].  Returns psi = logsumexp_t(phi[t-1] + x[t,c]) (+) r[start-1, n].
+  const int start = min(max(L, 1), T);
+  float rn = kLogZero, rb = kLogZero;
+  if (L == 0) rn = x[c];                                    // r[0, n] = x[0, c]
+  if (r_out) {
+    for (int t = 0; t < start; ++t) { r_out[2 * t] = (t == 0 && L == 0) ? rn : kLogZero; r_out[2 * t + 1] = kLogZero; }
+  }
+  // online logsumexp over {r[start-1, n]} U {phi[t-1] + x[t, c]}
+  float mx = rn, sum = 1.f;
+  float p_n = rprev[2 * (start - 1)], p_b = rprev[2 * (start - 1) + 1];
+  for (int t = start; t < T; ++t) {
+    const float phi = same_as_last ? p_b : lse2(p_n, p_b);
+    const float xc = x[(size_t)t * V + c], xb = x[(size_t)t * V];
+    const float nn = lse2(rn, phi) + xc;
+    const float nb = lse2(rn, rb) + xb;
+    rn = nn; rb = nb;
+    if (r_out) { r_out[2 * t] = rn; r_out[2 * t + 1] = rb; }
+    const float e = phi + xc;
+    if (e > mx) { sum = sum * expf(mx - e) + 1.f; mx = e; } else { sum += expf(e - mx); }
+    p_n = rprev[2 * t]; p_b = rprev[2 * t + 1];
+  }
+  psi = logf(sum) + mx;
+}
+
+__global__ void __launch_bounds__(64) ctc_prefix_kernel(SearchBuffers sb) {
+  const int r = blockIdx.x;
+  if (r >= *sb.n_rows) return;
+  const int sh = sb.row_sh[r], s = sh / sb.B, h = sh % sb.B;
+  const StreamCtl& c = sb.ctl[s];
+  const float* x = sb.ctcx + (size_t)s * sb.Tcap * sb.V;
+  const float* rprev = sb.ctc_r + beam_off(sb, c.cur, s, h) * sb.Tcap * 2;
+  const int L = c.len - 1, T = c.Tb;
+  const int last = sb.yseq[beam_off(sb, c.cur, s, h) * sb.Lcap + c.len - 1];
+  const int k = threadIdx.x;
+  if (k < kPreBeam) {
+    const int tok = sb.pre_ids[(size_t)r * kPreBeam + k];
+    float psi;
+    ctc_forward_column(x, sb.V, rprev, T, L, tok, tok == last, nullptr, psi);
+    sb.psi[(size_t)r * kPreBeam + k] = psi;
+  } else if (k == kPreBeam) {
+    sb.psi_eos[r] = lse2(rprev[2 * (T - 1)], rprev[2 * (T - 1) + 1]);   // r_sum[T-1]
+  }
+}
+
+int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st) {
+  ctc_prefix_kernel<<<sb.S * sb.B, 64, 0, st>>>(sb);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- combine + per-hypothesis top-B (beam_search.py:145-183, 723)
+// One warp per row.  Only the 40 candidates and <eos> can carry a real CTC score; every other token
+// scores w_ctc * (logzero - s_prev) and can never reach the top-B (B <= 20 < 39).
+__global__ void __launch_bounds__(128) combine_topk_kernel(SearchBuffers sb, const float* __restrict__ logp) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= *sb.n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int sh = sb.row_sh[r], s = sh / sb.B, h = sh % sb.B;
+  const StreamCtl& c = sb.ctl[s];
+  const float s_prev = sb.ctc_s[beam_off(sb, c.cur, s, h)];
+  const int eos = sb.V - 1;
+  const int* ids = sb.pre_ids + (size_t)r * kPreBeam;
+  // lane owns candidates lane and lane+32 (slot 40 = <eos> when it is not among the 40)
+  float val[2], dec[2], ctc[2], psi[2]; int tok[2];
+  bool eos_in = false;
+  for (int k = 0; k < kPreBeam; ++k) eos_in |= (ids[k] == eos);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int k = lane + 32 * q;
+    val[q] = -INFINITY; tok[q] = -1; dec[q] = 0.f; ctc[q] = 0.f; psi[q] = kLogZero;
+    int t = -1;
+    if (k < kPreBeam) t = ids[k];
+    else if (k == kPreBeam && !eos_in) t = eos;
+    if (t >= 0) {
+      float ps;
+      if (t == 0) ps = kLogZero;                        // blank is forced to logzero (:288)
+      else if (t == eos) ps = sb.psi_eos[r];            // eos = r_sum[T-1] (:284-285)
+      else ps = sb.psi[(size_t)r * kPreBeam + k];
+      const float d = logp[(size_t)r * sb.V + t];
+      const float cs = ps - s_prev;
+      tok[q] = t; dec[q] = d; ctc[q] = cs; psi[q] = ps;
+      val[q] = __fadd_rn(__fmul_rn(sb.w_dec, d), __fmul_rn(sb.w_ctc, cs));
+    }
+  }
+  // inherit-column token for select_state (scorers.py:418-425): the token itself if it was scored,
+  // otherwise candidate 0 of this hypothesis
+  const int col0 = ids[0];
+  for (int i = 0; i < sb.B; ++i) {
+    float bv = val[0]; int bq = 0;
+    if (val[1] > bv) { bv = val[1]; bq = 1; }
+    int bk = lane + 32 * bq;                             // candidate slot index (ties -> lowest token id)
+    int bt = tok[bq];
+    float cv = bv; int ck = bk, ct = bt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      int ok = __shfl_xor_sync(0xffffffffu, ck, o);
+      int ot = __shfl_xor_sync(0xffffffffu, ct, o);
+      if (ov > cv || (ov == cv && ot >= 0 && (ct < 0 || ot < ct))) { cv = ov; ck = ok; ct = ot; }
+    }
+    if ((ck & 31) == lane) {
+      const int q = ck >> 5;
+      const size_t o = (size_t)r * sb.B + i;
+      sb.cand_val[o] = val[q];
+      sb.cand_tok[o] = tok[q];
+      sb.cand_dec[o] = dec[q];
+      sb.cand_ctc[o] = ctc[q];
+      sb.cand_psi[o] = psi[q];
+      sb.cand_col[o] = (ck < kPreBeam) ? tok[q] : col0;
+      val[q] = -INFINITY;
+    }
+    __syncwarp();
+  }
+}
+
+int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st) {
+  combine_topk_kernel<<<cdiv(sb.S * sb.B, 4), 128, 0, st>>>(sb, logp);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- global prune + new beam + stop decision
+// One CTA (128 threads) per active stream.  (beam_search.py:721-809, hypothesis.py:132-168)
+constexpr int PMAXC = 13;   // ceil(20*20 / 32)
+
+__global__ void __launch_bounds__(128) beam_prune_kernel(SearchBuffers sb) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  StreamCtl& c = sb.ctl[s];
+  const int B = sb.B, nb = c.n_hyp, row0 = sb.row_base[s], cur = c.cur, nxt = cur ^ 1, len = c.len;
+  const int tid = threadIdx.x, eos = sb.V - 1;
+  __shared__ int sel[AMAXB];        // chosen candidate index (parent * B + rank)
+  __shared__ int s_tok[AMAXB];
+  __shared__ int s_flag;
+  if (tid < 32) {
+    const int ncand = nb * B;
+    double v[PMAXC];
+#pragma unroll
+    for (int i = 0; i < PMAXC; ++i) {
+      int ci = tid + 32 * i;
+      v[i] = -INFINITY;
+      if (ci < ncand) {
+        int p = ci / B, j = ci % B;
+        v[i] = sb.score[beam_off(sb, cur, s, p)] + (double)sb.cand_val[(size_t)(row0 + p) * B + j];
+      }
+    }
+    for (int k = 0; k < B; ++k) {
+      double bv = -INFINITY; int bi = 1 << 30;
+#pragma unroll
+      for (int i = 0; i < PMAXC; ++i) {
+        int ci = tid + 32 * i;
+        if (v[i] > bv || (v[i] == bv && ci < bi && v[i] > -INFINITY)) { bv = v[i]; bi = ci; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (tid == 0) sel[k] = bi;
+      if ((bi & 31) == tid) {
+        const int slot = bi >> 5;
+#pragma unroll
+        for (int i = 0; i < PMAXC; ++i) if (i == slot) v[i] = -INFINITY;
+      }
+    }
+  }
+  if (tid == 0) s_flag = 0;
+  __syncthreads();
+  // scalar fields of the new hypotheses
+  if (tid < B) {
+    const int ci = sel[tid], p = ci / B, j = ci % B;
+    const size_t co = (size_t)(row0 + p) * B + j, po = beam_off(sb, cur, s, p), no = beam_off(sb, nxt, s, tid);
+    const int tok = sb.cand_tok[co];
+    s_tok[tid] = tok;
+    sb.score[no] = sb.score[po] + (double)sb.cand_val[co];
+    sb.sc_dec[no] = sb.sc_dec[po] + (double)sb.cand_dec[co];
+    sb.sc_ctc[no] = sb.sc_ctc[po] + (double)sb.cand_ctc[co];
+    sb.ctc_s[no] = sb.cand_psi[co];
+    sb.new_parent[s * B + tid] = p;
+    sb.new_col[s * B + tid] = sb.cand_col[co];
+    sb.yseq[no * sb.Lcap + len] = tok;
+    sb.xpos[no * sb.Lcap + len] = c.Tb - 1;
+    sb.anc[no * sb.Lcap + len - 1] = (unsigned char)p;
+  }
+  __syncthreads();
+  // copy the parents' histories
+  for (int i = tid; i < B * len; i += blockDim.x) {
+    const int hn = i / len, j = i % len;
+    const int p = sel[hn] / B;
+    const size_t po = beam_off(sb, cur, s, p) * sb.Lcap, no = beam_off(sb, nxt, s, hn) * sb.Lcap;
+    sb.yseq[no + j] = sb.yseq[po + j];
+    sb.xpos[no + j] = sb.xpos[po + j];
+    if (j < len - 1) sb.anc[no + j] = sb.anc[po + j];
+  }
+  // BBD repetition test on the new beam (beam_search.py:466-505): last token occurs in yseq[1:-1]
+  if (sb.use_bbd && !c.is_final) {
+    for (int i = tid; i < B * len; i += blockDim.x) {
+      const int hn = i / len, j = i % len;
+      const int last = s_tok[hn];
+      if (j >= 1 && last != eos) {
+        const int p = sel[hn] / B;
+        if (sb.yseq[beam_off(sb, cur, s, p) * sb.Lcap + j] == last) s_flag = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    bool any_eos = false, all_eos = true;
+    for (int i = 0; i < B; ++i) { bool e = s_tok[i] == eos; any_eos |= e; all_eos &= e; }
+    const bool best_eos = s_tok[0] == eos;
+    int outcome = OUT_CONTINUE;
+    if (any_eos && (!c.is_final || best_eos)) outcome = OUT_BREAK_NEW;
+    if (outcome == OUT_CONTINUE && sb.use_bbd && !c.is_final && s_flag) outcome = OUT_BREAK_OLD;
+    if (outcome == OUT_CONTINUE && c.is_final && all_eos) outcome = OUT_BREAK_NEW;
+    c.outcome = outcome;
+    c.steps_total++;
+  }
+}
+
+int launch_beam_prune(const SearchBuffers& sb, cudaStream_t st) {
+  if (sb.B > AMAXB) { set_last_error("beam_prune: beam %d > %d", sb.B, AMAXB); return -1; }
+  beam_prune_kernel<<<sb.S, 128, 0, st>>>(sb);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- CTC state of the new beam (select_state, scorers.py:382-431)
+// One thread per (active stream, new hypothesis): rebuild the inherited forward column into the other
+// beam buffer.  Wasted (but harmless) when the step is later discarded by a rewind.
+__global__ void __launch_bounds__(32) ctc_state_update_kernel(SearchBuffers sb) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  const StreamCtl& c = sb.ctl[s];
+  const int hn = threadIdx.x;
+  if (hn >= sb.B) return;
+  const int p = sb.new_parent[s * sb.B + hn], col = sb.new_col[s * sb.B + hn];
+  const float* x = sb.ctcx + (size_t)s * sb.Tcap * sb.V;
+  const float* rprev = sb.ctc_r + beam_off(sb, c.cur, s, p) * sb.Tcap * 2;
+  float* rout = sb.ctc_r + beam_off(sb, c.cur ^ 1, s, hn) * sb.Tcap * 2;
+  const int last = sb.yseq[beam_off(sb, c.cur, s, p) * sb.Lcap + c.len - 1];
+  float psi;
+  ctc_forward_column(x, sb.V, rprev, c.Tb, c.len - 1, col, col == last, rout, psi);
+}
+
+int launch_ctc_state_update(const SearchBuffers& sb, cudaStream_t st) {
+  ctc_state_update_kernel<<<sb.S, 32, 0, st>>>(sb);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- commit the step: block end / rewind / next block
+__global__ void __launch_bounds__(64) step_commit_kernel(SearchBuffers sb) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  __shared__ StreamCtl c;
+  __shared__ int ended;
+  if (threadIdx.x == 0) {
+    c = sb.ctl[s];
+    ended = 0;
+    const int outcome = c.outcome;
+    if (outcome == OUT_CONTINUE) {
+      c.cur ^= 1; c.len += 1; c.n_hyp = sb.B; c.ctc_T = c.Tb; c.has_ctc = 1;
+      c.iters_done += 1; c.process_idx += 1;
+      if (c.process_idx >= kMaxLength) {                  // while-loop exhausted
+        ended = 1;
+        if (c.process_idx > 1 && c.iters_done >= 1) c.process_idx -= 1;   // rewind to an identical snapshot
+      }
+    } else {
+      ended = 1;
+      const bool rewind = c.process_idx > 1 && c.iters_done >= 1;         // beam_search.py:827-836
+      if (rewind) c.process_idx -= 1;                                     // beam = snapshot = current buffer
+      else if (outcome == OUT_BREAK_NEW) { c.cur ^= 1; c.len += 1; c.n_hyp = sb.B; c.ctc_T = c.Tb; c.has_ctc = 1; }
+    }
+  }
+  __syncthreads();
+  if (ended) advance_blocks(sb, s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) sb.ctl[s] = c;
+}
+
+int launch_step_finish(const SearchBuffers& sb, cudaStream_t st) {
+  step_commit_kernel<<<sb.S, 64, 0, st>>>(sb);
+  SCB_LAUNCH_CHECK();
+  compact_rows_kernel<<<1, 1024, 0, st>>>(sb);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace scb

@@ -1,0 +1,99 @@
+"""Drop-in `Speech2TextStreaming` on the B200 CUDA path.
+
+Same constructor, `__call__`, `reset`, `recognize`, `recognize_stream`, `n_best_hypotheses`,
+`get_best_hypothesis` and `create_streaming_interface` as the reference class
+(speechcatcher/speech2text_streaming.py:29-621).  Each instance is a one-stream view onto a
+`StreamGroup`; pass `group=`/`stream_id=` to share one engine between many facades (what the
+reference's server pool and segment loop do with N model copies, speechcatcher_server.py:331-357).
+
+Compat superset: `always_assemble_hyps` is accepted (the reference CLI passes
+it, speechcatcher.py:612) and results are ESPnet-shaped 5-tuples `(text, tokens, token_ids, token_pos,
+hyp)` whose first three fields equal the reference's 3-tuple.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .stream_group import StreamGroup
+
+
+class Speech2TextStreaming:
+    def __init__(self, model_dir: Union[str, Path] = None, beam_size: int = 5, ctc_weight: float = 0.3,
+                 device: str = "cuda", dtype: str = "float32", use_bbd: bool = False,
+                 group: Optional[StreamGroup] = None, stream_id: int = 0, max_chunk: int = 8192,
+                 max_seconds: float = 61.0):
+        if group is None:
+            if device == "cuda":
+                device = "cuda:0"
+            group = StreamGroup(model_dir, n_streams=1, beam_size=beam_size, ctc_weight=ctc_weight, device=device,
+                                dtype=dtype, use_bbd=use_bbd, max_chunk=max_chunk, max_seconds=max_seconds)
+            stream_id = 0
+        self.group, self.stream_id = group, stream_id
+        self.model_dir = Path(group.model_dir)
+        self.beam_size, self.ctc_weight, self.use_bbd = group.beam_size, group.ctc_weight, group.use_bbd
+        self.device, self.dtype = str(group.device), dtype
+        self.mean, self.std = group.mean, group.std
+        self.win_length, self.hop_length = 400, 160
+        self.token_list = None
+        self.tokenizer = None
+        bpe = self.model_dir / "bpe.model"
+        if bpe.exists():                       # speech2text_streaming.py:100-124
+            import sentencepiece as spm
+            self.tokenizer = spm.SentencePieceProcessor()
+            self.tokenizer.Load(str(bpe))
+            n = self.tokenizer.GetPieceSize()
+            self.token_list = (["<blank>", self.tokenizer.IdToPiece(0)] +
+                               [self.tokenizer.IdToPiece(i) for i in range(3, n)] + ["<sos/eos>"])
+        self.beam_state = None
+        self.processed_frames = 0
+        self.frontend_states = None
+        self.reset()
+
+    def reset(self):
+        self.beam_state = None
+        self.processed_frames = 0
+        self.frontend_states = None
+        self.group.reset([self.stream_id])
+
+    def __call__(self, speech: Union[np.ndarray, torch.Tensor], is_final: bool = False, finalize_all: bool = False,
+                 always_assemble_hyps: bool = True) -> List[Tuple]:
+        if isinstance(speech, torch.Tensor):
+            speech = speech.detach().cpu().numpy()
+        speech = np.asarray(speech, np.float32)
+        if speech.ndim != 1:
+            raise NotImplementedError("the B200 path takes raw 1-D waveforms (pre-computed features are not supported)")
+        self.group.push([self.stream_id], [speech], [is_final])
+        plan = self.group.last_plan(self.stream_id)
+        if not plan.called:
+            return []                           # speech2text_streaming.py:431-433
+        self.beam_state = self.group.beam(self.stream_id)
+        return self.group.results(self.stream_id, is_final, finalize_all, self.token_list)
+
+    def recognize(self, speech):
+        self.reset()
+        return self(speech, is_final=True)
+
+    def recognize_stream(self, chunks):
+        self.reset()
+        results = None
+        for i, chunk in enumerate(chunks):
+            results = self(chunk, is_final=(i == len(chunks) - 1))
+        return results if results is not None else []
+
+    @property
+    def n_best_hypotheses(self) -> int:
+        return self.beam_size
+
+    def get_best_hypothesis(self):
+        if self.beam_state is None or not self.beam_state[0]:
+            return None
+        res = self.group.results(self.stream_id, True, True, self.token_list)
+        return res[0] if res else None
+
+
+def create_streaming_interface(model_dir, beam_size: int = 5, ctc_weight: float = 0.3, device: str = "cuda"):
+    return Speech2TextStreaming(model_dir=model_dir, beam_size=beam_size, ctc_weight=ctc_weight, device=device)

@@ -1,0 +1,227 @@
+"""StreamGroup: the batched, device-resident engine under the Speech2TextStreaming facade.
+
+One StreamGroup per GPU holds S independent streams; `push` advances any subset of them by one
+chunk each (one reference `Speech2TextStreaming.__call__` per stream,
+speechcatcher/speech2text_streaming.py:402-539) in a single batched pass through the CUDA path.
+PyTorch is used for device memory, streams and H2D copies only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import yaml
+
+from . import _lib
+from ._lib import ScConfig, ScPushStats, ScStreamPlan
+from .weights import bf16_names, pack_weights
+
+EOS_FILTER_ID = 1023   # hard-coded in the reference's output filter (speech2text_streaming.py:474)
+
+
+def _find_checkpoint(model_dir: Path) -> Path:
+    """Same search order as the reference (speech2text_streaming.py:163-189)."""
+    names = ["valid.acc.best.pth", "valid.acc.ave_6best.pth", "valid.acc.ave.pth", "model.pth", "checkpoint.pth"]
+    paths = [model_dir / n for n in names]
+    for exp in sorted(model_dir.glob("exp/*/")):
+        paths += [exp / n for n in names]
+    for p in paths:
+        if p.exists():
+            return p
+    raise FileNotFoundError(f"No checkpoint found in {model_dir}")
+
+
+def load_stats(path: Path):
+    """speechcatcher/model/checkpoint_loader.py:210-237 (fp64 mean / std)."""
+    st = np.load(path)
+    if "mean" in st:
+        return np.asarray(st["mean"], np.float64), np.asarray(st["std"], np.float64)
+    count = st["count"]
+    mean = st["sum"] / count
+    std = np.sqrt(np.maximum(st["sum_square"] / count - mean ** 2, 1e-10))
+    return np.asarray(mean, np.float64), np.asarray(std, np.float64)
+
+
+def _frontend_tables():
+    """hann(400) and the slaney mel matrix exactly as the reference builds them
+    (model/frontend/stft_frontend.py:68-85: torch.hann_window + torchaudio melscale_fbanks)."""
+    import torchaudio
+    window = torch.hann_window(400)
+    mel = torchaudio.functional.melscale_fbanks(n_freqs=257, f_min=0.0, f_max=8000.0, n_mels=80,
+                                                sample_rate=16000, norm="slaney", mel_scale="slaney")
+    return window.contiguous(), mel.contiguous()
+
+
+class StreamGroup:
+    def __init__(self, model_dir, n_streams: int = 1, beam_size: int = 5, ctc_weight: float = 0.3,
+                 device: str = "cuda:0", dtype: str = "float32", use_bbd: bool = False,
+                 max_chunk: int = 8192, max_seconds: float = 61.0):
+        if not str(device).startswith("cuda"):
+            raise RuntimeError("speechcatcher_b200 runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device available: the B200 path cannot run")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.model_dir = Path(model_dir)
+        self.n_streams, self.beam_size, self.ctc_weight, self.use_bbd = n_streams, beam_size, ctc_weight, use_bbd
+        if dtype not in ("float32", "bfloat16"):
+            raise ValueError("dtype must be 'float32' (parity mode) or 'bfloat16' (tensor-core mode)")
+        self.precision = 0 if dtype == "float32" else 1
+        ckpt = torch.load(_find_checkpoint(self.model_dir), map_location="cpu")
+        sd = ckpt.get("model", ckpt)
+        vocab = sd["decoder.embed.0.weight"].shape[0]
+        cfg_path = self.model_dir / "config.yaml"
+        conf = yaml.safe_load(open(cfg_path)) if cfg_path.exists() else {}
+        enc, dec = conf.get("encoder_conf", {}), conf.get("decoder_conf", {})
+        self.max_chunk = int(max_chunk)
+        max_frames = int(max_seconds * 25) + 64
+        self.cfg = ScConfig(
+            d_model=enc.get("output_size", 256), enc_heads=enc.get("attention_heads", 4),
+            enc_layers=enc.get("num_blocks", 12), dec_heads=dec.get("attention_heads", 4),
+            dec_layers=dec.get("num_blocks", 6), vocab=vocab, ffn=2048, n_streams=n_streams, beam=beam_size,
+            max_chunk=self.max_chunk, max_frames=max_frames, use_bbd=int(use_bbd), precision=self.precision,
+            ctc_weight=ctc_weight)
+        with torch.cuda.device(self.device):
+            need = C.c_size_t()
+            _lib.check(self.lib.sc_engine_workspace_bytes(C.byref(self.cfg), C.byref(need)), "workspace_bytes")
+            self.workspace = torch.zeros(need.value + 256, dtype=torch.uint8, device=self.device)
+            base = self.workspace.data_ptr()
+            aligned = (base + 255) // 256 * 256
+            self.handle = C.c_void_p()
+            _lib.check(self.lib.sc_engine_create(C.byref(self.cfg), C.c_void_p(aligned), need.value,
+                                                 C.byref(self.handle)), "create")
+            packed = pack_weights(sd, self.cfg.enc_layers, self.cfg.dec_layers, self.cfg.d_model)
+            self.weights: Dict[str, torch.Tensor] = {}
+            for k, v in packed.items():
+                self.weights[k] = v.to(self.device)
+            if self.precision == 1:
+                for k in bf16_names(self.cfg.enc_layers, self.cfg.dec_layers):
+                    self.weights[k + ".bf16"] = self.weights[k].to(torch.bfloat16).contiguous()
+            for k, v in self.weights.items():
+                _lib.check(self.lib.sc_engine_set_weight(self.handle, k.encode(), C.c_void_p(v.data_ptr()),
+                                                         v.numel()), f"set_weight({k})")
+            window, mel = _frontend_tables()
+            self.mean = self.std = None
+            stats = self.model_dir / "feats_stats.npz"
+            if stats.exists():
+                self.mean, self.std = load_stats(stats)
+            mean_p = self.mean.ctypes.data_as(C.c_void_p) if self.mean is not None else None
+            std_p = self.std.ctypes.data_as(C.c_void_p) if self.std is not None else None
+            _lib.check(self.lib.sc_engine_set_frontend(self.handle, C.c_void_p(window.data_ptr()),
+                                                       C.c_void_p(mel.data_ptr()), mean_p, std_p), "set_frontend")
+            _lib.check(self.lib.sc_engine_finalize(self.handle), "finalize")
+        self.stream = torch.cuda.current_stream(self.device)
+        self._wave_dev = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32, device=self.device)
+        self._wave_host = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32).pin_memory()
+        self.last_stats = ScPushStats()
+        self.total_launches = 0
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sc_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, streams: Optional[Sequence[int]] = None):
+        ids = np.asarray(list(range(self.n_streams)) if streams is None else list(streams), np.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sc_engine_reset(self.handle, ids.ctypes.data_as(C.c_void_p), len(ids),
+                                                C.c_void_p(self.stream.cuda_stream)), "reset")
+
+    # ------------------------------------------------------------------ the hot call
+    def push(self, streams: Sequence[int], chunks: Sequence[np.ndarray], is_final: Sequence[bool]) -> ScPushStats:
+        """One chunk per listed stream (host buffers; the H2D copy is part of the call)."""
+        n = len(streams)
+        ids = np.asarray(streams, np.int32)
+        lens = np.asarray([len(c) for c in chunks], np.int32)
+        fin = np.asarray([1 if f else 0 for f in is_final], np.int32)
+        if n and lens.max() > self.max_chunk:
+            raise ValueError(f"chunk of {int(lens.max())} samples exceeds max_chunk={self.max_chunk}")
+        host = self._wave_host
+        for i, (s, c) in enumerate(zip(ids, chunks)):
+            if len(c):
+                host[s, : len(c)] = torch.as_tensor(np.asarray(c, np.float32))
+        with torch.cuda.device(self.device):
+            self._wave_dev.copy_(host, non_blocking=True)
+        return self.push_device(ids, self._wave_dev, lens, fin)
+
+    def push_device(self, ids: np.ndarray, wave_dev: torch.Tensor, lens: np.ndarray, fin: np.ndarray) -> ScPushStats:
+        """Same, with the waveforms already resident: wave_dev[s, :lens[i]] for s = ids[i]."""
+        assert wave_dev.dtype == torch.float32 and wave_dev.is_contiguous() and wave_dev.shape[0] == self.n_streams
+        ids = np.ascontiguousarray(ids, np.int32)
+        lens = np.ascontiguousarray(lens, np.int32)
+        fin = np.ascontiguousarray(fin, np.int32)
+        st = ScPushStats()
+        with torch.cuda.device(self.device):
+            rc = self.lib.sc_engine_push(self.handle, C.c_void_p(wave_dev.data_ptr()), wave_dev.shape[1],
+                                         ids.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
+                                         fin.ctypes.data_as(C.c_void_p), len(ids),
+                                         C.c_void_p(self.stream.cuda_stream), C.byref(st))
+        _lib.check(rc, "push")
+        self.last_stats = st
+        self.total_launches += st.n_kernel_launches
+        return st
+
+    # ------------------------------------------------------------------ results
+    def beam(self, stream: int) -> Tuple[List[List[int]], List[float], List[List[int]], int]:
+        """(yseq per hyp, fp64 scores, xpos per hyp, process_idx) of the running hypotheses."""
+        L = 512
+        yseq = np.zeros((self.beam_size, L), np.int32)
+        xpos = np.zeros((self.beam_size, L), np.int32)
+        score = np.zeros(self.beam_size, np.float64)
+        n_hyp, ln, pidx = C.c_int32(), C.c_int32(), C.c_int32()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sc_engine_read_beam(
+                self.handle, stream, L, C.byref(n_hyp), C.byref(ln), C.byref(pidx),
+                yseq.ctypes.data_as(C.c_void_p), xpos.ctypes.data_as(C.c_void_p), score.ctypes.data_as(C.c_void_p),
+                C.c_void_p(self.stream.cuda_stream)), "read_beam")
+        n, l = n_hyp.value, ln.value
+        return ([yseq[h, :l].tolist() for h in range(n)], score[:n].tolist(),
+                [xpos[h, :l].tolist() for h in range(n)], pidx.value)
+
+    def last_plan(self, stream: int) -> ScStreamPlan:
+        p = ScStreamPlan()
+        _lib.check(self.lib.sc_engine_last_plan(self.handle, stream, C.byref(p)), "last_plan")
+        return p
+
+    def buffer(self, name: str, dtype=torch.float32) -> torch.Tensor:
+        """Debug view of a named internal device buffer (tests)."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _lib.check(self.lib.sc_engine_buffer(self.handle, name.encode(), C.byref(ptr), C.byref(n)), "buffer")
+        base = self.workspace.data_ptr()
+        off = ptr.value - base
+        nbytes = n.value * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off: off + nbytes].view(dtype)
+
+    def results(self, stream: int, is_final: bool, finalize_all: bool, token_list=None):
+        """Output assembly of Speech2TextStreaming.__call__ (speech2text_streaming.py:466-539)."""
+        yseqs, scores, xposs, _ = self.beam(stream)
+        out = []
+        for y, sc, xp in zip(yseqs, scores, xposs):
+            if (not is_final or not finalize_all) and y[-1] != EOS_FILTER_ID:
+                continue
+            if is_final:
+                ids, pos = y[1:], xp[1:]
+                if ids and ids[-1] == EOS_FILTER_ID:
+                    ids, pos = ids[:-1], pos[:-1]
+            else:
+                ids, pos = [], []            # output_index is always 0 in the reference
+            keep = [(t, p) for t, p in zip(ids, pos) if t not in (0, 1, EOS_FILTER_ID)]
+            ids_f = [t for t, _ in keep]
+            if token_list is not None:
+                toks = [token_list[t] for t in ids_f]
+                text = "".join(toks).replace("▁", " ").strip()
+            else:
+                toks = [str(t) for t in ids_f]
+                text = " ".join(toks)
+            out.append((text, toks, ids_f, [p for _, p in keep], dict(yseq=y, score=sc, xpos=xp)))
+        return out
