@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Benchmark of the multi-stream streaming decode path (BASELINE.json metric: audio-sec/sec, RTFx).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle port of the reference path
+
+Workload (BASELINE.json configs[1]): de_streaming_transformer_xl architecture with random-init
+weights, 256 concurrent streams per GPU, beam 10, 60 s of synthetic 16 kHz audio per stream fed in
+8192-sample chunks, last chunk final.  One "step" = decoding all streams' 60 s (118 pushes).
+Streams are independent, so N GPUs run N x 256 streams with no data-path collective (weak scaling);
+torch.distributed (NCCL) is used only for the barrier, the max-over-ranks timing and result checks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+CHUNK = 8192
+SR = 16000
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+def _cpu_worker(args):
+    md, stream, n_samples, beam = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle.speech2text import OracleSpeech2Text
+    from speechcatcher_b200.synthetic import synth_audio
+    audio = synth_audio(stream, n_samples)
+    o = OracleSpeech2Text(md, beam_size=beam, ctc_weight=0.3)
+    t0 = time.perf_counter()
+    lat = []
+    for i in range(0, n_samples, CHUNK):
+        fin = i + CHUNK >= n_samples
+        t1 = time.perf_counter()
+        o(audio[i:i + CHUNK], is_final=fin, finalize_all=fin)
+        lat.append(time.perf_counter() - t1)
+    return time.perf_counter() - t0, lat
+
+
+def cpu_baseline_pass(md, beam, sample_seconds, procs, first_stream=0):
+    """`procs` single-threaded processes, one stream each (mirrors the reference CLI's process pool,
+    speechcatcher.py:481-497).  Returns (audio-s/s aggregate, p50 per-chunk latency in ms)."""
+    from concurrent.futures import ProcessPoolExecutor
+    n = int(sample_seconds * SR)
+    jobs = [(str(md), first_stream + i, n, beam) for i in range(procs)]
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=procs) as ex:
+        res = list(ex.map(_cpu_worker, jobs))
+    wall = time.perf_counter() - t0
+    lat = [x for _, l in res for x in l]
+    compute = max(r[0] for r in res)          # excludes process start-up / model load
+    return procs * sample_seconds / compute, 1000.0 * statistics.median(lat), wall
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="xl")
+    ap.add_argument("--streams", type=int, default=256, help="streams per GPU")
+    ap.add_argument("--beam", type=int, default=10)
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--dtype", default=os.environ.get("SCB_BENCH_DTYPE", "float32"), choices=["float32", "bfloat16"])
+    ap.add_argument("--cpu-sample-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-kernel", default="auto")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    workload = (f"de_streaming_transformer_{args.arch} arch (random-init), {args.streams} streams/GPU, beam {args.beam}, "
+                f"{args.seconds:g} s synthetic 16 kHz audio/stream, 8192-sample chunks, ctc_weight 0.3, use_bbd False")
+
+    from speechcatcher_b200.synthetic import make_model_dir, synth_audio
+    tmp = tempfile.TemporaryDirectory(prefix=f"scb200_bench_r{rank}_")
+    md = make_model_dir(Path(tmp.name) / args.arch, args.arch, seed=0)
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle port
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, str(REPO))
+        procs = cores
+        vals, p50s = [], []
+        for i in range(args.warmup + args.steps):
+            v, p50, _ = cpu_baseline_pass(md, args.beam, args.cpu_sample_seconds, procs)
+            if i >= args.warmup:
+                vals.append(v); p50s.append(p50)
+        v = float(np.mean(vals))
+        sample = (f"{procs} streams x {args.cpu_sample_seconds:g} s (first seconds of the workload's streams), one "
+                  f"single-threaded process per stream; per-step cost of the reference grows with utterance length, "
+                  f"so a short sample over-states its 60 s throughput")
+        line = {"impl": "reference", "metric": "audio-sec/sec (RTFx)", "value": v, "unit": "audio-s/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * procs * args.cpu_sample_seconds / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "inputs": "host"},
+                "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": procs, "kind": "port", "sample": sample,
+                                 "p50_chunk_ms": float(np.mean(p50s))},
+                "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ this repo's CUDA path
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from speechcatcher_b200 import StreamGroup
+
+    S = args.streams
+    n_samples = int(args.seconds * SR)
+    n_chunks = (n_samples + CHUNK - 1) // CHUNK
+    host = torch.empty(S, n_chunks * CHUNK, dtype=torch.float32).pin_memory()
+    host.zero_()
+    for s in range(S):
+        host[s, :n_samples] = torch.from_numpy(synth_audio(rank * S + s, n_samples))
+    grp = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype=args.dtype,
+                      use_bbd=False, max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
+    resident = host.to(dev)                           # inputs resident in HBM for `value`
+    ids = np.arange(S, dtype=np.int32)
+    lens_all = [np.full(S, min(CHUNK, n_samples - c * CHUNK), np.int32) for c in range(n_chunks)]
+    fin_all = [np.full(S, 1 if c == n_chunks - 1 else 0, np.int32) for c in range(n_chunks)]
+    stats = {"steps": 0, "launches": 0, "blocks": 0}
+
+    def one_pass_resident():
+        grp.reset()
+        for c in range(n_chunks):
+            st = grp.push_device(ids, resident, lens_all[c], fin_all[c], col_offset=c * CHUNK)
+            stats["steps"] += st.n_decode_steps; stats["launches"] += st.n_kernel_launches
+            stats["blocks"] += st.n_encoder_blocks
+
+    lat_ms = []
+
+    def one_pass_e2e():
+        """Public API with host buffers: per-chunk H2D from pinned memory inside, results read back."""
+        grp.reset()
+        for c in range(n_chunks):
+            t1 = time.perf_counter()
+            grp.push_batch(ids, host[:, c * CHUNK: c * CHUNK + int(lens_all[c][0])], lens_all[c], fin_all[c])
+            lat_ms.append(1000.0 * (time.perf_counter() - t1))
+        out = [grp.results(s, True, True) for s in range(S)]
+        return out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass_resident()
+    prof = grp.profile_begin(args.profile_kernel)
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = {"steps": 0, "launches": 0, "blocks": 0}
+    e0.record()
+    for _ in range(args.steps):
+        one_pass_resident()
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    roof = grp.profile_end(prof)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    audio_s = world * S * args.seconds * args.steps
+    value = audio_s / (ms / 1000.0)
+
+    e2e = None
+    if not args.no_e2e:
+        one_pass_e2e()                                 # warm the host path
+        lat_ms.clear()
+        sync_all()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 2))
+        d2h = 0
+        for _ in range(n_e2e):
+            out = one_pass_e2e()
+            d2h = sum(len(r[4]["yseq"]) * 8 + 8 for res in out for r in res)
+        sync_all()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * S * args.seconds * n_e2e / dt, "unit": "audio-s/s",
+               "h2d_bytes_per_step": int(S * n_samples * 4), "d2h_bytes_per_step": int(d2h),
+               "p50_chunk_ms": float(statistics.median(lat_ms)), "p95_chunk_ms": float(np.percentile(lat_ms, 95))}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, p50, wall = cpu_baseline_pass(md, args.beam, args.cpu_sample_seconds, cores)
+        cpu_base = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                    "sample": f"{cores} streams x {args.cpu_sample_seconds:g} s of the same workload, one single-threaded "
+                              f"process per stream (oracle port of the reference path; short sample flatters the CPU)",
+                    "p50_chunk_ms": p50}
+    if rank == 0:
+        line = {"metric": "audio-sec/sec (RTFx)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.dtype == "float32" else "bf16", "data": "synthetic",
+                "config": {"workload": workload, "l2": "inputs larger than L2 (983 MB of waveforms per GPU)",
+                           "decode_steps_per_pass": stats["steps"] // max(1, args.steps),
+                           "encoder_blocks_per_pass": stats["blocks"] // max(1, args.steps)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": stats["launches"],
+                "roofline": roof, "cpu_baseline": cpu_base}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,13 @@ int sc_engine_last_plan(void* handle, int32_t stream_id, ScStreamPlan* plan);
 /* Named internal device buffer (tests / debugging): pointer, element count and row pitch. */
 int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem);
 
+/* Live timing of one tagged kernel with CUDA-event pairs on the launching stream (bench.py roofline).
+ * tag: 1 ctc_prefix, 2 dec_self_attn, 3 dec_cross_attn, 4 dec_ffn1, 5 enc_ffn1, 6 prebeam, 7 enc_attn,
+ *      8 conv2, 9 dec_ffn2, 10 enc_ffn2, 11 ctc_state_update.  counters8: device-side algorithmic counters. */
+int sc_engine_profile_begin(void* handle, int32_t tag, int32_t max_launches);
+int sc_engine_profile_end(void* handle, int32_t* n_launches, double* total_ms, double* host_flops,
+                          uint64_t* counters8);
+
 /* ---- host-only shape planner (no CUDA calls; CPU-testable) ---- */
 int sc_planner_create(int32_t n_streams, void** planner);
 int sc_planner_destroy(void* planner);

@@ -35,7 +35,9 @@ static Caps make_caps(const ScConfig& c) {
   k.nb_cap = std::max(1, (k.sub_cap - 24 + 15) / 16);
   k.qcap = k.nb_cap + 2;
   k.Tcap = c.max_frames;
-  k.Lcap = 512;                                          // > max_length (500) + sos + 1
+  // hypotheses grow by one token per completed iteration (<= max_length 500) plus one for every block whose
+  // first iteration already ends in <eos> (kept without a rewind, beam_search.py:827): bound by the block count
+  k.Lcap = ((kMaxLength + 2 + c.max_frames / kHopB + 8) + 31) / 32 * 32;
   k.nb_max = c.n_streams * k.nb_cap;
   k.rows_max = k.nb_max * kSlots;
   k.sub_rows_max = c.n_streams * k.t2_cap;
@@ -82,6 +84,11 @@ struct Engine {
   std::unordered_map<std::string, std::pair<void*, size_t>> named;
   std::vector<ScStreamPlan> last_plan;
   int launches = 0;
+  // live kernel timing (bench.py roofline): CUDA-event pairs around every launch of one tagged kernel
+  int prof_tag = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_used = 0;
+  double prof_flops = 0.0;          // host-known algorithmic FLOPs of the tagged launches (encoder GEMMs)
 
   explicit Engine(const ScConfig& c) : cfg(c), cap(make_caps(c)), planner(c.n_streams), last_plan(c.n_streams) {}
 };
@@ -146,7 +153,7 @@ static void carve(Engine& e, Carver& cv) {
   sb.ctl = cv.take<StreamCtl>(S); reg("ctl", sb.ctl, S * sizeof(StreamCtl) / sizeof(int));
   sb.blkq_T = cv.take<int>(S * k.qcap); sb.blkq_final = cv.take<int>(S * k.qcap);
   sb.row_sh = cv.take<int>(R); sb.row_base = cv.take<int>(S); sb.act_streams = cv.take<int>(S);
-  sb.n_rows = cv.take<int>(1); sb.n_active = cv.take<int>(1);
+  sb.n_rows = cv.take<int>(1); sb.n_active = cv.take<int>(2);   // [1] = capacity error flag
   sb.logp = e.dlogp;
   sb.pre_ids = cv.take<int>(R * kPreBeam); reg("pre_ids", sb.pre_ids, R * kPreBeam);
   sb.psi = cv.take<float>(R * kPreBeam); reg("psi", sb.psi, R * kPreBeam);
@@ -154,6 +161,7 @@ static void carve(Engine& e, Carver& cv) {
   sb.cand_val = cv.take<float>(R * B); sb.cand_tok = cv.take<int>(R * B); sb.cand_dec = cv.take<float>(R * B);
   sb.cand_ctc = cv.take<float>(R * B); sb.cand_psi = cv.take<float>(R * B); sb.cand_col = cv.take<int>(R * B);
   sb.new_parent = cv.take<int>(S * B); sb.new_col = cv.take<int>(S * B); sb.upd_flag = cv.take<int>(S);
+  sb.prof = cv.take<unsigned long long>(8);
   // descriptors
   e.d_fd = cv.take<FrontendDesc>(S); e.d_sd = cv.take<SubDesc>(S); e.d_blk = cv.take<BlockDesc>(k.nb_max);
   e.d_carry_f = cv.take<int>(3 * S); e.d_carry_s = cv.take<int>(3 * S);
@@ -185,6 +193,19 @@ static int linear(Engine& e, const Lin& l, cudaStream_t st) {
 
 #define TRY(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
 
+enum { PROF_NONE = 0, PROF_CTC_PREFIX = 1, PROF_DEC_SELF_ATTN = 2, PROF_DEC_CROSS_ATTN = 3, PROF_DEC_FFN1 = 4,
+       PROF_ENC_FFN1 = 5, PROF_PREBEAM = 6, PROF_ENC_ATTN = 7, PROF_CONV2 = 8, PROF_DEC_FFN2 = 9, PROF_ENC_FFN2 = 10,
+       PROF_CTC_UPDATE = 11 };
+
+// wraps a launch in an event pair when its tag is being profiled
+#define PROF(tag, expr)                                                                  \
+  do {                                                                                   \
+    const bool _p = e.prof_tag == (tag) && e.prof_used + 2 <= (int)e.prof_ev.size();     \
+    if (_p) cudaEventRecord(e.prof_ev[e.prof_used], st);                                 \
+    TRY(expr);                                                                           \
+    if (_p) { cudaEventRecord(e.prof_ev[e.prof_used + 1], st); e.prof_used += 2; }       \
+  } while (0)
+
 // ---------------------------------------------------------------- encoder layers over all blocks of the push
 static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, rows = n_blk * kSlots;
@@ -194,12 +215,13 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
     if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln1w, w.ln1b, e.Nrm16, D, rows, D, nullptr, st));
     else TRY(launch_layernorm(e.X, D, w.ln1w, w.ln1b, e.Nrm, D, rows, D, nullptr, st));
     TRY(linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
-    TRY(launch_enc_attention(e.QKV, e.Att, e.d_blk, n_blk, c.enc_heads, D, st));
+    PROF(PROF_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, e.d_blk, n_blk, c.enc_heads, D, st));
     TRY(linear(e, Lin{e.Att, D, nullptr, w.ow, nullptr, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
     if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
     else TRY(launch_layernorm(e.X, D, w.ln2w, w.ln2b, e.Nrm, D, rows, D, nullptr, st));
-    TRY(linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
-    TRY(linear(e, Lin{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr}, st));
+    if (e.prof_tag == PROF_ENC_FFN1 || e.prof_tag == PROF_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
+    PROF(PROF_ENC_FFN1, linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
+    PROF(PROF_ENC_FFN2, linear(e, Lin{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr}, st));
     TRY(launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, st));
     e.launches += 5;
   }
@@ -218,27 +240,27 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
     if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
     else TRY(launch_layernorm(e.dx, D, w.ln1w, w.ln1b, e.dn, D, R, D, nr, st));
     TRY(linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
-    TRY(launch_dec_attention(sb, 0, l, e.dqkv, 3 * D, e.dqkv + D, 3 * D, e.dattn, st));
+    PROF(PROF_DEC_SELF_ATTN, launch_dec_attention(sb, 0, l, e.dqkv, 3 * D, e.dqkv + D, 3 * D, e.dattn, st));
     TRY(linear(e, Lin{e.dattn, D, nullptr, w.sow, nullptr, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
     if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln2w, w.ln2b, e.dn16, D, R, D, nr, st));
     else TRY(launch_layernorm(e.dx, D, w.ln2w, w.ln2b, e.dn, D, R, D, nr, st));
     TRY(linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
-    TRY(launch_dec_attention(sb, 1, l, e.dq, D, nullptr, 0, e.dattn, st));
+    PROF(PROF_DEC_CROSS_ATTN, launch_dec_attention(sb, 1, l, e.dq, D, nullptr, 0, e.dattn, st));
     TRY(linear(e, Lin{e.dattn, D, nullptr, w.cow, nullptr, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
     if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
     else TRY(launch_layernorm(e.dx, D, w.ln3w, w.ln3b, e.dn, D, R, D, nr, st));
-    TRY(linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
-    TRY(linear(e, Lin{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr}, st));
+    PROF(PROF_DEC_FFN1, linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
+    PROF(PROF_DEC_FFN2, linear(e, Lin{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr}, st));
     e.launches += 5;
   }
   if (tc) TRY(launch_layernorm_bf16(e.dx, D, e.daw, e.dab, e.dn16, D, R, D, nr, st));
   else TRY(launch_layernorm(e.dx, D, e.daw, e.dab, e.dn, D, R, D, nr, st));
   TRY(linear(e, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
-  TRY(launch_logsoftmax_prebeam(sb, e.dlogp, st));
-  TRY(launch_ctc_prefix(sb, st));
+  PROF(PROF_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
+  PROF(PROF_CTC_PREFIX, launch_ctc_prefix(sb, st));
   TRY(launch_combine_topk(sb, e.dlogp, st));
   TRY(launch_beam_prune(sb, st));
-  TRY(launch_ctc_state_update(sb, st));
+  PROF(PROF_CTC_UPDATE, launch_ctc_state_update(sb, st));
   TRY(launch_step_finish(sb, st));
   e.launches += 9;
   return 0;
@@ -291,7 +313,7 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   const size_t S = cfg->n_streams;
   e->h_stage_bytes = sizeof(FrontendDesc) * S + sizeof(SubDesc) * S + sizeof(BlockDesc) * k.nb_max + sizeof(int) * (6 * S) +
                      (sizeof(int64_t) * 3 + sizeof(int)) * S * k.sub_cap + sizeof(int) * (2 * S + 2 * S * k.qcap) + sizeof(int) * S + 4096;
-  if (cudaMallocHost(&e->h_stage, e->h_stage_bytes) != cudaSuccess || cudaMallocHost(&e->h_flag, 2 * sizeof(int)) != cudaSuccess) {
+  if (cudaMallocHost(&e->h_stage, e->h_stage_bytes) != cudaSuccess || cudaMallocHost(&e->h_flag, 4 * sizeof(int)) != cudaSuccess) {
     set_last_error("pinned host allocation failed"); delete e; return SC_ERR_CUDA;
   }
   cudaEventCreateWithFlags(&e->ev[0], cudaEventDisableTiming);
@@ -528,7 +550,13 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     GemmArgs g;
     g.A = e->h1; g.a_row_off = e->d_c2_a; g.a_seg_off = e->d_c2_seg; g.seg_len = D; g.W = e->c2w; g.bias = e->c2b;
     g.C = e->h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
-    TRY(launch_gemm_f32(g, st));
+    {
+      Engine& e_ = *e;
+      const bool _p = e_.prof_tag == PROF_CONV2 && e_.prof_used + 2 <= (int)e_.prof_ev.size();
+      if (_p) { cudaEventRecord(e_.prof_ev[e_.prof_used], st); e_.prof_flops += 2.0 * g.M * (double)g.N * g.K; }
+      TRY(launch_gemm_f32(g, st));
+      if (_p) { cudaEventRecord(e_.prof_ev[e_.prof_used + 1], st); e_.prof_used += 2; }
+    }
     GemmArgs o;
     o.A = e->h2; o.lda = 19 * D; o.W = e->eow; o.bias = e->eob; o.C = e->subbuf; o.c_row_off = e->d_c2_c;
     o.M = sub_rows; o.N = D; o.K = 19 * D;
@@ -564,7 +592,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   int steps = 0;
   TRY(launch_search_begin(e->sb, e->d_q, e->d_q + S, e->d_q + 2 * S, e->d_q + 2 * S + S * k.qcap, n_q, st));
   e->launches += 2;
-  SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[0], e->sb.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[0], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   SCB_CUDA_CHECK(cudaEventRecord(e->ev[0], st));
   if (n_q == 0) {
     SCB_CUDA_CHECK(cudaEventSynchronize(e->ev[0]));
@@ -573,13 +601,17 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     for (int i = 0;; ++i) {
       TRY(run_decode_step(*e, st));
       steps++;
-      SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[(i + 1) & 1], e->sb.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[2 * ((i + 1) & 1)], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
       SCB_CUDA_CHECK(cudaEventRecord(e->ev[(i + 1) & 1], st));
       SCB_CUDA_CHECK(cudaEventSynchronize(e->ev[i & 1]));
-      if (e->h_flag[i & 1] == 0) break;
+      if (e->h_flag[2 * (i & 1)] == 0) break;
       if (steps > 4 * kMaxLength + 64) { set_last_error("decode loop did not terminate"); return SC_ERR_STATE; }
     }
     SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (e->h_flag[1] || e->h_flag[3]) {
+      set_last_error("a hypothesis outgrew the token capacity (%d); raise max_frames", k.Lcap);
+      return SC_ERR_CAPACITY;
+    }
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -600,7 +632,7 @@ int sc_engine_read_beam(void* handle, int32_t s, int32_t max_len, int32_t* n_hyp
   SCB_CUDA_CHECK(cudaMemcpyAsync(&ctl, sb.ctl + s, sizeof(ctl), cudaMemcpyDeviceToHost, st));
   SCB_CUDA_CHECK(cudaStreamSynchronize(st));
   *n_hyp = ctl.n_hyp; *len = ctl.len; *process_idx = ctl.process_idx;
-  if (ctl.len > max_len) { set_last_error("read_beam: max_len %d < len %d", max_len, ctl.len); return SC_ERR_ARG; }
+  if (ctl.len > max_len || ctl.len > sb.Lcap) { set_last_error("read_beam: max_len %d < len %d", max_len, ctl.len); return SC_ERR_ARG; }
   for (int h = 0; h < ctl.n_hyp; ++h) {
     const size_t o = (((size_t)ctl.cur * sb.S + s) * sb.B + h);
     SCB_CUDA_CHECK(cudaMemcpyAsync(yseq + (size_t)h * max_len, sb.yseq + o * sb.Lcap, ctl.len * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -624,6 +656,36 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
   auto it = e->named.find(name);
   if (it == e->named.end()) { set_last_error("unknown buffer %s", name); return SC_ERR_ARG; }
   *ptr = it->second.first; *n_elem = it->second.second;
+  return SC_OK;
+}
+
+// ---------------- live kernel timing
+int sc_engine_profile_begin(void* handle, int32_t tag, int32_t max_launches) {
+  Engine* e = (Engine*)handle;
+  if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
+  while ((int)e->prof_ev.size() < 2 * max_launches) {
+    cudaEvent_t ev;
+    SCB_CUDA_CHECK(cudaEventCreate(&ev));
+    e->prof_ev.push_back(ev);
+  }
+  e->prof_tag = tag; e->prof_used = 0; e->prof_flops = 0.0;
+  SCB_CUDA_CHECK(cudaMemset(e->sb.prof, 0, 8 * sizeof(unsigned long long)));
+  return SC_OK;
+}
+
+int sc_engine_profile_end(void* handle, int32_t* n_launches, double* total_ms, double* host_flops, uint64_t* counters8) {
+  Engine* e = (Engine*)handle;
+  if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
+  SCB_CUDA_CHECK(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (int i = 0; i + 1 < e->prof_used; i += 2) {
+    float t = 0.f;
+    SCB_CUDA_CHECK(cudaEventElapsedTime(&t, e->prof_ev[i], e->prof_ev[i + 1]));
+    ms += t;
+  }
+  *n_launches = e->prof_used / 2; *total_ms = ms; *host_flops = e->prof_flops;
+  SCB_CUDA_CHECK(cudaMemcpy(counters8, e->sb.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  e->prof_tag = 0;
   return SC_OK;
 }
 

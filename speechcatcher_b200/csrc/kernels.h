@@ -159,6 +159,8 @@ struct SearchBuffers {
   int* new_parent;        // [S][B] parent slot of each new hypothesis (this step)
   int* new_col;           // [S][B]
   int* upd_flag;          // [S] 1 -> the CTC state of the new beam must be written this step
+  unsigned long long* prof;   // [8] device counters: 0 ctc algorithmic bytes, 1 sum of active rows,
+                              //     2 cross-attention KV bytes, 3 self-attention KV bytes, 4 search iterations
 };
 
 int launch_search_reset(const SearchBuffers& sb, const int* streams, int n, cudaStream_t st);

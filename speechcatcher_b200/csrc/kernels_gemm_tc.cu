@@ -1,9 +1,312 @@
-// bf16 tensor-core GEMM (tcgen05 + TMEM + TMA) -- placeholder until the tcgen05 kernel lands.
+// bf16 tensor-core GEMM for sm_100a: C = act(A * W^T + bias) + R, fp32 accumulation in TMEM.
+//
+//   * operands: A [M][K] and W [N][K], both K-major bf16, staged by TMA (cp.async.bulk.tensor.2d,
+//     128-byte swizzle) into a 4-stage shared-memory ring;
+//   * math: tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, issued by one elected thread,
+//     accumulator (128 lanes x BN fp32 columns) lives in tensor memory;
+//   * epilogue: four warps read their TMEM lane quarter with tcgen05.ld (32x32b), fuse bias / ReLU /
+//     residual and write fp32 and/or bf16 rows (optionally scattered through a row-offset table);
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//
+// This is the bf16 counterpart of every torch.nn.functional.linear on the hot path
+// (speechcatcher/model/attention/multi_head_attention.py:79-83,133, layers/feed_forward.py:50,
+//  decoder/transformer_decoder.py:249, ctc.py:40).
+#include <cuda.h>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "kernels.h"
+
 namespace scb {
-int launch_gemm_bf16(const __nv_bfloat16*, int, const __nv_bfloat16*, const float*, const float*, int, float*, int,
-                     __nv_bfloat16*, int, int, int, int, int, const int*, cudaStream_t) {
-  set_last_error("bf16 tensor-core GEMM is not built in this revision");
-  return -1;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int UMMA_K = 16;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between row groups), [46,48) version = 1,
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcParams {
+  const float* bias; const float* R; int ldr; float* C; int ldc; __nv_bfloat16* Cb; int ldcb;
+  const int64_t* c_row_off; int M, N, K, relu; const int* n_rows_dev;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                     const __grid_constant__ CUtensorMap map_b,
+                                                                     TcParams p) {
+  int M = p.M;
+  if (p.n_rows_dev) M = min(M, *p.n_rows_dev);
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  if (m0 >= M) return;                       // uniform for the whole CTA, before any barrier / allocation
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + TC_STAGES * A_BYTES;
+  uint64_t* full_bar = (uint64_t*)(sB + TC_STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                           // TMEM allocation: BN fp32 columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        tma_load_2d(&map_a, &full_bar[s], sA + s * A_BYTES, kb * TC_BK, m0);
+        tma_load_2d(&map_b, &full_bar[s], sB + s * B_BYTES, kb * TC_BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(smem_u32(sA + s * A_BYTES));
+        const uint64_t db = make_smem_desc(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < TC_BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);           // frees the smem stage once the MMAs have read it
+      }
+      umma_commit(tmem_full);                 // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < M;
+    float* crow = nullptr;
+    __nv_bfloat16* cbrow = nullptr;
+    const float* rrow = nullptr;
+    if (row_ok) {
+      if (p.C) crow = p.c_row_off ? p.C + p.c_row_off[m] : p.C + (size_t)m * p.ldc;
+      if (p.Cb) cbrow = p.c_row_off ? p.Cb + p.c_row_off[m] : p.Cb + (size_t)m * p.ldcb;
+      if (p.R) rrow = p.R + (size_t)m * p.ldr;
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (row_ok) {
+        const int n = n0 + c0;
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (p.bias) x += __ldg(p.bias + n + j);
+          if (p.relu) x = fmaxf(x, 0.f);
+          o[j] = x;
+        }
+        if (rrow) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 r4 = *reinterpret_cast<const float4*>(rrow + n + j);
+            o[j] += r4.x; o[j + 1] += r4.y; o[j + 2] += r4.z; o[j + 3] += r4.w;
+          }
+        }
+        if (crow) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(crow + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+        if (cbrow) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o[j], o[j + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(cbrow + n + j) = u;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+// ---------------------------------------------------------------- host: tensor maps + launch
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::mutex g_map_mu;
+static std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
+
+static int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      set_last_error("cuTensorMapEncodeTiled entry point not found");
+      return -1;
+    }
+    g_encode = (PFN_encodeTiled)fn;
+  }
+  auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return 0; }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return -1; }
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = m;
+  *out = m;
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = 1024 + TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(smem=%zu) failed", smem);
+      return -1;
+    }
+    attr_set = true;
+  }
+  dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
+  gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
+                        int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
+                        int K, int relu, const int* n_rows_dev, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  if (K % TC_BK != 0 || N % 64 != 0 || lda % 8 != 0) {
+    set_last_error("gemm_bf16: unsupported shape M=%d N=%d K=%d lda=%d", M, N, K, lda);
+    return -1;
+  }
+  const bool small = (N % 128 != 0) || ((long)cdiv(M, TC_BM) * (N / 128) < kNumSMs);
+  const int BN = small ? 64 : 128;
+  CUtensorMap ma, mb;
+  if (get_map(A, M, K, lda, TC_BM, &ma)) return -1;
+  if (get_map(W, N, K, K, BN, &mb)) return -1;
+  TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev};
+  return small ? launch_bn<64>(ma, mb, p, st) : launch_bn<128>(ma, mb, p, st);
+}
+
+int launch_gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
+                     int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int K, int relu,
+                     const int* n_rows_dev, cudaStream_t st) {
+  return launch_gemm_bf16_ex(A, lda, W, bias, R, ldr, C, ldc, Cb, ldcb, nullptr, M, N, K, relu, n_rows_dev, st);
+}
+
 }  // namespace scb

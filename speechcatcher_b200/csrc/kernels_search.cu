@@ -34,6 +34,7 @@ __global__ void search_reset_kernel(SearchBuffers sb, const int* __restrict__ st
     sb.xpos[o * sb.Lcap] = 0;
     sb.score[o] = 0.0; sb.sc_dec[o] = 0.0; sb.sc_ctc[o] = 0.0;
     sb.ctc_s[o] = 0.f;
+    if (i == 0) sb.n_active[1] = 0;            // clear the capacity-error flag
   }
 }
 
@@ -158,7 +159,10 @@ __global__ void compact_rows_kernel(SearchBuffers sb) {
     if (threadIdx.x == blockDim.x - 1) { s_base += incl; s_nact += s_scan[threadIdx.x]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { *sb.n_rows = s_base; *sb.n_active = s_nact; }
+  if (threadIdx.x == 0) {
+    *sb.n_rows = s_base; *sb.n_active = s_nact;
+    if (s_base > 0) { atomicAdd(&sb.prof[1], (unsigned long long)s_base); atomicAdd(&sb.prof[4], 1ull); }
+  }
 }
 
 int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int* q_n, const int* q_T,
@@ -224,6 +228,8 @@ __global__ void __launch_bounds__(128) dec_attention_kernel(SearchBuffers sb, in
   for (int i = tid; i < nb * DK; i += blockDim.x) qs[i] = q[(size_t)(row0 + i / DK) * ldq + head * DK + i % DK];
   if (tid < AMAXB) { sm_m[tid] = -INFINITY; sm_l[tid] = 0.f; }
   const size_t row_stride = 2 * (size_t)D;                  // K|V row
+  if (tid == 0)   // cross K|V read once per stream, self K|V once per hypothesis
+    atomicAdd(&sb.prof[mode == 1 ? 2 : 3], (unsigned long long)((mode == 1 ? 1 : nb) * 2ll * npos * DK * 4));
   const float* base;
   if (mode == 0) {
     float* store = sb.skv + ((size_t)layer * sb.S + s) * sb.Lcap * sb.B * row_stride;
@@ -479,6 +485,8 @@ __global__ void __launch_bounds__(64) ctc_prefix_kernel(SearchBuffers sb) {
   const int L = c.len - 1, T = c.Tb;
   const int last = sb.yseq[beam_off(sb, c.cur, s, h) * sb.Lcap + c.len - 1];
   const int k = threadIdx.x;
+  if (k == kPreBeam + 1)   // algorithmic bytes of one row = 4*T*(3K+2) + 4*V
+    atomicAdd(&sb.prof[0], (unsigned long long)(4ll * T * (3 * kPreBeam + 2) + 4ll * sb.V));
   if (k < kPreBeam) {
     const int tok = sb.pre_ids[(size_t)r * kPreBeam + k];
     float psi;
@@ -718,6 +726,9 @@ __global__ void __launch_bounds__(64) step_commit_kernel(SearchBuffers sb) {
       const bool rewind = c.process_idx > 1 && c.iters_done >= 1;         // beam_search.py:827-836
       if (rewind) c.process_idx -= 1;                                     // beam = snapshot = current buffer
       else if (outcome == OUT_BREAK_NEW) { c.cur ^= 1; c.len += 1; c.n_hyp = sb.B; c.ctc_T = c.Tb; c.has_ctc = 1; }
+    }
+    if (c.len >= sb.Lcap - 1) {       // token capacity reached: stop this stream and raise the error flag
+      c.blk_next = c.blk_count; ended = 1; sb.n_active[1] = 1;
     }
   }
   __syncthreads();

@@ -154,15 +154,25 @@ class StreamGroup:
             self._wave_dev.copy_(host, non_blocking=True)
         return self.push_device(ids, self._wave_dev, lens, fin)
 
-    def push_device(self, ids: np.ndarray, wave_dev: torch.Tensor, lens: np.ndarray, fin: np.ndarray) -> ScPushStats:
-        """Same, with the waveforms already resident: wave_dev[s, :lens[i]] for s = ids[i]."""
+    def push_batch(self, ids: np.ndarray, wave_host: torch.Tensor, lens: np.ndarray, fin: np.ndarray) -> ScPushStats:
+        """Host waveforms as one [n_streams, L] float32 tensor (row s = stream s); one pinned H2D copy."""
+        L = wave_host.shape[1]
+        if L > self.max_chunk:
+            raise ValueError(f"chunk of {L} samples exceeds max_chunk={self.max_chunk}")
+        with torch.cuda.device(self.device):
+            self._wave_dev[:, :L].copy_(wave_host, non_blocking=True)
+        return self.push_device(ids, self._wave_dev, lens, fin)
+
+    def push_device(self, ids: np.ndarray, wave_dev: torch.Tensor, lens: np.ndarray, fin: np.ndarray,
+                    col_offset: int = 0) -> ScPushStats:
+        """Same, with the waveforms already resident: wave_dev[s, col_offset : col_offset+lens[i]] for s = ids[i]."""
         assert wave_dev.dtype == torch.float32 and wave_dev.is_contiguous() and wave_dev.shape[0] == self.n_streams
         ids = np.ascontiguousarray(ids, np.int32)
         lens = np.ascontiguousarray(lens, np.int32)
         fin = np.ascontiguousarray(fin, np.int32)
         st = ScPushStats()
         with torch.cuda.device(self.device):
-            rc = self.lib.sc_engine_push(self.handle, C.c_void_p(wave_dev.data_ptr()), wave_dev.shape[1],
+            rc = self.lib.sc_engine_push(self.handle, C.c_void_p(wave_dev.data_ptr() + 4 * col_offset), wave_dev.shape[1],
                                          ids.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
                                          fin.ctypes.data_as(C.c_void_p), len(ids),
                                          C.c_void_p(self.stream.cuda_stream), C.byref(st))
@@ -174,7 +184,7 @@ class StreamGroup:
     # ------------------------------------------------------------------ results
     def beam(self, stream: int) -> Tuple[List[List[int]], List[float], List[List[int]], int]:
         """(yseq per hyp, fp64 scores, xpos per hyp, process_idx) of the running hypotheses."""
-        L = 512
+        L = 1024
         yseq = np.zeros((self.beam_size, L), np.int32)
         xpos = np.zeros((self.beam_size, L), np.int32)
         score = np.zeros(self.beam_size, np.float64)
@@ -187,6 +197,45 @@ class StreamGroup:
         n, l = n_hyp.value, ln.value
         return ([yseq[h, :l].tolist() for h in range(n)], score[:n].tolist(),
                 [xpos[h, :l].tolist() for h in range(n)], pidx.value)
+
+    # ------------------------------------------------------------------ live kernel timing (bench.py roofline)
+    PROF_TAGS = {"ctc_prefix": 1, "dec_self_attn": 2, "dec_cross_attn": 3, "dec_ffn1": 4, "enc_ffn1": 5, "prebeam": 6,
+                 "enc_attn": 7, "conv2": 8, "dec_ffn2": 9, "enc_ffn2": 10, "ctc_state_update": 11}
+
+    def profile_begin(self, kernel: str = "auto", max_launches: int = 60000) -> str:
+        if kernel == "auto":
+            kernel = "dec_cross_attn"
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sc_engine_profile_begin(self.handle, self.PROF_TAGS[kernel], max_launches), "profile_begin")
+        return kernel
+
+    def profile_end(self, kernel: str) -> dict:
+        """Roofline object for bench.py: algorithmic bytes (or FLOPs) of the tagged kernel's launches divided by
+        their CUDA-event time, against the measured peak in MEASURED_PEAKS.json (else the recipe's fallback)."""
+        import json
+        n, ms, fl = C.c_int32(), C.c_double(), C.c_double()
+        cnt = (C.c_uint64 * 8)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sc_engine_profile_end(self.handle, C.byref(n), C.byref(ms), C.byref(fl), cnt), "profile_end")
+        peaks_path = Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"
+        peaks, src = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+        if peaks_path.exists():
+            peaks, src = json.load(open(peaks_path)), "measured"
+        D, F = self.cfg.d_model, self.cfg.ffn
+        sec = max(ms.value, 1e-9) / 1e3
+        hbm = {"ctc_prefix": cnt[0], "dec_cross_attn": cnt[2], "dec_self_attn": cnt[3]}
+        if kernel in hbm:
+            ach = hbm[kernel] / sec / 1e9
+            peak = float(peaks["hbm_gbs"])
+            out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+        else:
+            flops = fl.value if kernel in ("enc_ffn1", "enc_ffn2", "conv2") else 2.0 * cnt[1] * F * D
+            ach = flops / sec / 1e12
+            peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+            out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+        out.update({"kernel": kernel, "launches": n.value, "kernel_ms_total": ms.value, "peak_source": src,
+                    "traffic": None, "search_iterations": int(cnt[4]), "active_rows_total": int(cnt[1])})
+        return out
 
     def last_plan(self, stream: int) -> ScStreamPlan:
         p = ScStreamPlan()

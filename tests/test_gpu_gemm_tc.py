@@ -1,0 +1,51 @@
+"""GPU: the tcgen05/TMEM/TMA bf16 GEMM (sc_linear_bf16) against a plain PyTorch fp32 reference of the
+same op on the same bf16-rounded operands.  Tolerance: fp32 accumulation order only (2e-3 relative to
+the row scale), bf16 output additionally rounds to 8 bits of mantissa."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # (M, N, K, relu, residual, bf16_out)
+    (128, 128, 64, 0, False, False),
+    (128, 128, 256, 0, False, False),
+    (256, 256, 256, 0, False, False),
+    (300, 768, 256, 0, False, False),       # ragged M, QKV shape
+    (2560, 256, 256, 0, True, False),       # decoder projections with residual
+    (2560, 2048, 256, 1, False, True),      # FFN1: ReLU + bf16 output
+    (2560, 256, 2048, 0, True, False),      # FFN2
+    (10752, 2048, 256, 1, False, True),     # encoder FFN1 at 256 streams x 1 block
+    (10752, 256, 2048, 0, True, False),
+    (77, 1024, 256, 0, False, False),       # output layer, small M
+    (640, 512, 256, 0, False, False),       # cross K|V
+    (3000, 256, 4864, 0, False, False),     # embed.out
+]
+
+
+@pytest.mark.parametrize("M,N,K,relu,res,bf16_out", SHAPES)
+def test_linear_bf16_matches_fp32_reference(M, N, K, relu, res, bf16_out):
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, generator=g, device="cuda")).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda")
+    r = torch.randn(M, N, generator=g, device="cuda")
+    y = r.clone() if res else torch.full((M, N), float("nan"), device="cuda")
+    y16 = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda") if bf16_out else None
+    _lib.check(lib.sc_linear_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr() if res else None,
+                                  y.data_ptr(), y16.data_ptr() if bf16_out else None, M, N, K, relu, None), "linear_bf16")
+    torch.cuda.synchronize()
+    want = a.float() @ w.float().t() + bias
+    if relu:
+        want = want.relu()
+    if res:
+        want = want + r
+    err = (y - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert np.isfinite(err) and err <= 2e-3 * max(1.0, scale), f"max err {err} (scale {scale})"
+    if bf16_out:
+        err16 = (y16.float() - want).abs().max().item()
+        assert err16 <= 1e-2 * max(1.0, scale)
