@@ -17,6 +17,9 @@ namespace scb {
 int launch_gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
                      int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int K, int relu,
                      const int* n_rows_dev, cudaStream_t st);
+int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
+                        int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
+                        int K, int relu, const int* n_rows_dev, cudaStream_t st);
 
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -177,17 +180,19 @@ static void carve(Engine& e, Carver& cv) {
 struct Lin {
   const float* A; int lda; const __nv_bfloat16* A16; const float* W; const __nv_bfloat16* W16; const float* bias;
   const float* R; int ldr; float* C; int ldc; __nv_bfloat16* C16; int M, N, K, relu; const int* n_rows_dev;
+  const int64_t* c_row_off = nullptr;
 };
 
 static int linear(Engine& e, const Lin& l, cudaStream_t st) {
   e.launches++;
-  if (e.cfg.precision == 1 && l.A16 && l.W16) {
-    return launch_gemm_bf16(l.A16, l.lda, l.W16, l.bias, l.R, l.ldr, l.C, l.ldc, l.C16, l.ldc, l.M, l.N, l.K,
-                            l.relu, l.n_rows_dev, st);
+  if (e.cfg.precision == 1) {
+    if (!l.A16 || !l.W16) { set_last_error("bf16 mode: missing bf16 operand for a %dx%dx%d linear", l.M, l.N, l.K); return -1; }
+    return launch_gemm_bf16_ex(l.A16, l.lda, l.W16, l.bias, l.R, l.ldr, l.C, l.ldc, l.C16, l.ldc, l.c_row_off, l.M, l.N,
+                               l.K, l.relu, l.n_rows_dev, st);
   }
   GemmArgs g;
   g.A = l.A; g.lda = l.lda; g.W = l.W; g.bias = l.bias; g.R = l.R; g.ldr = l.ldr; g.C = l.C; g.ldc = l.ldc;
-  g.M = l.M; g.N = l.N; g.K = l.K; g.relu = l.relu; g.n_rows_dev = l.n_rows_dev;
+  g.M = l.M; g.N = l.N; g.K = l.K; g.relu = l.relu; g.n_rows_dev = l.n_rows_dev; g.c_row_off = l.c_row_off;
   return launch_gemm_f32(g, st);
 }
 
@@ -215,12 +220,12 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
     if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln1w, w.ln1b, e.Nrm16, D, rows, D, nullptr, st));
     else TRY(launch_layernorm(e.X, D, w.ln1w, w.ln1b, e.Nrm, D, rows, D, nullptr, st));
     TRY(linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
-    PROF(PROF_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, e.d_blk, n_blk, c.enc_heads, D, st));
-    TRY(linear(e, Lin{e.Att, D, nullptr, w.ow, nullptr, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
+    PROF(PROF_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
+    TRY(linear(e, Lin{e.Att, D, e.Att16, w.ow, w.ow16, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
     if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
     else TRY(launch_layernorm(e.X, D, w.ln2w, w.ln2b, e.Nrm, D, rows, D, nullptr, st));
     if (e.prof_tag == PROF_ENC_FFN1 || e.prof_tag == PROF_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
-    PROF(PROF_ENC_FFN1, linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
+    PROF(PROF_ENC_FFN1, linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
     PROF(PROF_ENC_FFN2, linear(e, Lin{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr}, st));
     TRY(launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, st));
     e.launches += 5;
@@ -240,16 +245,16 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
     if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
     else TRY(launch_layernorm(e.dx, D, w.ln1w, w.ln1b, e.dn, D, R, D, nr, st));
     TRY(linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
-    PROF(PROF_DEC_SELF_ATTN, launch_dec_attention(sb, 0, l, e.dqkv, 3 * D, e.dqkv + D, 3 * D, e.dattn, st));
-    TRY(linear(e, Lin{e.dattn, D, nullptr, w.sow, nullptr, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
+    PROF(PROF_DEC_SELF_ATTN, launch_dec_attention(sb, 0, l, e.dqkv, 3 * D, e.dqkv + D, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
+    TRY(linear(e, Lin{e.dattn, D, e.dattn16, w.sow, w.sow16, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
     if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln2w, w.ln2b, e.dn16, D, R, D, nr, st));
     else TRY(launch_layernorm(e.dx, D, w.ln2w, w.ln2b, e.dn, D, R, D, nr, st));
     TRY(linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
-    PROF(PROF_DEC_CROSS_ATTN, launch_dec_attention(sb, 1, l, e.dq, D, nullptr, 0, e.dattn, st));
-    TRY(linear(e, Lin{e.dattn, D, nullptr, w.cow, nullptr, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
+    PROF(PROF_DEC_CROSS_ATTN, launch_dec_attention(sb, 1, l, e.dq, D, nullptr, 0, e.dattn, tc ? e.dattn16 : nullptr, st));
+    TRY(linear(e, Lin{e.dattn, D, e.dattn16, w.cow, w.cow16, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
     if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
     else TRY(launch_layernorm(e.dx, D, w.ln3w, w.ln3b, e.dn, D, R, D, nr, st));
-    PROF(PROF_DEC_FFN1, linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
+    PROF(PROF_DEC_FFN1, linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
     PROF(PROF_DEC_FFN2, linear(e, Lin{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr}, st));
     e.launches += 5;
   }
@@ -501,6 +506,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     for (auto b : p.blocks) {
       if ((int)n_blk >= k.nb_max) { set_last_error("block capacity exceeded"); return SC_ERR_CAPACITY; }
       if (b.prev_blk >= 0) b.prev_blk += blk0;
+      b.out_row0 = n_en + (b.out_t0 - p.enc_t0);
       h_blk[n_blk++] = b;
     }
     for (int t = 0; t < p.n_enc_out; ++t) {
@@ -550,6 +556,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     GemmArgs g;
     g.A = e->h1; g.a_row_off = e->d_c2_a; g.a_seg_off = e->d_c2_seg; g.seg_len = D; g.W = e->c2w; g.bias = e->c2b;
     g.C = e->h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
+    if (tc) { g.Cb = e->h2_16; g.ldcb = D; }
     {
       Engine& e_ = *e;
       const bool _p = e_.prof_tag == PROF_CONV2 && e_.prof_used + 2 <= (int)e_.prof_ev.size();
@@ -557,10 +564,11 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
       TRY(launch_gemm_f32(g, st));
       if (_p) { cudaEventRecord(e_.prof_ev[e_.prof_used + 1], st); e_.prof_used += 2; }
     }
-    GemmArgs o;
-    o.A = e->h2; o.lda = 19 * D; o.W = e->eow; o.bias = e->eob; o.C = e->subbuf; o.c_row_off = e->d_c2_c;
-    o.M = sub_rows; o.N = D; o.K = 19 * D;
-    TRY(launch_gemm_f32(o, st));
+    {
+      Lin o{e->h2, 19 * D, e->h2_16, e->eow, e->eow16, e->eob, nullptr, 0, e->subbuf, 0, nullptr, sub_rows, D, 19 * D, 0, nullptr};
+      o.c_row_off = e->d_c2_c;
+      TRY(linear(*e, o, st));
+    }
     e->launches += 4;
   }
   if (n_cf) { TRY(launch_carry_rows(e->featbuf, k.feat_cap, 80, e->d_carry_f, e->d_carry_f + S, e->d_carry_f + 2 * S, n_cf, st)); e->launches++; }
@@ -568,22 +576,35 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   if (n_blk > 0) {
     TRY(launch_block_assemble(e->subbuf, k.sub_cap, e->pe, e->d_blk, n_blk, e->addin, e->prev_addin, e->X, D, st));
     TRY(run_encoder_layers(*e, n_blk, st));
-    TRY(launch_stitch_norm(e->X, e->d_blk, n_blk, e->eaw, e->eab, e->encbuf, k.Tcap, D, st));
+    TRY(launch_stitch_norm(e->X, e->d_blk, n_blk, e->eaw, e->eab, e->encbuf, k.Tcap, D, tc ? e->encnew16 : nullptr, st));
     e->launches += 4;
   }
   if (n_cs) { TRY(launch_carry_rows(e->subbuf, k.sub_cap, D, e->d_carry_s, e->d_carry_s + S, e->d_carry_s + 2 * S, n_cs, st)); e->launches++; }
   // ---------------- CTC head + cross-attention K|V for the new encoder frames
   if (n_en > 0) {
-    GemmArgs g;
-    g.A = e->encbuf; g.a_row_off = e->d_en_a; g.W = e->ctcw; g.bias = e->ctcb; g.C = e->ctcx; g.c_row_off = e->d_en_ctc;
-    g.M = n_en; g.N = V; g.K = D;
-    TRY(launch_gemm_f32(g, st));
+    if (tc) {
+      Lin g{nullptr, D, e->encnew16, e->ctcw, e->ctcw16, e->ctcb, nullptr, 0, e->ctcx, 0, nullptr, n_en, V, D, 0, nullptr};
+      g.c_row_off = e->d_en_ctc;
+      TRY(linear(*e, g, st));
+    } else {
+      GemmArgs g;
+      g.A = e->encbuf; g.a_row_off = e->d_en_a; g.W = e->ctcw; g.bias = e->ctcb; g.C = e->ctcx; g.c_row_off = e->d_en_ctc;
+      g.M = n_en; g.N = V; g.K = D;
+      TRY(launch_gemm_f32(g, st));
+    }
     TRY(launch_logsoftmax_rows(e->ctcx, e->d_en_ctc, e->d_en_flag, n_en, V, st));
     for (int l = 0; l < c.dec_layers; ++l) {
-      GemmArgs kv;
-      kv.A = e->encbuf; kv.a_row_off = e->d_en_a; kv.W = e->dec[l].ckvw; kv.bias = e->dec[l].ckvb;
-      kv.C = e->sb.xkv + (size_t)l * S * k.Tcap * 2 * D; kv.c_row_off = e->d_en_kv; kv.M = n_en; kv.N = 2 * D; kv.K = D;
-      TRY(launch_gemm_f32(kv, st));
+      float* dst = e->sb.xkv + (size_t)l * S * k.Tcap * 2 * D;
+      if (tc) {
+        Lin kv{nullptr, D, e->encnew16, e->dec[l].ckvw, e->dec[l].ckvw16, e->dec[l].ckvb, nullptr, 0, dst, 0, nullptr, n_en, 2 * D, D, 0, nullptr};
+        kv.c_row_off = e->d_en_kv;
+        TRY(linear(*e, kv, st));
+      } else {
+        GemmArgs kv;
+        kv.A = e->encbuf; kv.a_row_off = e->d_en_a; kv.W = e->dec[l].ckvw; kv.bias = e->dec[l].ckvb;
+        kv.C = dst; kv.c_row_off = e->d_en_kv; kv.M = n_en; kv.N = 2 * D; kv.K = D;
+        TRY(launch_gemm_f32(kv, st));
+      }
     }
     e->launches += 2 + c.dec_layers;
   }

@@ -36,6 +36,8 @@ struct BlockDesc {
   int n_rows;        // rows that take part in attention: 42, or T for the short path
   int short_path;    // 1: no mask, no context slots
   int has_past_ctx;  // stream carries past_encoder_ctx from an earlier call
+  int out_row0;      // dense index (over all streams of the push) of the block's first emitted frame
+  int pad_;
 };
 
 // ---------------------------------------------------------------- elementwise
@@ -62,6 +64,8 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0;
   int relu = 0;
   const int* n_rows_dev = nullptr;     // optional dynamic M (device scalar)
+  __nv_bfloat16* Cb = nullptr;         // optional bf16 copy of the output, dense [M][ldcb]
+  int ldcb = 0;
 };
 int launch_gemm_f32(const GemmArgs& g, cudaStream_t st);
 
@@ -93,12 +97,12 @@ int launch_carry_rows(float* buf, int cap, int width, const int* stream, const i
                       int n_desc, cudaStream_t st);
 int launch_block_assemble(const float* subbuf, int sub_cap, const float* pe, const BlockDesc* blk, int n_blk,
                           float* addin, float* prev_addin, float* X, int D, cudaStream_t st);
-int launch_enc_attention(const float* qkv, float* out, const BlockDesc* blk, int n_blk, int n_head, int d_model,
-                         cudaStream_t st);
+int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
+                         int n_head, int d_model, cudaStream_t st);
 int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const BlockDesc* blk, int n_blk,
                         int D, cudaStream_t st);
 int launch_stitch_norm(const float* X, const BlockDesc* blk, int n_blk, const float* w, const float* b,
-                       float* encbuf, int t_cap, int D, cudaStream_t st);
+                       float* encbuf, int t_cap, int D, __nv_bfloat16* dense16, cudaStream_t st);
 
 // ---------------------------------------------------------------- decoder / search
 struct StreamCtl {     // per-stream search state that lives on the device
@@ -170,7 +174,7 @@ int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int*
 int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, cudaStream_t st);
 // mode 0: self attention over the tree KV store (appends this step's K|V first); mode 1: cross attention
 int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
-                         const float* kv_new, int ldkv, float* out, cudaStream_t st);
+                         const float* kv_new, int ldkv, float* out, __nv_bfloat16* out16, cudaStream_t st);
 int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st);
 int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st);
 int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st);

@@ -170,6 +170,7 @@ int launch_block_assemble(const float* subbuf, int sub_cap, const float* pe, con
 // overwritten by the context hand-over; key 41 is never visible).  Short path: rows 0..T-1, no mask.
 template <int DK>
 __global__ void __launch_bounds__(128) enc_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                            __nv_bfloat16* __restrict__ out16,
                                                             const BlockDesc* __restrict__ blk, int D) {
   const BlockDesc b = blk[blockIdx.x];
   const int head = blockIdx.y;
@@ -215,16 +216,17 @@ __global__ void __launch_bounds__(128) enc_attention_kernel(const float* __restr
     if (qi >= q_lo && qi < q_hi)
       for (int ki = k_lo; ki < k_hi; ++ki) acc = fmaf(P[qi][ki], Vv[ki][c], acc);
     obase[(size_t)qi * D + c] = acc;     // rows outside [q_lo, q_hi) get 0 (fully masked rows)
+    if (out16) out16[((size_t)blockIdx.x * kSlots + qi) * D + head * DK + c] = __float2bfloat16(acc);
   }
 }
 
-int launch_enc_attention(const float* qkv, float* out, const BlockDesc* blk, int n_blk, int n_head, int d_model,
-                         cudaStream_t st) {
+int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
+                         int n_head, int d_model, cudaStream_t st) {
   if (n_blk <= 0) return 0;
   dim3 grid(n_blk, n_head);
   int dk = d_model / n_head;
-  if (dk == 32) enc_attention_kernel<32><<<grid, 128, 0, st>>>(qkv, out, blk, d_model);
-  else if (dk == 64) enc_attention_kernel<64><<<grid, 128, 0, st>>>(qkv, out, blk, d_model);
+  if (dk == 32) enc_attention_kernel<32><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model);
+  else if (dk == 64) enc_attention_kernel<64><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model);
   else { set_last_error("enc_attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;
@@ -263,7 +265,8 @@ int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const
 // One warp per emitted frame: LayerNorm of X[blk][slot] -> encbuf[stream][t].
 __global__ void stitch_norm_kernel(const float* __restrict__ X, const BlockDesc* __restrict__ blk,
                                    const float* __restrict__ w, const float* __restrict__ bb,
-                                   float* __restrict__ encbuf, int t_cap, int D) {
+                                   float* __restrict__ encbuf, int t_cap, int D,
+                                   __nv_bfloat16* __restrict__ dense16) {
   const BlockDesc b = blk[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int r = warp; r < b.out_count; r += nwarp) {
@@ -280,14 +283,19 @@ __global__ void stitch_norm_kernel(const float* __restrict__ X, const BlockDesc*
     float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + 1e-12f);
     float* yr = encbuf + ((size_t)b.stream * t_cap + b.out_t0 + r) * D;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) if (i < nv) { int c = lane + 32 * i; yr[c] = (v[i] - mean) * rstd * w[c] + bb[c]; }
+    for (int i = 0; i < 16; ++i) if (i < nv) {
+      int c = lane + 32 * i;
+      float o = (v[i] - mean) * rstd * w[c] + bb[c];
+      yr[c] = o;
+      if (dense16) dense16[(size_t)(b.out_row0 + r) * D + c] = __float2bfloat16(o);
+    }
   }
 }
 
 int launch_stitch_norm(const float* X, const BlockDesc* blk, int n_blk, const float* w, const float* b,
-                       float* encbuf, int t_cap, int D, cudaStream_t st) {
+                       float* encbuf, int t_cap, int D, __nv_bfloat16* dense16, cudaStream_t st) {
   if (n_blk <= 0) return 0;
-  stitch_norm_kernel<<<n_blk, 256, 0, st>>>(X, blk, w, b, encbuf, t_cap, D);
+  stitch_norm_kernel<<<n_blk, 256, 0, st>>>(X, blk, w, b, encbuf, t_cap, D, dense16);
   SCB_LAUNCH_CHECK();
   return 0;
 }

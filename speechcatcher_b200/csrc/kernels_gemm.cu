@@ -83,7 +83,7 @@ constexpr int GBM = 64, GBN = 64, GBK = 16;
 struct GemmParams {
   const float* A; int lda; const int64_t* a_row_off; const int* a_seg_off; int seg_len;
   const float* W; const float* bias; const float* R; int ldr; float* C; int ldc;
-  const int64_t* c_row_off; int M, N, K, relu; const int* n_rows_dev;
+  const int64_t* c_row_off; int M, N, K, relu; const int* n_rows_dev; __nv_bfloat16* Cb; int ldcb;
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
@@ -165,6 +165,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
       }
       *reinterpret_cast<float4*>(crow + n) = o;
+      if (p.Cb) {
+        __nv_bfloat16* cb = p.Cb + (size_t)m * p.ldcb + n;
+        cb[0] = __float2bfloat16(o.x); cb[1] = __float2bfloat16(o.y); cb[2] = __float2bfloat16(o.z); cb[3] = __float2bfloat16(o.w);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -187,7 +191,7 @@ int launch_gemm_f32(const GemmArgs& g, cudaStream_t st) {
   }
   if (g.N % 4 != 0) { set_last_error("gemm_f32: N=%d must be a multiple of 4", g.N); return -1; }
   GemmParams p{g.A, g.lda, g.a_row_off, g.a_seg_off, g.seg_len, g.W, g.bias, g.R, g.ldr, g.C, g.ldc,
-               g.c_row_off, g.M, g.N, g.K, g.relu, g.n_rows_dev};
+               g.c_row_off, g.M, g.N, g.K, g.relu, g.n_rows_dev, g.Cb, g.ldcb};
   dim3 grid(cdiv(g.N, GBN), cdiv(g.M, GBM));
   gemm_f32_kernel<<<grid, 256, 0, st>>>(p);
   SCB_LAUNCH_CHECK();

@@ -208,7 +208,7 @@ template <int DK>
 __global__ void __launch_bounds__(128) dec_attention_kernel(SearchBuffers sb, int mode, int layer,
                                                             const float* __restrict__ q, int ldq,
                                                             const float* __restrict__ kv_new, int ldkv,
-                                                            float* __restrict__ out) {
+                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   const int head = blockIdx.y;
@@ -343,18 +343,22 @@ __global__ void __launch_bounds__(128) dec_attention_kernel(SearchBuffers sb, in
 #pragma unroll
   for (int i = 0; i < NACC; ++i) {
     int b = g + i * G;
-    if (b < nb) out[(size_t)(row0 + b) * D + head * DK + cdim] = acc[i] / sm_l[b];
+    if (b < nb) {
+      const float o = acc[i] / sm_l[b];
+      out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
+      if (out16) out16[(size_t)(row0 + b) * D + head * DK + cdim] = __float2bfloat16(o);
+    }
   }
 }
 
 int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
-                         const float* kv_new, int ldkv, float* out, cudaStream_t st) {
+                         const float* kv_new, int ldkv, float* out, __nv_bfloat16* out16, cudaStream_t st) {
   if (sb.B > AMAXB) { set_last_error("dec_attention: beam %d > %d", sb.B, AMAXB); return -1; }
   const int dk = sb.D / sb.H;
   dim3 grid(sb.S, sb.H);
   size_t smem = sizeof(float) * (AMAXB * dk + AMAXB * ATILE + 3 * AMAXB) + (mode == 0 ? (size_t)AMAXB * sb.Lcap : 0);
-  if (dk == 32) dec_attention_kernel<32><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out);
-  else if (dk == 64) dec_attention_kernel<64><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out);
+  if (dk == 32) dec_attention_kernel<32><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out, out16);
+  else if (dk == 64) dec_attention_kernel<64><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out, out16);
   else { set_last_error("dec_attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;

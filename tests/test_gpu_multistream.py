@@ -1,0 +1,85 @@
+"""GPU: several ragged streams batched in one StreamGroup against the live CPU oracle (one oracle
+object per stream), fp32 mode: n-best tokens, timestamps and order exact; scores 2e-3."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import model_dir
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(arch, beam, lengths, chunk_of, use_bbd=False, kind="noise", dtype="float32"):
+    from oracle.speech2text import OracleSpeech2Text
+    from speechcatcher_b200 import StreamGroup
+    from speechcatcher_b200.synthetic import synth_audio
+    md = model_dir(arch)
+    S = len(lengths)
+    audio = [synth_audio(10 + s, n, kind) for s, n in enumerate(lengths)]
+    grp = StreamGroup(md, n_streams=S, beam_size=beam, device="cuda:0", dtype=dtype, use_bbd=use_bbd,
+                      max_chunk=max(chunk_of.values()), max_seconds=max(lengths) / 16000 + 2)
+    orc = [OracleSpeech2Text(md, beam_size=beam, use_bbd=use_bbd) for _ in range(S)]
+    pos = [0] * S
+    done = [False] * S
+    step = 0
+    while not all(done):
+        ids, chunks, fins = [], [], []
+        for s in range(S):
+            if done[s] or (step % 3 == 2 and s % 2 == 1):      # some streams skip some pushes
+                continue
+            c = chunk_of[s]
+            a = audio[s][pos[s]: pos[s] + c]
+            fin = pos[s] + c >= lengths[s]
+            ids.append(s); chunks.append(a); fins.append(fin)
+            pos[s] += c
+            done[s] = fin
+        step += 1
+        if not ids:
+            continue
+        grp.push(ids, chunks, fins)
+        for s, a, fin in zip(ids, chunks, fins):
+            want = orc[s](a, is_final=fin, finalize_all=fin)
+            plan = grp.last_plan(s)
+            assert bool(plan.called) == (orc[s].last_feats is not None)
+            if not plan.called:
+                continue
+            ys, sc, xp, pidx = grp.beam(s)
+            hyps = orc[s].hyps
+            assert ys == [list(h.yseq) for h in hyps], f"stream {s} step {step}"
+            assert xp == [list(h.xpos) for h in hyps], f"stream {s} step {step}"
+            np.testing.assert_allclose(sc, [h.score for h in hyps], atol=2e-3, rtol=0)
+            assert pidx == orc[s].search.process_idx
+            got = grp.results(s, fin, fin)
+            assert [r[2] for r in got] == [r[2] for r in want]
+    return grp
+
+
+def test_three_ragged_streams_m_d2():
+    _run("m_d2", 5, [5 * 16000 + 77, 3 * 16000, 6 * 16000 + 4000], {0: 8192, 1: 8192, 2: 8192})
+
+
+def test_mixed_chunk_sizes_xl_d4_beam10():
+    _run("xl_d4", 10, [4 * 16000, 4 * 16000 + 123, 20000, 3 * 16000], {0: 8192, 1: 4096, 2: 8192, 3: 6000}, kind="tones")
+
+
+def test_bbd_streams():
+    _run("m_d2", 5, [4 * 16000, 4 * 16000 + 999], {0: 8192, 1: 8192}, use_bbd=True)
+
+
+def test_reset_reuses_stream_slot():
+    from oracle.speech2text import OracleSpeech2Text
+    from speechcatcher_b200 import Speech2TextStreaming
+    from speechcatcher_b200.synthetic import synth_audio
+    md = model_dir("m_d2")
+    gpu = Speech2TextStreaming(md, beam_size=5, device="cuda:0")
+    for utt in range(2):
+        audio = synth_audio(40 + utt, 3 * 16000 + 500)
+        orc = OracleSpeech2Text(md, beam_size=5)
+        gpu.reset()
+        for i in range(0, len(audio), 8192):
+            fin = i + 8192 >= len(audio)
+            a = gpu(audio[i:i + 8192], is_final=fin, finalize_all=fin)
+            b = orc(audio[i:i + 8192], is_final=fin, finalize_all=fin)
+            assert [r[2] for r in a] == [r[2] for r in b]
+            assert [r[0] for r in a] == [r[0] for r in b]
+        assert gpu.beam_state[0] == [list(h.yseq) for h in orc.hyps]
