@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
+    ap.add_argument("--breakdown", action="store_true", help="always run the all-kernel timing pass")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -220,6 +221,24 @@ def main():
 
     for _ in range(args.warmup):
         one_pass_resident()
+    # one extra untimed pass with every kernel wrapped in CUDA events (decode steps sampled 1 in 8): the share of
+    # each kernel in the step, used to pick the dominant kernel for the roofline object
+    breakdown = None
+    if args.profile_kernel == "auto" or args.breakdown:
+        grp.profile_begin("all", max_launches=400000, stride=8)
+        one_pass_resident()
+        raw = grp.profile_end("all")
+        raw.pop("_counters", None)
+        tot = {k: v for k, v in raw.items() if k in ("decode_step_total", "encoder_total")}
+        parts = {k: v for k, v in raw.items() if k not in tot}
+        s_ms = sum(v[1] for v in parts.values())
+        breakdown = {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / s_ms, 4)}
+                     for k, v in sorted(parts.items(), key=lambda kv: -kv[1][1])}
+        breakdown["_totals"] = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in tot.items()}
+        if args.profile_kernel == "auto":
+            rankable = [k for k in parts if k in ("ctc_prefix", "dec_self_attn", "dec_cross_attn", "dec_ffn1", "dec_ffn2",
+                                                  "enc_ffn1", "enc_ffn2", "conv2")]
+            args.profile_kernel = max(rankable, key=lambda k: parts[k][1])
     prof = grp.profile_begin(args.profile_kernel)
     sampler = ClockSampler(local_rank)
     sync_all()
@@ -278,7 +297,7 @@ def main():
                            "decode_steps_per_pass": stats["steps"] // max(1, args.steps),
                            "encoder_blocks_per_pass": stats["blocks"] // max(1, args.steps)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": stats["launches"],
-                "roofline": roof, "cpu_baseline": cpu_base}
+                "roofline": roof, "cpu_baseline": cpu_base, "kernel_breakdown_sampled": breakdown}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -101,12 +101,17 @@ int sc_engine_last_plan(void* handle, int32_t stream_id, ScStreamPlan* plan);
 /* Named internal device buffer (tests / debugging): pointer, element count and row pitch. */
 int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem);
 
-/* Live timing of one tagged kernel with CUDA-event pairs on the launching stream (bench.py roofline).
- * tag: 1 ctc_prefix, 2 dec_self_attn, 3 dec_cross_attn, 4 dec_ffn1, 5 enc_ffn1, 6 prebeam, 7 enc_attn,
- *      8 conv2, 9 dec_ffn2, 10 enc_ffn2, 11 ctc_state_update.  counters8: device-side algorithmic counters. */
-int sc_engine_profile_begin(void* handle, int32_t tag, int32_t max_launches);
-int sc_engine_profile_end(void* handle, int32_t* n_launches, double* total_ms, double* host_flops,
-                          uint64_t* counters8);
+/* Live kernel timing with CUDA-event pairs on the launching stream (bench.py roofline and step breakdown).
+ * tag > 0: every launch of that kernel; tag = -1: every kernel, decode steps sampled every `stride` steps.
+ * Tags: 1 ctc_prefix, 2 dec_self_attn, 3 dec_cross_attn, 4 dec_ffn1, 5 enc_ffn1, 6 prebeam, 7 enc_attn, 8 conv2,
+ * 9 dec_ffn2, 10 enc_ffn2, 11 ctc_state_update, 12 frontend, 13 conv1, 14 sub_out, 15 block_assemble, 16 enc_ln,
+ * 17 enc_qkv, 18 enc_o, 19 enc_handover, 20 stitch_norm, 21 ctc_head, 22 cross_kv, 23 dec_embed, 24 dec_ln,
+ * 25 dec_qkv, 26 dec_self_o, 27 dec_cross_q, 28 dec_cross_o, 29 dec_out, 30 combine_topk, 31 beam_prune,
+ * 32 step_finish, 33 decode_step_total, 34 encoder_total.  counters8: device-side algorithmic counters
+ * (0 ctc bytes, 1 active rows, 2 cross-KV bytes, 3 self-KV bytes, 4 search iterations). */
+int sc_engine_profile_begin(void* handle, int32_t tag, int32_t max_launches, int32_t stride);
+int sc_engine_profile_end(void* handle, int32_t n_tags, int32_t* launches_per_tag, double* ms_per_tag,
+                          double* host_flops, uint64_t* counters8);
 
 /* ---- host-only shape planner (no CUDA calls; CPU-testable) ---- */
 int sc_planner_create(int32_t n_streams, void** planner);

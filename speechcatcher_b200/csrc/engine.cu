@@ -88,8 +88,12 @@ struct Engine {
   std::vector<ScStreamPlan> last_plan;
   int launches = 0;
   // live kernel timing (bench.py roofline): CUDA-event pairs around every launch of one tagged kernel
-  int prof_tag = 0;
+  int prof_tag = 0;                 // 0 off, >0 one tag, -1 every tag (decode steps sampled every prof_stride)
+  int prof_stride = 1;
+  long step_seq = 0;
+  bool prof_sample = false;         // current decode step is sampled (all-tags mode)
   std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_ev_tag;
   int prof_used = 0;
   double prof_flops = 0.0;          // host-known algorithmic FLOPs of the tagged launches (encoder GEMMs)
 
@@ -145,8 +149,11 @@ static void carve(Engine& e, Carver& cv) {
   sb.Tcap = k.Tcap; sb.Lcap = k.Lcap; sb.use_bbd = c.use_bbd; sb.qcap = k.qcap;
   sb.w_dec = (float)(1.0 - (double)c.ctc_weight); sb.w_ctc = c.ctc_weight;
   sb.ctcx = e.ctcx;
-  sb.xkv = cv.take<float>((size_t)c.dec_layers * S * k.Tcap * 2 * D);
-  sb.skv = cv.take<float>((size_t)c.dec_layers * S * k.Lcap * B * 2 * D);
+  sb.kv_bf16 = c.precision == 1;
+  if (sb.kv_bf16) sb.xkv = reinterpret_cast<float*>(cv.take<__nv_bfloat16>((size_t)c.dec_layers * S * k.Tcap * 2 * D));
+  else sb.xkv = cv.take<float>((size_t)c.dec_layers * S * k.Tcap * 2 * D);
+  if (sb.kv_bf16) sb.skv = reinterpret_cast<float*>(cv.take<__nv_bfloat16>((size_t)c.dec_layers * S * k.Lcap * B * 2 * D));
+  else sb.skv = cv.take<float>((size_t)c.dec_layers * S * k.Lcap * B * 2 * D);
   sb.yseq = cv.take<int>(2 * S * B * k.Lcap); reg("yseq", sb.yseq, 2 * S * B * k.Lcap);
   sb.xpos = cv.take<int>(2 * S * B * k.Lcap);
   sb.anc = cv.take<unsigned char>(2 * S * B * k.Lcap);
@@ -198,18 +205,33 @@ static int linear(Engine& e, const Lin& l, cudaStream_t st) {
 
 #define TRY(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
 
-enum { PROF_NONE = 0, PROF_CTC_PREFIX = 1, PROF_DEC_SELF_ATTN = 2, PROF_DEC_CROSS_ATTN = 3, PROF_DEC_FFN1 = 4,
-       PROF_ENC_FFN1 = 5, PROF_PREBEAM = 6, PROF_ENC_ATTN = 7, PROF_CONV2 = 8, PROF_DEC_FFN2 = 9, PROF_ENC_FFN2 = 10,
-       PROF_CTC_UPDATE = 11 };
+enum ProfTag { T_NONE = 0, T_CTC_PREFIX = 1, T_DEC_SELF_ATTN = 2, T_DEC_CROSS_ATTN = 3, T_DEC_FFN1 = 4, T_ENC_FFN1 = 5,
+               T_PREBEAM = 6, T_ENC_ATTN = 7, T_CONV2 = 8, T_DEC_FFN2 = 9, T_ENC_FFN2 = 10, T_CTC_UPDATE = 11,
+               T_FRONTEND = 12, T_CONV1 = 13, T_SUBOUT = 14, T_BLOCK_ASM = 15, T_ENC_LN = 16, T_ENC_QKV = 17, T_ENC_O = 18,
+               T_ENC_HANDOVER = 19, T_STITCH = 20, T_CTC_HEAD = 21, T_XKV = 22, T_DEC_EMBED = 23, T_DEC_LN = 24,
+               T_DEC_QKV = 25, T_DEC_SO = 26, T_DEC_CQ = 27, T_DEC_CO = 28, T_DEC_OUT = 29, T_COMBINE = 30, T_PRUNE = 31,
+               T_STEP_FINISH = 32, T_DEC_STEP_TOTAL = 33, T_ENC_TOTAL = 34, T_COUNT = 35 };
 
-// wraps a launch in an event pair when its tag is being profiled
-#define PROF(tag, expr)                                                                  \
-  do {                                                                                   \
-    const bool _p = e.prof_tag == (tag) && e.prof_used + 2 <= (int)e.prof_ev.size();     \
-    if (_p) cudaEventRecord(e.prof_ev[e.prof_used], st);                                 \
-    TRY(expr);                                                                           \
-    if (_p) { cudaEventRecord(e.prof_ev[e.prof_used + 1], st); e.prof_used += 2; }       \
+static inline bool prof_on(const Engine& e, int tag, bool decode_kernel) {
+  if (e.prof_tag == 0 || e.prof_used + 2 > (int)e.prof_ev.size()) return false;
+  if (e.prof_tag == tag) return true;
+  return e.prof_tag == -1 && (!decode_kernel || e.prof_sample);
+}
+static inline void prof_mark(Engine& e, int tag, cudaStream_t st, bool begin) {
+  cudaEventRecord(e.prof_ev[e.prof_used], st);
+  e.prof_ev_tag[e.prof_used] = begin ? tag : -tag;
+  e.prof_used++;
+}
+// wraps a launch in an event pair when its tag is being profiled (D = decode-step kernel, E = per-push kernel)
+#define PROFX(tag, dec, expr)                                \
+  do {                                                       \
+    const bool _p = prof_on(e, (tag), (dec));                \
+    if (_p) prof_mark(e, (tag), st, true);                   \
+    TRY(expr);                                               \
+    if (_p) prof_mark(e, (tag), st, false);                  \
   } while (0)
+#define PD(tag, expr) PROFX(tag, true, expr)
+#define PE(tag, expr) PROFX(tag, false, expr)
 
 // ---------------------------------------------------------------- encoder layers over all blocks of the push
 static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
@@ -217,18 +239,18 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
   const bool tc = c.precision == 1;
   for (int l = 0; l < c.enc_layers; ++l) {
     const EncLayerW& w = e.enc[l];
-    if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln1w, w.ln1b, e.Nrm16, D, rows, D, nullptr, st));
-    else TRY(launch_layernorm(e.X, D, w.ln1w, w.ln1b, e.Nrm, D, rows, D, nullptr, st));
-    TRY(linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
-    PROF(PROF_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
-    TRY(linear(e, Lin{e.Att, D, e.Att16, w.ow, w.ow16, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
-    if (tc) TRY(launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
-    else TRY(launch_layernorm(e.X, D, w.ln2w, w.ln2b, e.Nrm, D, rows, D, nullptr, st));
-    if (e.prof_tag == PROF_ENC_FFN1 || e.prof_tag == PROF_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
-    PROF(PROF_ENC_FFN1, linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
-    PROF(PROF_ENC_FFN2, linear(e, Lin{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr}, st));
-    TRY(launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, st));
-    e.launches += 5;
+    if (tc) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln1w, w.ln1b, e.Nrm16, D, rows, D, nullptr, st));
+    else PE(T_ENC_LN, launch_layernorm(e.X, D, w.ln1w, w.ln1b, e.Nrm, D, rows, D, nullptr, st));
+    PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
+    PE(T_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
+    PE(T_ENC_O, linear(e, Lin{e.Att, D, e.Att16, w.ow, w.ow16, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
+    if (tc) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
+    else PE(T_ENC_LN, launch_layernorm(e.X, D, w.ln2w, w.ln2b, e.Nrm, D, rows, D, nullptr, st));
+    if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
+    PE(T_ENC_FFN1, linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
+    PE(T_ENC_FFN2, linear(e, Lin{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr}, st));
+    PE(T_ENC_HANDOVER, launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, st));
+    e.launches += 4;
   }
   return 0;
 }
@@ -239,34 +261,38 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   const SearchBuffers& sb = e.sb;
   const int* nr = sb.n_rows;
   const bool tc = c.precision == 1;
-  TRY(launch_dec_embed(sb, e.demb, e.pe, e.dx, st));
+  e.prof_sample = (e.step_seq++ % e.prof_stride) == 0;
+  const bool ptot = prof_on(e, T_DEC_STEP_TOTAL, true);
+  if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, true);
+  PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
-    if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
-    else TRY(launch_layernorm(e.dx, D, w.ln1w, w.ln1b, e.dn, D, R, D, nr, st));
-    TRY(linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
-    PROF(PROF_DEC_SELF_ATTN, launch_dec_attention(sb, 0, l, e.dqkv, 3 * D, e.dqkv + D, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
-    TRY(linear(e, Lin{e.dattn, D, e.dattn16, w.sow, w.sow16, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
-    if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln2w, w.ln2b, e.dn16, D, R, D, nr, st));
-    else TRY(launch_layernorm(e.dx, D, w.ln2w, w.ln2b, e.dn, D, R, D, nr, st));
-    TRY(linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
-    PROF(PROF_DEC_CROSS_ATTN, launch_dec_attention(sb, 1, l, e.dq, D, nullptr, 0, e.dattn, tc ? e.dattn16 : nullptr, st));
-    TRY(linear(e, Lin{e.dattn, D, e.dattn16, w.cow, w.cow16, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
-    if (tc) TRY(launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
-    else TRY(launch_layernorm(e.dx, D, w.ln3w, w.ln3b, e.dn, D, R, D, nr, st));
-    PROF(PROF_DEC_FFN1, linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
-    PROF(PROF_DEC_FFN2, linear(e, Lin{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr}, st));
+    if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
+    else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln1w, w.ln1b, e.dn, D, R, D, nr, st));
+    PD(T_DEC_QKV, linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
+    PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
+    PD(T_DEC_SO, linear(e, Lin{e.dattn, D, e.dattn16, w.sow, w.sow16, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
+    if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln2w, w.ln2b, e.dn16, D, R, D, nr, st));
+    else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln2w, w.ln2b, e.dn, D, R, D, nr, st));
+    PD(T_DEC_CQ, linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
+    PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, e.dattn, tc ? e.dattn16 : nullptr, st));
+    PD(T_DEC_CO, linear(e, Lin{e.dattn, D, e.dattn16, w.cow, w.cow16, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
+    if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
+    else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln3w, w.ln3b, e.dn, D, R, D, nr, st));
+    PD(T_DEC_FFN1, linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
+    PD(T_DEC_FFN2, linear(e, Lin{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr}, st));
     e.launches += 5;
   }
-  if (tc) TRY(launch_layernorm_bf16(e.dx, D, e.daw, e.dab, e.dn16, D, R, D, nr, st));
-  else TRY(launch_layernorm(e.dx, D, e.daw, e.dab, e.dn, D, R, D, nr, st));
-  TRY(linear(e, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
-  PROF(PROF_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
-  PROF(PROF_CTC_PREFIX, launch_ctc_prefix(sb, st));
-  TRY(launch_combine_topk(sb, e.dlogp, st));
-  TRY(launch_beam_prune(sb, st));
-  PROF(PROF_CTC_UPDATE, launch_ctc_state_update(sb, st));
-  TRY(launch_step_finish(sb, st));
+  if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, e.daw, e.dab, e.dn16, D, R, D, nr, st));
+  else PD(T_DEC_LN, launch_layernorm(e.dx, D, e.daw, e.dab, e.dn, D, R, D, nr, st));
+  PD(T_DEC_OUT, linear(e, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
+  PD(T_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
+  PD(T_CTC_PREFIX, launch_ctc_prefix(sb, st));
+  PD(T_COMBINE, launch_combine_topk(sb, e.dlogp, st));
+  PD(T_PRUNE, launch_beam_prune(sb, st));
+  PD(T_CTC_UPDATE, launch_ctc_state_update(sb, st));
+  PD(T_STEP_FINISH, launch_step_finish(sb, st));
+  if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, false);
   e.launches += 9;
   return 0;
 }
@@ -440,6 +466,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   cudaStream_t st = (cudaStream_t)stream;
   const int S = c.n_streams, D = c.d_model, V = c.vocab;
   e->launches = 0;
+  Engine& eref = *e;
   if (n < 0 || n > S) { set_last_error("push: n=%d out of range", n); return SC_ERR_ARG; }
   // ---------------- plan on the host
   std::vector<StreamPush> plans(n);
@@ -544,39 +571,46 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   TRY(up(e->d_en_flag, h_en_flag, sizeof(int) * n_en));
   if (n_q) TRY(up(e->d_q, h_q, sizeof(int) * (2 * S + 2 * S * k.qcap)));
   // ---------------- frontend
-  TRY(launch_frontend(wave_dev, ld_wave, e->wbuf, 512, e->d_fd, n_fd, frame_base, e->has_stats ? e->d_mean : nullptr,
-                      e->has_stats ? e->d_std : nullptr, e->featbuf, k.feat_cap, st));
+#define e eref
+  const bool petot = prof_on(e, T_ENC_TOTAL, false);
+  if (petot) prof_mark(e, T_ENC_TOTAL, st, true);
+  PE(T_FRONTEND, launch_frontend(wave_dev, ld_wave, e.wbuf, 512, e.d_fd, n_fd, frame_base, e.has_stats ? e.d_mean : nullptr,
+                      e.has_stats ? e.d_std : nullptr, e.featbuf, k.feat_cap, st));
+#undef e
   TRY(launch_wavebuf_update(wave_dev, ld_wave, e->wbuf, 512, e->d_fd, n_fd_all, st));
   e->launches += 2;
   // ---------------- conv2d sub-sampling
   const bool tc = c.precision == 1;
   if (n_sd > 0) {
-    TRY(launch_conv1(e->featbuf, k.feat_cap, e->c1w, e->c1b, e->h1, k.t1_cap, e->d_sd, n_sd, D, st));
+#define e eref
+    PE(T_CONV1, launch_conv1(e.featbuf, k.feat_cap, e.c1w, e.c1b, e.h1, k.t1_cap, e.d_sd, n_sd, D, st));
+#undef e
     TRY(launch_conv2_rows(e->d_sd, n_sd, k.t1_cap, k.sub_cap, D, e->d_c2_a, e->d_c2_c, st));
     GemmArgs g;
     g.A = e->h1; g.a_row_off = e->d_c2_a; g.a_seg_off = e->d_c2_seg; g.seg_len = D; g.W = e->c2w; g.bias = e->c2b;
     g.C = e->h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
     if (tc) { g.Cb = e->h2_16; g.ldcb = D; }
-    {
-      Engine& e_ = *e;
-      const bool _p = e_.prof_tag == PROF_CONV2 && e_.prof_used + 2 <= (int)e_.prof_ev.size();
-      if (_p) { cudaEventRecord(e_.prof_ev[e_.prof_used], st); e_.prof_flops += 2.0 * g.M * (double)g.N * g.K; }
-      TRY(launch_gemm_f32(g, st));
-      if (_p) { cudaEventRecord(e_.prof_ev[e_.prof_used + 1], st); e_.prof_used += 2; }
-    }
+#define e eref
+    if (e.prof_tag == T_CONV2) e.prof_flops += 2.0 * g.M * (double)g.N * g.K;
+    PE(T_CONV2, launch_gemm_f32(g, st));
+#undef e
     {
       Lin o{e->h2, 19 * D, e->h2_16, e->eow, e->eow16, e->eob, nullptr, 0, e->subbuf, 0, nullptr, sub_rows, D, 19 * D, 0, nullptr};
       o.c_row_off = e->d_c2_c;
-      TRY(linear(*e, o, st));
+#define e eref
+      PE(T_SUBOUT, linear(e, o, st));
+#undef e
     }
     e->launches += 4;
   }
   if (n_cf) { TRY(launch_carry_rows(e->featbuf, k.feat_cap, 80, e->d_carry_f, e->d_carry_f + S, e->d_carry_f + 2 * S, n_cf, st)); e->launches++; }
   // ---------------- encoder blocks
   if (n_blk > 0) {
-    TRY(launch_block_assemble(e->subbuf, k.sub_cap, e->pe, e->d_blk, n_blk, e->addin, e->prev_addin, e->X, D, st));
-    TRY(run_encoder_layers(*e, n_blk, st));
-    TRY(launch_stitch_norm(e->X, e->d_blk, n_blk, e->eaw, e->eab, e->encbuf, k.Tcap, D, tc ? e->encnew16 : nullptr, st));
+#define e eref
+    PE(T_BLOCK_ASM, launch_block_assemble(e.subbuf, k.sub_cap, e.pe, e.d_blk, n_blk, e.addin, e.prev_addin, e.X, D, st));
+    TRY(run_encoder_layers(e, n_blk, st));
+    PE(T_STITCH, launch_stitch_norm(e.X, e.d_blk, n_blk, e.eaw, e.eab, e.encbuf, k.Tcap, D, tc ? e.encnew16 : nullptr, st));
+#undef e
     e->launches += 4;
   }
   if (n_cs) { TRY(launch_carry_rows(e->subbuf, k.sub_cap, D, e->d_carry_s, e->d_carry_s + S, e->d_carry_s + 2 * S, n_cs, st)); e->launches++; }
@@ -585,30 +619,39 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     if (tc) {
       Lin g{nullptr, D, e->encnew16, e->ctcw, e->ctcw16, e->ctcb, nullptr, 0, e->ctcx, 0, nullptr, n_en, V, D, 0, nullptr};
       g.c_row_off = e->d_en_ctc;
-      TRY(linear(*e, g, st));
+#define e eref
+      PE(T_CTC_HEAD, linear(e, g, st));
+#undef e
     } else {
       GemmArgs g;
       g.A = e->encbuf; g.a_row_off = e->d_en_a; g.W = e->ctcw; g.bias = e->ctcb; g.C = e->ctcx; g.c_row_off = e->d_en_ctc;
       g.M = n_en; g.N = V; g.K = D;
-      TRY(launch_gemm_f32(g, st));
+#define e eref
+      PE(T_CTC_HEAD, launch_gemm_f32(g, st));
+#undef e
     }
     TRY(launch_logsoftmax_rows(e->ctcx, e->d_en_ctc, e->d_en_flag, n_en, V, st));
     for (int l = 0; l < c.dec_layers; ++l) {
       float* dst = e->sb.xkv + (size_t)l * S * k.Tcap * 2 * D;
       if (tc) {
-        Lin kv{nullptr, D, e->encnew16, e->dec[l].ckvw, e->dec[l].ckvw16, e->dec[l].ckvb, nullptr, 0, dst, 0, nullptr, n_en, 2 * D, D, 0, nullptr};
+        __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(e->sb.xkv) + (size_t)l * S * k.Tcap * 2 * D;
+        Lin kv{nullptr, D, e->encnew16, e->dec[l].ckvw, e->dec[l].ckvw16, e->dec[l].ckvb, nullptr, 0, nullptr, 0, dst16, n_en, 2 * D, D, 0, nullptr};
         kv.c_row_off = e->d_en_kv;
-        TRY(linear(*e, kv, st));
+#define e eref
+        PE(T_XKV, linear(e, kv, st));
+#undef e
       } else {
         GemmArgs kv;
         kv.A = e->encbuf; kv.a_row_off = e->d_en_a; kv.W = e->dec[l].ckvw; kv.bias = e->dec[l].ckvb;
         kv.C = dst; kv.c_row_off = e->d_en_kv; kv.M = n_en; kv.N = 2 * D; kv.K = D;
-        TRY(launch_gemm_f32(kv, st));
+#define e eref
+        PE(T_XKV, launch_gemm_f32(kv, st));
+#undef e
       }
     }
     e->launches += 2 + c.dec_layers;
   }
-  (void)tc;
+  if (petot) prof_mark(eref, T_ENC_TOTAL, st, false);
   // ---------------- block-synchronous beam search
   int steps = 0;
   TRY(launch_search_begin(e->sb, e->d_q, e->d_q + S, e->d_q + 2 * S, e->d_q + 2 * S + S * k.qcap, n_q, st));
@@ -681,7 +724,7 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
 }
 
 // ---------------- live kernel timing
-int sc_engine_profile_begin(void* handle, int32_t tag, int32_t max_launches) {
+int sc_engine_profile_begin(void* handle, int32_t tag, int32_t max_launches, int32_t stride) {
   Engine* e = (Engine*)handle;
   if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
   while ((int)e->prof_ev.size() < 2 * max_launches) {
@@ -689,24 +732,33 @@ int sc_engine_profile_begin(void* handle, int32_t tag, int32_t max_launches) {
     SCB_CUDA_CHECK(cudaEventCreate(&ev));
     e->prof_ev.push_back(ev);
   }
-  e->prof_tag = tag; e->prof_used = 0; e->prof_flops = 0.0;
+  e->prof_ev_tag.assign(e->prof_ev.size(), 0);
+  e->prof_tag = tag; e->prof_used = 0; e->prof_flops = 0.0; e->prof_stride = stride < 1 ? 1 : stride; e->step_seq = 0;
   SCB_CUDA_CHECK(cudaMemset(e->sb.prof, 0, 8 * sizeof(unsigned long long)));
   return SC_OK;
 }
 
-int sc_engine_profile_end(void* handle, int32_t* n_launches, double* total_ms, double* host_flops, uint64_t* counters8) {
+int sc_engine_profile_end(void* handle, int32_t n_tags, int32_t* launches_per_tag, double* ms_per_tag, double* host_flops,
+                          uint64_t* counters8) {
   Engine* e = (Engine*)handle;
   if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
   SCB_CUDA_CHECK(cudaDeviceSynchronize());
-  double ms = 0.0;
-  for (int i = 0; i + 1 < e->prof_used; i += 2) {
-    float t = 0.f;
-    SCB_CUDA_CHECK(cudaEventElapsedTime(&t, e->prof_ev[i], e->prof_ev[i + 1]));
-    ms += t;
+  for (int i = 0; i < n_tags; ++i) { launches_per_tag[i] = 0; ms_per_tag[i] = 0.0; }
+  // events come in (begin, end) pairs per tag; totals (T_DEC_STEP_TOTAL / T_ENC_TOTAL) enclose other pairs
+  std::vector<int> open_idx(T_COUNT, -1);
+  for (int i = 0; i < e->prof_used; ++i) {
+    const int t = e->prof_ev_tag[i];
+    if (t > 0) { if (t < T_COUNT) open_idx[t] = i; continue; }
+    const int tag = -t;
+    if (tag <= 0 || tag >= T_COUNT || open_idx[tag] < 0) continue;
+    float ms = 0.f;
+    SCB_CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof_ev[open_idx[tag]], e->prof_ev[i]));
+    open_idx[tag] = -1;
+    if (tag < n_tags) { ms_per_tag[tag] += ms; launches_per_tag[tag]++; }
   }
-  *n_launches = e->prof_used / 2; *total_ms = ms; *host_flops = e->prof_flops;
+  *host_flops = e->prof_flops;
   SCB_CUDA_CHECK(cudaMemcpy(counters8, e->sb.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  e->prof_tag = 0;
+  e->prof_tag = 0; e->prof_stride = 1;
   return SC_OK;
 }
 

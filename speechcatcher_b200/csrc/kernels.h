@@ -129,7 +129,8 @@ struct SearchBuffers {
   float w_dec, w_ctc;
   // model memory
   const float* ctcx;      // [S][Tcap][V]
-  float* xkv;             // [Ld][S][Tcap][2D]  cross-attention K|V
+  float* xkv;             // [Ld][S][Tcap][2D]  cross-attention K|V (bf16 elements when kv_bf16)
+  int kv_bf16;
   float* skv;             // [Ld][S][Lcap][B][2D] self-attention K|V (tree storage)
   // beam (ping-pong)
   int* yseq;              // [2][S][B][Lcap]
@@ -175,6 +176,10 @@ int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe,
 // mode 0: self attention over the tree KV store (appends this step's K|V first); mode 1: cross attention
 int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
                          const float* kv_new, int ldkv, float* out, __nv_bfloat16* out16, cudaStream_t st);
+int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
+                              __nv_bfloat16* out16, cudaStream_t st);
+int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
+                               __nv_bfloat16* out16, cudaStream_t st);
 int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st);
 int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st);
 int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st);

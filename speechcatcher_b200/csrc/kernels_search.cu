@@ -351,6 +351,402 @@ __global__ void __launch_bounds__(128) dec_attention_kernel(SearchBuffers sb, in
   }
 }
 
+// ---------------------------------------------------------------- cross attention, shared-memory staged
+// One CTA per (active stream, head).  All hypotheses of a stream see the same memory, so each K|V tile is
+// loaded once (coalesced, converted to fp32), staged in shared memory and reused by every hypothesis.
+// K rows are padded to DK+4 floats so that the per-position float4 row reads are bank-conflict free.
+template <int DK, typename KVT>
+__global__ void __launch_bounds__(128) dec_cross_attn_kernel(SearchBuffers sb, const KVT* __restrict__ xkv_layer,
+                                                             const float* __restrict__ q, int ldq,
+                                                             float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  const int head = blockIdx.y;
+  const StreamCtl& c = sb.ctl[s];
+  const int nb = c.n_hyp, row0 = sb.row_base[s], D = sb.D, npos = c.Tb;
+  const int tid = threadIdx.x;
+  constexpr int TILE = 4096 / DK;          // 128 positions (DK = 32) or 64 (DK = 64)
+  constexpr int KS = DK + 4;
+  constexpr int CH = DK / 4;               // 4-element chunks per row
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* Ks = reinterpret_cast<float*>(smem_raw);       // [TILE][KS]
+  float* Vs = Ks + TILE * KS;                            // [TILE][DK]
+  float* sc = Vs + TILE * DK;                            // [AMAXB][TILE]
+  float* qs = sc + AMAXB * TILE;                         // [AMAXB][DK]
+  float* sm_m = qs + AMAXB * DK;
+  float* sm_l = sm_m + AMAXB;
+  float* sm_f = sm_l + AMAXB;
+  if (tid == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * npos * DK * sizeof(KVT)));
+  for (int i = tid; i < nb * DK; i += 128) qs[i] = q[(size_t)(row0 + i / DK) * ldq + head * DK + i % DK];
+  if (tid < AMAXB) { sm_m[tid] = -INFINITY; sm_l[tid] = 0.f; }
+  const size_t row_stride = 2 * (size_t)D;
+  const KVT* base = xkv_layer + (size_t)s * sb.Tcap * row_stride + head * DK;
+  const float sqrt_dk = sqrtf((float)DK);
+  constexpr int G = 128 / DK;
+  constexpr int NACC = (AMAXB + G - 1) / G;
+  const int g = tid / DK, cdim = tid % DK;
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+  for (int t0 = 0; t0 < npos; t0 += TILE) {
+    const int jn = min(TILE, npos - t0);
+    __syncthreads();                       // previous tile fully consumed (also orders the q / m / l init)
+    for (int idx = tid; idx < jn * CH; idx += 128) {
+      const int r = idx / CH, ch = idx % CH;
+      const KVT* kp = base + (size_t)(t0 + r) * row_stride + ch * 4;
+      float4 kf, vf;
+      if constexpr (sizeof(KVT) == 4) {
+        kf = *reinterpret_cast<const float4*>(kp);
+        vf = *reinterpret_cast<const float4*>(kp + D);
+      } else {
+        const uint2 ku = *reinterpret_cast<const uint2*>(kp);
+        const uint2 vu = *reinterpret_cast<const uint2*>(kp + D);
+        const float2 k0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ku.x));
+        const float2 k1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ku.y));
+        const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vu.x));
+        const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vu.y));
+        kf = make_float4(k0.x, k0.y, k1.x, k1.y);
+        vf = make_float4(v0.x, v0.y, v1.x, v1.y);
+      }
+      *reinterpret_cast<float4*>(Ks + r * KS + ch * 4) = kf;
+      *reinterpret_cast<float4*>(Vs + r * DK + ch * 4) = vf;
+    }
+    __syncthreads();
+    if (tid < TILE) {
+      if (tid < jn) {
+        float kreg[DK];
+#pragma unroll
+        for (int i = 0; i < DK; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Ks + tid * KS + i);
+          kreg[i] = v.x; kreg[i + 1] = v.y; kreg[i + 2] = v.z; kreg[i + 3] = v.w;
+        }
+        for (int b = 0; b < nb; ++b) {
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < DK; ++i) d = fmaf(qs[b * DK + i], kreg[i], d);
+          sc[b * TILE + tid] = d / sqrt_dk;
+        }
+      } else {
+        for (int b = 0; b < nb; ++b) sc[b * TILE + tid] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int b = warp; b < nb; b += 4) {
+        float m = -INFINITY;
+        for (int i = lane; i < TILE; i += 32) m = fmaxf(m, sc[b * TILE + i]);
+        m = warp_max(m);
+        const float m_old = sm_m[b];
+        const float m_new = fmaxf(m_old, m);
+        float ssum = 0.f;
+        for (int i = lane; i < TILE; i += 32) {
+          const float e = expf(sc[b * TILE + i] - m_new);
+          sc[b * TILE + i] = e;
+          ssum += e;
+        }
+        ssum = warp_sum(ssum);
+        if (lane == 0) {
+          const float f = expf(m_old - m_new);
+          sm_f[b] = f;
+          sm_l[b] = sm_l[b] * f + ssum;
+          sm_m[b] = m_new;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+      const int b = g + i * G;
+      if (b < nb) acc[i] *= sm_f[b];
+    }
+#pragma unroll 4
+    for (int jj = 0; jj < jn; ++jj) {
+      const float v = Vs[jj * DK + cdim];
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        const int b = g + i * G;
+        if (b < nb) acc[i] = fmaf(sc[b * TILE + jj], v, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    const int b = g + i * G;
+    if (b < nb) {
+      const float o = acc[i] / sm_l[b];
+      out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
+      if (out16) out16[(size_t)(row0 + b) * D + head * DK + cdim] = __float2bfloat16(o);
+    }
+  }
+}
+
+template <typename KVT>
+static int launch_cross_t(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
+                          __nv_bfloat16* out16, cudaStream_t st) {
+  const int dk = sb.D / sb.H;
+  const KVT* base = reinterpret_cast<const KVT*>(sb.xkv) + (size_t)layer * sb.S * sb.Tcap * 2 * sb.D;
+  dim3 grid(sb.S, sb.H);
+  const int tile = 4096 / dk;
+  const size_t smem = sizeof(float) * ((size_t)tile * (dk + 4) + (size_t)tile * dk + (size_t)AMAXB * tile + AMAXB * dk + 3 * AMAXB);
+  if (dk == 32) {
+    static bool a = false;
+    if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+    dec_cross_attn_kernel<32, KVT><<<grid, 128, smem, st>>>(sb, base, q, ldq, out, out16);
+  } else if (dk == 64) {
+    static bool a = false;
+    if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+    dec_cross_attn_kernel<64, KVT><<<grid, 128, smem, st>>>(sb, base, q, ldq, out, out16);
+  } else { set_last_error("cross attention: unsupported head dim %d", dk); return -1; }
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
+                               __nv_bfloat16* out16, cudaStream_t st) {
+  if (sb.B > AMAXB) { set_last_error("cross attention: beam %d > %d", sb.B, AMAXB); return -1; }
+  return sb.kv_bf16 ? launch_cross_t<__nv_bfloat16>(sb, layer, q, ldq, out, out16, st)
+                    : launch_cross_t<float>(sb, layer, q, ldq, out, out16, st);
+}
+
+// ---------------------------------------------------------------- self attention over the KV tree, shared-memory staged
+// One CTA per (active stream, head).  The hypotheses of a beam share a common ancestor chain for all
+// but the last few positions (paths in the tree never re-merge), so positions [0, Lc) are loaded once
+// and scored for every hypothesis like in the cross-attention kernel; the divergent tail [Lc, len) is
+// processed as a flat list of (hypothesis, position) pairs, each pair contributing to its own
+// hypothesis only.  This step's K|V (columns D..3D of the fused QKV GEMM) is appended first.
+template <int DK, typename KVT>
+__global__ void __launch_bounds__(128) dec_self_attn_kernel(SearchBuffers sb, KVT* skv_layer,
+                                                            const float* __restrict__ qkv, int ldq,
+                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  const int head = blockIdx.y;
+  const StreamCtl& c = sb.ctl[s];
+  const int nb = c.n_hyp, row0 = sb.row_base[s], D = sb.D, len = c.len, B = sb.B;
+  const int tid = threadIdx.x;
+  constexpr int TILE = 4096 / DK;
+  constexpr int KS = DK + 4;
+  constexpr int CH = DK / 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* Ks = reinterpret_cast<float*>(smem_raw);
+  float* Vs = Ks + TILE * KS;
+  float* sc = Vs + TILE * DK;                            // [AMAXB][TILE]; row 0 doubles as the flat pair scores
+  float* qs = sc + AMAXB * TILE;
+  float* sm_m = qs + AMAXB * DK;
+  float* sm_l = sm_m + AMAXB;
+  float* sm_f = sm_l + AMAXB;
+  int* s_lc = reinterpret_cast<int*>(sm_f + AMAXB);
+  unsigned char* ancs = reinterpret_cast<unsigned char*>(s_lc + 4);   // [AMAXB][Lcap]
+  const size_t row_stride = 2 * (size_t)D;
+  KVT* store = skv_layer + (size_t)s * sb.Lcap * B * row_stride;
+  if (tid == 0) {
+    atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * sizeof(KVT)));
+    *s_lc = len;
+  }
+  for (int i = tid; i < nb * DK; i += 128) qs[i] = qkv[(size_t)(row0 + i / DK) * ldq + head * DK + i % DK];
+  if (tid < AMAXB) { sm_m[tid] = -INFINITY; sm_l[tid] = 0.f; }
+  for (int i = tid; i < nb * 2 * DK; i += 128) {        // append K|V of the scored token at [len-1][b]
+    const int b = i / (2 * DK), rem = i % (2 * DK), which = rem / DK, cc = rem % DK;
+    const float v = qkv[(size_t)(row0 + b) * ldq + D + which * D + head * DK + cc];
+    store[((size_t)(len - 1) * B + b) * row_stride + which * D + head * DK + cc] = (KVT)v;
+  }
+  for (int i = tid; i < nb * len; i += 128) {
+    const int b = i / len, j = i % len;
+    ancs[b * sb.Lcap + j] = (j == len - 1) ? (unsigned char)b : sb.anc[beam_off(sb, c.cur, s, b) * sb.Lcap + j];
+  }
+  __syncthreads();
+  for (int j = tid; j < len; j += 128) {
+    const unsigned char a0 = ancs[j];
+    bool same = true;
+    for (int b = 1; b < nb; ++b) same &= (ancs[b * sb.Lcap + j] == a0);
+    if (!same) atomicMin(s_lc, j);
+  }
+  __syncthreads();
+  const int Lc = *s_lc;
+  const float sqrt_dk = sqrtf((float)DK);
+  constexpr int G = 128 / DK;
+  constexpr int NACC = (AMAXB + G - 1) / G;
+  const int g = tid / DK, cdim = tid % DK;
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+  auto load_row = [&](int r, int ch, const KVT* kp) {
+    float4 kf, vf;
+    if constexpr (sizeof(KVT) == 4) {
+      kf = *reinterpret_cast<const float4*>(kp);
+      vf = *reinterpret_cast<const float4*>(kp + D);
+    } else {
+      const uint2 ku = *reinterpret_cast<const uint2*>(kp);
+      const uint2 vu = *reinterpret_cast<const uint2*>(kp + D);
+      const float2 k0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ku.x));
+      const float2 k1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ku.y));
+      const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vu.x));
+      const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vu.y));
+      kf = make_float4(k0.x, k0.y, k1.x, k1.y);
+      vf = make_float4(v0.x, v0.y, v1.x, v1.y);
+    }
+    *reinterpret_cast<float4*>(Ks + r * KS + ch * 4) = kf;
+    *reinterpret_cast<float4*>(Vs + r * DK + ch * 4) = vf;
+  };
+
+  // ---------------- common ancestor chain: one row per position, shared by every hypothesis
+  for (int t0 = 0; t0 < Lc; t0 += TILE) {
+    const int jn = min(TILE, Lc - t0);
+    __syncthreads();
+    for (int idx = tid; idx < jn * CH; idx += 128) {
+      const int r = idx / CH, ch = idx % CH, j = t0 + r;
+      load_row(r, ch, store + ((size_t)j * B + ancs[j]) * row_stride + head * DK + ch * 4);
+    }
+    __syncthreads();
+    if (tid < TILE) {
+      if (tid < jn) {
+        float kreg[DK];
+#pragma unroll
+        for (int i = 0; i < DK; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Ks + tid * KS + i);
+          kreg[i] = v.x; kreg[i + 1] = v.y; kreg[i + 2] = v.z; kreg[i + 3] = v.w;
+        }
+        for (int b = 0; b < nb; ++b) {
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < DK; ++i) d = fmaf(qs[b * DK + i], kreg[i], d);
+          sc[b * TILE + tid] = d / sqrt_dk;
+        }
+      } else {
+        for (int b = 0; b < nb; ++b) sc[b * TILE + tid] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int b = warp; b < nb; b += 4) {
+        float m = -INFINITY;
+        for (int i = lane; i < TILE; i += 32) m = fmaxf(m, sc[b * TILE + i]);
+        m = warp_max(m);
+        const float m_old = sm_m[b], m_new = fmaxf(m_old, m);
+        float ssum = 0.f;
+        for (int i = lane; i < TILE; i += 32) {
+          const float e = expf(sc[b * TILE + i] - m_new);
+          sc[b * TILE + i] = e;
+          ssum += e;
+        }
+        ssum = warp_sum(ssum);
+        if (lane == 0) {
+          const float f = expf(m_old - m_new);
+          sm_f[b] = f; sm_l[b] = sm_l[b] * f + ssum; sm_m[b] = m_new;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { const int b = g + i * G; if (b < nb) acc[i] *= sm_f[b]; }
+#pragma unroll 4
+    for (int jj = 0; jj < jn; ++jj) {
+      const float v = Vs[jj * DK + cdim];
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) { const int b = g + i * G; if (b < nb) acc[i] = fmaf(sc[b * TILE + jj], v, acc[i]); }
+    }
+  }
+  // ---------------- divergent tail: flat list of (hypothesis, position) pairs, ordered by hypothesis
+  const int n_div = len - Lc;
+  const int n_pairs = nb * n_div;
+  for (int p0 = 0; p0 < n_pairs; p0 += TILE) {
+    const int pn = min(TILE, n_pairs - p0);
+    __syncthreads();
+    for (int idx = tid; idx < pn * CH; idx += 128) {
+      const int r = idx / CH, ch = idx % CH, u = p0 + r, b = u / n_div, j = Lc + u % n_div;
+      load_row(r, ch, store + ((size_t)j * B + ancs[b * sb.Lcap + j]) * row_stride + head * DK + ch * 4);
+    }
+    __syncthreads();
+    if (tid < pn) {
+      const int b = (p0 + tid) / n_div;
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < DK; i += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(Ks + tid * KS + i);
+        const float4 qv = *reinterpret_cast<const float4*>(qs + b * DK + i);
+        d = fmaf(qv.x, kv.x, d); d = fmaf(qv.y, kv.y, d); d = fmaf(qv.z, kv.z, d); d = fmaf(qv.w, kv.w, d);
+      }
+      sc[tid] = d / sqrt_dk;
+    }
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int b = warp; b < nb; b += 4) {
+        const int lo = max(b * n_div, p0) - p0, hi = min((b + 1) * n_div, p0 + pn) - p0;
+        if (lo >= hi) { if (lane == 0) sm_f[b] = 1.f; continue; }
+        float m = -INFINITY;
+        for (int i = lo + lane; i < hi; i += 32) m = fmaxf(m, sc[i]);
+        m = warp_max(m);
+        const float m_old = sm_m[b], m_new = fmaxf(m_old, m);
+        float ssum = 0.f;
+        for (int i = lo + lane; i < hi; i += 32) {
+          const float e = expf(sc[i] - m_new);
+          sc[i] = e;
+          ssum += e;
+        }
+        ssum = warp_sum(ssum);
+        if (lane == 0) {
+          const float f = expf(m_old - m_new);
+          sm_f[b] = f; sm_l[b] = sm_l[b] * f + ssum; sm_m[b] = m_new;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+      const int b = g + i * G;
+      if (b < nb) {
+        const int lo = max(b * n_div, p0) - p0, hi = min((b + 1) * n_div, p0 + pn) - p0;
+        float a = acc[i] * sm_f[b];
+        for (int jj = lo; jj < hi; ++jj) a = fmaf(sc[jj], Vs[jj * DK + cdim], a);
+        acc[i] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    const int b = g + i * G;
+    if (b < nb) {
+      const float o = acc[i] / sm_l[b];
+      out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
+      if (out16) out16[(size_t)(row0 + b) * D + head * DK + cdim] = __float2bfloat16(o);
+    }
+  }
+}
+
+template <typename KVT>
+static int launch_self_t(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
+                         __nv_bfloat16* out16, cudaStream_t st) {
+  const int dk = sb.D / sb.H;
+  KVT* base = reinterpret_cast<KVT*>(sb.skv) + (size_t)layer * sb.S * sb.Lcap * sb.B * 2 * sb.D;
+  dim3 grid(sb.S, sb.H);
+  const int tile = 4096 / dk;
+  const size_t smem = sizeof(float) * ((size_t)tile * (dk + 4) + (size_t)tile * dk + (size_t)AMAXB * tile + AMAXB * dk + 3 * AMAXB) +
+                      16 + (size_t)AMAXB * sb.Lcap;
+  if (dk == 32) {
+    static size_t a = 0;
+    if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
+    dec_self_attn_kernel<32, KVT><<<grid, 128, smem, st>>>(sb, base, qkv, ldq, out, out16);
+  } else if (dk == 64) {
+    static size_t a = 0;
+    if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
+    dec_self_attn_kernel<64, KVT><<<grid, 128, smem, st>>>(sb, base, qkv, ldq, out, out16);
+  } else { set_last_error("self attention: unsupported head dim %d", dk); return -1; }
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
+                              __nv_bfloat16* out16, cudaStream_t st) {
+  if (sb.B > AMAXB) { set_last_error("self attention: beam %d > %d", sb.B, AMAXB); return -1; }
+  return sb.kv_bf16 ? launch_self_t<__nv_bfloat16>(sb, layer, qkv, ldq, out, out16, st)
+                    : launch_self_t<float>(sb, layer, qkv, ldq, out, out16, st);
+}
+
 int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
                          const float* kv_new, int ldkv, float* out, __nv_bfloat16* out16, cudaStream_t st) {
   if (sb.B > AMAXB) { set_last_error("dec_attention: beam %d > %d", sb.B, AMAXB); return -1; }

@@ -200,29 +200,41 @@ class StreamGroup:
 
     # ------------------------------------------------------------------ live kernel timing (bench.py roofline)
     PROF_TAGS = {"ctc_prefix": 1, "dec_self_attn": 2, "dec_cross_attn": 3, "dec_ffn1": 4, "enc_ffn1": 5, "prebeam": 6,
-                 "enc_attn": 7, "conv2": 8, "dec_ffn2": 9, "enc_ffn2": 10, "ctc_state_update": 11}
+                 "enc_attn": 7, "conv2": 8, "dec_ffn2": 9, "enc_ffn2": 10, "ctc_state_update": 11, "frontend": 12,
+                 "conv1": 13, "sub_out": 14, "block_assemble": 15, "enc_ln": 16, "enc_qkv": 17, "enc_o": 18,
+                 "enc_handover": 19, "stitch_norm": 20, "ctc_head": 21, "cross_kv": 22, "dec_embed": 23, "dec_ln": 24,
+                 "dec_qkv": 25, "dec_self_o": 26, "dec_cross_q": 27, "dec_cross_o": 28, "dec_out": 29,
+                 "combine_topk": 30, "beam_prune": 31, "step_finish": 32, "decode_step_total": 33, "encoder_total": 34}
+    N_TAGS = 35
 
-    def profile_begin(self, kernel: str = "auto", max_launches: int = 60000) -> str:
-        if kernel == "auto":
-            kernel = "dec_cross_attn"
+    def profile_begin(self, kernel: str = "all", max_launches: int = 60000, stride: int = 1) -> str:
+        tag = -1 if kernel == "all" else self.PROF_TAGS[kernel]
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.sc_engine_profile_begin(self.handle, self.PROF_TAGS[kernel], max_launches), "profile_begin")
+            _lib.check(self.lib.sc_engine_profile_begin(self.handle, tag, max_launches, stride), "profile_begin")
         return kernel
 
     def profile_end(self, kernel: str) -> dict:
-        """Roofline object for bench.py: algorithmic bytes (or FLOPs) of the tagged kernel's launches divided by
-        their CUDA-event time, against the measured peak in MEASURED_PEAKS.json (else the recipe's fallback)."""
+        """kernel == "all": {name: (launches, ms)} over the sampled launches.  Otherwise the roofline object for
+        bench.py: algorithmic bytes (or FLOPs) of the tagged kernel's launches / their CUDA-event time, against the
+        measured peak in MEASURED_PEAKS.json (else the profiling recipe's fallback)."""
         import json
-        n, ms, fl = C.c_int32(), C.c_double(), C.c_double()
+        n = (C.c_int32 * self.N_TAGS)()
+        ms = (C.c_double * self.N_TAGS)()
+        fl = C.c_double()
         cnt = (C.c_uint64 * 8)()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.sc_engine_profile_end(self.handle, C.byref(n), C.byref(ms), C.byref(fl), cnt), "profile_end")
+            _lib.check(self.lib.sc_engine_profile_end(self.handle, self.N_TAGS, n, ms, C.byref(fl), cnt), "profile_end")
+        if kernel == "all":
+            out = {name: (int(n[t]), float(ms[t])) for name, t in self.PROF_TAGS.items() if n[t]}
+            out["_counters"] = [int(x) for x in cnt]
+            return out
+        t = self.PROF_TAGS[kernel]
         peaks_path = Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"
         peaks, src = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}, "fallback"
         if peaks_path.exists():
             peaks, src = json.load(open(peaks_path)), "measured"
         D, F = self.cfg.d_model, self.cfg.ffn
-        sec = max(ms.value, 1e-9) / 1e3
+        sec = max(ms[t], 1e-9) / 1e3
         hbm = {"ctc_prefix": cnt[0], "dec_cross_attn": cnt[2], "dec_self_attn": cnt[3]}
         if kernel in hbm:
             ach = hbm[kernel] / sec / 1e9
@@ -233,7 +245,7 @@ class StreamGroup:
             ach = flops / sec / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
             out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
-        out.update({"kernel": kernel, "launches": n.value, "kernel_ms_total": ms.value, "peak_source": src,
+        out.update({"kernel": kernel, "launches": int(n[t]), "kernel_ms_total": float(ms[t]), "peak_source": src,
                     "traffic": None, "search_iterations": int(cnt[4]), "active_rows_total": int(cnt[1])})
         return out
 
