@@ -3,6 +3,7 @@
 //
 // Replaces (batched, on device): speechcatcher/speech2text_streaming.py:402-464 (__call__),
 //   speechcatcher/beam_search/beam_search.py:507-653 (process_block) and everything below them.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -17,6 +18,8 @@ namespace scb {
 int launch_gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
                      int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int K, int relu,
                      const int* n_rows_dev, cudaStream_t st);
+int launch_dec_attention_mma(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
+                             __nv_bfloat16* out16, cudaStream_t st);
 int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
                         int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
                         int K, int relu, const int* n_rows_dev, cudaStream_t st);
@@ -73,7 +76,7 @@ struct Engine {
   // device buffers
   float *wbuf, *featbuf, *h1, *h2, *subbuf, *prev_addin, *enc_ctx, *addin, *X, *Nrm, *QKV, *Att, *FF, *encbuf, *ctcx;
   float *dx, *dn, *dqkv, *dq, *dattn, *dffn, *dlogp;
-  __nv_bfloat16 *Nrm16, *Att16, *FF16, *h2_16, *dn16, *dattn16, *dffn16, *encnew16;
+  __nv_bfloat16 *Nrm16, *Att16, *FF16, *h2_16, *dn16, *dattn16, *dffn16, *encnew16, *im2col16;
   SearchBuffers sb;
   // device descriptor arrays
   FrontendDesc* d_fd; SubDesc* d_sd; BlockDesc* d_blk;
@@ -87,6 +90,7 @@ struct Engine {
   std::unordered_map<std::string, std::pair<void*, size_t>> named;
   std::vector<ScStreamPlan> last_plan;
   int launches = 0;
+  bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
   // live kernel timing (bench.py roofline): CUDA-event pairs around every launch of one tagged kernel
   int prof_tag = 0;                 // 0 off, >0 one tag, -1 every tag (decode steps sampled every prof_stride)
   int prof_stride = 1;
@@ -143,6 +147,7 @@ static void carve(Engine& e, Carver& cv) {
     e.dn16 = cv.take<__nv_bfloat16>(R * D); e.dattn16 = cv.take<__nv_bfloat16>(R * D);
     e.dffn16 = cv.take<__nv_bfloat16>(R * F);
     e.encnew16 = cv.take<__nv_bfloat16>(S * k.sub_cap * D);
+    e.im2col16 = cv.take<__nv_bfloat16>((size_t)k.sub_rows_max * 19 * 9 * D);
   }
   SearchBuffers& sb = e.sb;
   sb.S = c.n_streams; sb.B = c.beam; sb.V = c.vocab; sb.D = c.d_model; sb.H = c.dec_heads; sb.Ld = c.dec_layers;
@@ -270,12 +275,14 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
     if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
     else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln1w, w.ln1b, e.dn, D, R, D, nr, st));
     PD(T_DEC_QKV, linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
-    PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
+    if (e.mma_attn) PD(T_DEC_SELF_ATTN, launch_dec_attention_mma(sb, 0, l, e.dqkv, 3 * D, e.dattn, e.dattn16, st));
+    else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
     PD(T_DEC_SO, linear(e, Lin{e.dattn, D, e.dattn16, w.sow, w.sow16, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
     if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln2w, w.ln2b, e.dn16, D, R, D, nr, st));
     else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln2w, w.ln2b, e.dn, D, R, D, nr, st));
     PD(T_DEC_CQ, linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
-    PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, e.dattn, tc ? e.dattn16 : nullptr, st));
+    if (e.mma_attn) PD(T_DEC_CROSS_ATTN, launch_dec_attention_mma(sb, 1, l, e.dq, D, e.dattn, e.dattn16, st));
+    else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, e.dattn, tc ? e.dattn16 : nullptr, st));
     PD(T_DEC_CO, linear(e, Lin{e.dattn, D, e.dattn16, w.cow, w.cow16, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
     if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
     else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln3w, w.ln3b, e.dn, D, R, D, nr, st));
@@ -350,6 +357,10 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   cudaEventCreateWithFlags(&e->ev[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev[1], cudaEventDisableTiming);
   e->enc.resize(cfg->enc_layers); e->dec.resize(cfg->dec_layers);
+  {
+    const char* a = getenv("SCB_ATTN");     // "simt" forces the CUDA-core attention kernels in the bf16 mode (A/B tests)
+    e->mma_attn = cfg->precision == 1 && cfg->beam <= 16 && !(a && strcmp(a, "simt") == 0);
+  }
   *handle = e;
   return SC_OK;
 }
@@ -407,7 +418,7 @@ int sc_engine_finalize(void* handle) {
   e->ctcw = getf("ctc.w"); e->ctcb = getf("ctc.b");
   e->demb = getf("dec.emb"); e->daw = getf("dec.after.w"); e->dab = getf("dec.after.b");
   e->doutw = getf("dec.out.w"); e->doutb = getf("dec.out.b");
-  e->eow16 = geth("enc.out.w"); e->ctcw16 = geth("ctc.w"); e->doutw16 = geth("dec.out.w");
+  e->eow16 = geth("enc.out.w"); e->ctcw16 = geth("ctc.w"); e->doutw16 = geth("dec.out.w"); e->c2w16 = geth("enc.conv2.w");
   for (int l = 0; l < e->cfg.enc_layers; ++l) {
     std::string p = "enc." + std::to_string(l) + ".";
     EncLayerW& w = e->enc[l];
@@ -583,24 +594,27 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   const bool tc = c.precision == 1;
   if (n_sd > 0) {
 #define e eref
-    PE(T_CONV1, launch_conv1(e.featbuf, k.feat_cap, e.c1w, e.c1b, e.h1, k.t1_cap, e.d_sd, n_sd, D, st));
-#undef e
-    TRY(launch_conv2_rows(e->d_sd, n_sd, k.t1_cap, k.sub_cap, D, e->d_c2_a, e->d_c2_c, st));
-    GemmArgs g;
-    g.A = e->h1; g.a_row_off = e->d_c2_a; g.a_seg_off = e->d_c2_seg; g.seg_len = D; g.W = e->c2w; g.bias = e->c2b;
-    g.C = e->h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
-    if (tc) { g.Cb = e->h2_16; g.ldcb = D; }
-#define e eref
-    if (e.prof_tag == T_CONV2) e.prof_flops += 2.0 * g.M * (double)g.N * g.K;
-    PE(T_CONV2, launch_gemm_f32(g, st));
-#undef e
-    {
-      Lin o{e->h2, 19 * D, e->h2_16, e->eow, e->eow16, e->eob, nullptr, 0, e->subbuf, 0, nullptr, sub_rows, D, 19 * D, 0, nullptr};
-      o.c_row_off = e->d_c2_c;
-#define e eref
-      PE(T_SUBOUT, linear(e, o, st));
-#undef e
+    PE(T_SUBOUT, launch_conv2_rows(e.d_sd, n_sd, k.t1_cap, k.sub_cap, D, e.d_c2_a, e.d_c2_c, st));
+    if (tc) {
+      // conv1 (+ReLU) fused with im2col -> bf16 A operand; conv2 and the output projection on tensor cores
+      PE(T_CONV1, launch_conv1_im2col_bf16(e.featbuf, k.feat_cap, e.c1w, e.c1b, e.im2col16, k.t2_cap, e.d_sd, n_sd, D, st));
+      if (e.prof_tag == T_CONV2) e.prof_flops += 2.0 * sub_rows * 19 * (double)D * 9 * D;
+      Lin g{nullptr, 9 * D, e.im2col16, e.c2w, e.c2w16, e.c2b, nullptr, 0, nullptr, D, e.h2_16, sub_rows * 19, D, 9 * D, 1, nullptr};
+      PE(T_CONV2, linear(e, g, st));
+    } else {
+      PE(T_CONV1, launch_conv1(e.featbuf, k.feat_cap, e.c1w, e.c1b, e.h1, k.t1_cap, e.d_sd, n_sd, D, st));
+      GemmArgs g;
+      g.A = e.h1; g.a_row_off = e.d_c2_a; g.a_seg_off = e.d_c2_seg; g.seg_len = D; g.W = e.c2w; g.bias = e.c2b;
+      g.C = e.h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
+      if (e.prof_tag == T_CONV2) e.prof_flops += 2.0 * g.M * (double)g.N * g.K;
+      PE(T_CONV2, launch_gemm_f32(g, st));
     }
+    {
+      Lin o{e.h2, 19 * D, e.h2_16, e.eow, e.eow16, e.eob, nullptr, 0, e.subbuf, 0, nullptr, sub_rows, D, 19 * D, 0, nullptr};
+      o.c_row_off = e.d_c2_c;
+      PE(T_SUBOUT, linear(e, o, st));
+    }
+#undef e
     e->launches += 4;
   }
   if (n_cf) { TRY(launch_carry_rows(e->featbuf, k.feat_cap, 80, e->d_carry_f, e->d_carry_f + S, e->d_carry_f + 2 * S, n_cf, st)); e->launches++; }

@@ -90,6 +90,8 @@ struct SubDesc {       // one per stream that runs conv2d subsampling in this pu
 };
 int launch_conv1(const float* featbuf, int feat_cap, const float* w1, const float* b1, float* h1, int t1_cap,
                  const SubDesc* desc, int n_desc, int D, cudaStream_t st);
+int launch_conv1_im2col_bf16(const float* featbuf, int feat_cap, const float* w1, const float* b1, __nv_bfloat16* A16,
+                             int t2_cap, const SubDesc* desc, int n_desc, int D, cudaStream_t st);
 int launch_conv2_rows(const SubDesc* desc, int n_desc, int t1_cap, int sub_cap, int D, int64_t* a_row_off,
                       int64_t* c_row_off, cudaStream_t st);
 // move rows [src, src+n) of buf[stream] (row width `width`, `cap` rows per stream) to the front

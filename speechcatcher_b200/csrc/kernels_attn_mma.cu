@@ -1,0 +1,308 @@
+// Decoder attention on tensor cores for the bf16 mode (bf16 K|V caches): flash-style, split-KV across the
+// four warps of a CTA, mma.sync.m16n8k16 (bf16 x bf16 -> fp32) for Q*K^T and P*V, K|V tiles streamed with
+// cp.async double buffering.  One CTA per (active stream, head); the <=16 hypotheses of the stream are the
+// 16 rows of the MMA tile, so every K|V byte is read once per stream and the kernel is HBM-bound instead
+// of shared-memory-issue bound like the fp32 SIMT variant in kernels_search.cu.
+//
+// Keys are an abstract list so that one kernel serves both attentions:
+//   cross: key u = encoder frame u of the stream (visible to every hypothesis);
+//   self : keys [0, Lc) = the beam's common ancestor chain (visible to all), followed by the divergent tail
+//          as (hypothesis, position) pairs, each visible to its own hypothesis only (owner mask).
+//
+// Replaces the attention part of speechcatcher/model/decoder/decoder_layer.py:80-113.
+#include "kernels.h"
+
+namespace scb {
+
+constexpr int MMA_TILE = 128;      // keys per tile (32 per warp)
+constexpr int MMA_MAXB = 16;       // rows of the m16 tile
+constexpr int MMA_ANC_B = 20;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_bf16(float* d, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int DK, int MODE>
+__global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __nv_bfloat16* kv_layer,
+                                                           const float* __restrict__ q, int ldq, int q_off,
+                                                           float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  const int head = blockIdx.y;
+  const StreamCtl& c = sb.ctl[s];
+  const int nb = c.n_hyp, row0 = sb.row_base[s], D = sb.D, B = sb.B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int RS = DK + 8;                 // padded smem row (bf16 elements): conflict-free ldmatrix
+  constexpr int CPR = DK / 8;                // 16-byte chunks per K (or V) row
+  constexpr int KSTEPS = DK / 16;
+  constexpr int NDT = DK / 8;                // n-tiles of the output
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);               // [16][RS]
+  __nv_bfloat16* Kt = Qs + 16 * RS;                                             // [2][TILE][RS]
+  __nv_bfloat16* Vt = Kt + 2 * MMA_TILE * RS;                                   // [2][TILE][RS]
+  signed char* own = reinterpret_cast<signed char*>(Vt + 2 * MMA_TILE * RS);    // [2][TILE]
+  int* s_lc = reinterpret_cast<int*>(own + 2 * MMA_TILE);
+  unsigned char* ancs = reinterpret_cast<unsigned char*>(s_lc + 4);             // self only: [MMA_ANC_B][Lcap]
+  // merge scratch aliases the K tiles after the main loop
+  float* mrg_m = reinterpret_cast<float*>(Kt);                                   // [4][16]
+  float* mrg_l = mrg_m + 64;                                                     // [4][16]
+  float* mrg_o = mrg_l + 64;                                                     // [4][16][DK]
+
+  const size_t row_stride = 2 * (size_t)D;
+  const int len = c.len;
+  __nv_bfloat16* base;
+  if (MODE == 1) base = kv_layer + (size_t)s * sb.Tcap * row_stride + head * DK;
+  else base = kv_layer + (size_t)s * sb.Lcap * B * row_stride + head * DK;
+
+  // ---- Q tile (rows >= nb are zero), self: append K|V and build the ancestor tables
+  for (int i = tid; i < 16 * DK; i += 128) {
+    const int r = i / DK, d = i % DK;
+    const float v = r < nb ? q[(size_t)(row0 + r) * ldq + q_off + head * DK + d] : 0.f;
+    Qs[r * RS + d] = __float2bfloat16(v);
+  }
+  int Lc = 0, n_div = 0, n_keys;
+  if (MODE == 0) {
+    if (tid == 0) {
+      *s_lc = len;
+      atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * 2));
+    }
+    for (int i = tid; i < nb * 2 * DK; i += 128) {
+      const int b = i / (2 * DK), rem = i % (2 * DK), which = rem / DK, cc = rem % DK;
+      const float v = q[(size_t)(row0 + b) * ldq + D + which * D + head * DK + cc];
+      base[((size_t)(len - 1) * B + b) * row_stride + which * D + cc] = __float2bfloat16(v);
+    }
+    for (int i = tid; i < nb * len; i += 128) {
+      const int b = i / len, j = i % len;
+      ancs[b * sb.Lcap + j] = (j == len - 1) ? (unsigned char)b : sb.anc[(((size_t)c.cur * sb.S + s) * B + b) * sb.Lcap + j];
+    }
+    __syncthreads();
+    for (int j = tid; j < len; j += 128) {
+      const unsigned char a0 = ancs[j];
+      bool same = true;
+      for (int b = 1; b < nb; ++b) same &= (ancs[b * sb.Lcap + j] == a0);
+      if (!same) atomicMin(s_lc, j);
+    }
+    __syncthreads();
+    Lc = *s_lc;
+    n_div = len - Lc;
+    n_keys = Lc + nb * n_div;
+  } else {
+    n_keys = c.Tb;
+    if (tid == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 2));
+  }
+  const int n_tiles = (n_keys + MMA_TILE - 1) / MMA_TILE;
+
+  auto issue_tile = [&](int t, int buf) {
+    const int u0 = t * MMA_TILE;
+    __nv_bfloat16* kd = Kt + (size_t)buf * MMA_TILE * RS;
+    __nv_bfloat16* vd = Vt + (size_t)buf * MMA_TILE * RS;
+    for (int idx = tid; idx < MMA_TILE * CPR; idx += 128) {
+      const int r = idx / CPR, ch = idx % CPR, u = u0 + r;
+      if (u < n_keys) {
+        const __nv_bfloat16* src;
+        int owner = -1;
+        if (MODE == 1) src = base + (size_t)u * row_stride;
+        else if (u < Lc) src = base + ((size_t)u * B + ancs[u]) * row_stride;
+        else {
+          const int p = u - Lc, b = p / n_div, j = Lc + p % n_div;
+          src = base + ((size_t)j * B + ancs[b * sb.Lcap + j]) * row_stride;
+          owner = b;
+        }
+        cp_async16(kd + r * RS + ch * 8, src + ch * 8);
+        cp_async16(vd + r * RS + ch * 8, src + D + ch * 8);
+        if (ch == 0) own[buf * MMA_TILE + r] = (signed char)owner;
+      } else {
+        *reinterpret_cast<uint4*>(kd + r * RS + ch * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(vd + r * RS + ch * 8) = make_uint4(0, 0, 0, 0);
+        if (ch == 0) own[buf * MMA_TILE + r] = (signed char)-2;      // invisible to everyone
+      }
+    }
+    cp_async_commit();
+  };
+
+  if (n_tiles > 0) issue_tile(0, 0);
+  __syncthreads();                      // Qs complete
+  uint32_t qa[KSTEPS][4];
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    ldsm_x4(qa[ks], Qs + ((lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 16 * ks + 8 * (lane >> 4));
+
+  const float inv_sqrt = 1.0f / sqrtf((float)DK);
+  const int r0 = lane >> 2, r1 = r0 + 8, qd = lane & 3;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[NDT][4];
+#pragma unroll
+  for (int i = 0; i < NDT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < n_tiles) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const __nv_bfloat16* kb = Kt + (size_t)buf * MMA_TILE * RS + (size_t)(32 * warp) * RS;
+    const __nv_bfloat16* vb = Vt + (size_t)buf * MMA_TILE * RS + (size_t)(32 * warp) * RS;
+    const signed char* ob = own + buf * MMA_TILE + 32 * warp;
+    // ---- S = Q K^T for this warp's 32 keys
+    float sacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        uint32_t bfr[2];
+        ldsm_x2(bfr, kb + (8 * nt + (lane & 7)) * RS + 16 * ks + 8 * ((lane >> 3) & 1));
+        mma_bf16(sacc[nt], qa[ks], bfr);
+      }
+    }
+    // ---- mask + online softmax (rows r0, r1 of this thread)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = 8 * nt + 2 * qd + (e & 1);
+        const int row = (e & 2) ? r1 : r0;
+        const int ow = ob[key];
+        const bool vis = row < nb && (ow == -1 || ow == row);
+        const float v = vis ? sacc[nt][e] * inv_sqrt : -INFINITY;
+        sacc[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float scale[2], psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      const float m_new = fmaxf(m_run[h], mx[h]);
+      scale[h] = (m_new == -INFINITY) ? 1.f : expf(m_run[h] - m_new);
+      m_run[h] = m_new;
+    }
+    uint32_t pa[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float mref = m_run[e >> 1];
+        p[e] = (mref == -INFINITY) ? 0.f : expf(sacc[nt][e] - mref);
+        psum[e >> 1] += p[e];
+      }
+      // C fragment of S -> A fragment of P: n-tile 2kk -> a0/a1, n-tile 2kk+1 -> a2/a3
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      psum[h] += __shfl_xor_sync(0xffffffffu, psum[h], 1);
+      psum[h] += __shfl_xor_sync(0xffffffffu, psum[h], 2);
+      l_run[h] = l_run[h] * scale[h] + psum[h];
+    }
+#pragma unroll
+    for (int nd = 0; nd < NDT; ++nd) { o[nd][0] *= scale[0]; o[nd][1] *= scale[0]; o[nd][2] *= scale[1]; o[nd][3] *= scale[1]; }
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int nd = 0; nd < NDT; ++nd) {
+        uint32_t bfr[2];
+        ldsm_x2_trans(bfr, vb + (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 8 * nd);
+        mma_bf16(o[nd], pa[kk], bfr);
+      }
+    }
+    __syncthreads();                    // tile fully consumed before its buffer is refilled
+  }
+  // ---- merge the four warps' partial (m, l, O)
+  if (qd == 0) {
+    mrg_m[warp * 16 + r0] = m_run[0]; mrg_m[warp * 16 + r1] = m_run[1];
+    mrg_l[warp * 16 + r0] = l_run[0]; mrg_l[warp * 16 + r1] = l_run[1];
+  }
+#pragma unroll
+  for (int nd = 0; nd < NDT; ++nd) {
+    float* dst = mrg_o + (size_t)warp * 16 * DK;
+    dst[r0 * DK + 8 * nd + 2 * qd] = o[nd][0]; dst[r0 * DK + 8 * nd + 2 * qd + 1] = o[nd][1];
+    dst[r1 * DK + 8 * nd + 2 * qd] = o[nd][2]; dst[r1 * DK + 8 * nd + 2 * qd + 1] = o[nd][3];
+  }
+  __syncthreads();
+  for (int i = tid; i < nb * DK; i += 128) {
+    const int r = i / DK, d = i % DK;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, mrg_m[w * 16 + r]);
+    float L = 0.f, acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = mrg_m[w * 16 + r];
+      const float f = (mw == -INFINITY) ? 0.f : expf(mw - M);
+      L += mrg_l[w * 16 + r] * f;
+      acc += mrg_o[((size_t)w * 16 + r) * DK + d] * f;
+    }
+    const float res = acc / L;
+    out[(size_t)(row0 + r) * D + head * DK + d] = res;
+    if (out16) out16[(size_t)(row0 + r) * D + head * DK + d] = __float2bfloat16(res);
+  }
+}
+
+template <int DK, int MODE>
+static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const float* q, int ldq, int q_off, float* out,
+                        __nv_bfloat16* out16, cudaStream_t st) {
+  constexpr int RS = DK + 8;
+  size_t smem = sizeof(__nv_bfloat16) * ((size_t)16 * RS + 4 * (size_t)MMA_TILE * RS) + 2 * MMA_TILE + 16;
+  if (MODE == 0) smem += (size_t)MMA_ANC_B * sb.Lcap;
+  const size_t merge = sizeof(float) * (128 + 4 * 16 * DK);
+  if (sizeof(__nv_bfloat16) * 2 * (size_t)MMA_TILE * RS < merge) { set_last_error("attn_mma: merge scratch does not fit"); return -1; }
+  static size_t attr = 0;
+  if (attr < smem) {
+    if (cudaFuncSetAttribute(dec_attn_mma_kernel<DK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_last_error("attn_mma: cudaFuncSetAttribute(%zu) failed", smem);
+      return -1;
+    }
+    attr = smem;
+  }
+  dim3 grid(sb.S, sb.H);
+  dec_attn_mma_kernel<DK, MODE><<<grid, 128, smem, st>>>(sb, kv_layer, q, ldq, q_off, out, out16);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// mode 0: self attention (q = fused QKV GEMM output, row stride ldq = 3D; K|V of the new token at +D);
+// mode 1: cross attention.  Requires bf16 KV caches and beam <= 16.
+int launch_dec_attention_mma(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
+                             __nv_bfloat16* out16, cudaStream_t st) {
+  if (!sb.kv_bf16 || sb.B > MMA_MAXB) { set_last_error("attn_mma: needs bf16 KV and beam <= %d", MMA_MAXB); return -1; }
+  const int dk = sb.D / sb.H;
+  __nv_bfloat16* kv = mode == 0
+      ? reinterpret_cast<__nv_bfloat16*>(sb.skv) + (size_t)layer * sb.S * sb.Lcap * sb.B * 2 * sb.D
+      : reinterpret_cast<__nv_bfloat16*>(sb.xkv) + (size_t)layer * sb.S * sb.Tcap * 2 * sb.D;
+  if (dk == 32) return mode == 0 ? launch_mma_t<32, 0>(sb, kv, q, ldq, 0, out, out16, st) : launch_mma_t<32, 1>(sb, kv, q, ldq, 0, out, out16, st);
+  if (dk == 64) return mode == 0 ? launch_mma_t<64, 0>(sb, kv, q, ldq, 0, out, out16, st) : launch_mma_t<64, 1>(sb, kv, q, ldq, 0, out, out16, st);
+  set_last_error("attn_mma: unsupported head dim %d", dk);
+  return -1;
+}
+
+}  // namespace scb

@@ -48,6 +48,54 @@ int launch_conv1(const float* featbuf, int feat_cap, const float* w1, const floa
   return 0;
 }
 
+// bf16 mode: conv1 + ReLU fused with the im2col of conv2.  One CTA per (stream, t2), thread = channel c.
+// A16[(row0 + t2) * 19 + f2][(kt * 3 + kf) * D + c] = bf16(relu(conv1(t1 = 2 t2 + kt, f1 = 2 f2 + kf, c))),
+// i.e. the dense K-major operand of the conv2 tensor-core GEMM (K = 9 D).  conv1 is only 9 MACs per
+// value, so recomputing it for the (at most four) windows a value belongs to is cheaper than a round trip.
+__global__ void __launch_bounds__(256) conv1_im2col_bf16_kernel(const float* __restrict__ featbuf, int feat_cap,
+                                                                const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                __nv_bfloat16* __restrict__ A16,
+                                                                const SubDesc* __restrict__ desc, int D) {
+  const SubDesc d = desc[blockIdx.y];
+  const int t2 = blockIdx.x;
+  if (t2 >= d.t2) return;
+  __shared__ float xin[7][NMEL];
+  const float* src = featbuf + ((size_t)d.stream * feat_cap + 4 * t2) * NMEL;
+  for (int i = threadIdx.x; i < 7 * NMEL; i += blockDim.x) xin[i / NMEL][i % NMEL] = src[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float w[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) w[i] = w1[c * 9 + i];
+  const float bias = b1[c];
+  __nv_bfloat16* dst = A16 + ((size_t)(d.row0 + t2) * F2) * 9 * D;
+  for (int f2 = 0; f2 < F2; ++f2) {
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+      for (int kf = 0; kf < 3; ++kf) {
+        const int f1 = 2 * f2 + kf;            // conv1 output column; its inputs are feature bins 2 f1 .. 2 f1 + 2
+        float acc = bias;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) acc = fmaf(w[a * 3 + b], xin[2 * kt + a][2 * f1 + b], acc);
+        dst[((size_t)f2 * 9 + kt * 3 + kf) * D + c] = __float2bfloat16(fmaxf(acc, 0.f));
+      }
+    }
+  }
+}
+
+int launch_conv1_im2col_bf16(const float* featbuf, int feat_cap, const float* w1, const float* b1, __nv_bfloat16* A16,
+                             int t2_cap, const SubDesc* desc, int n_desc, int D, cudaStream_t st) {
+  if (n_desc <= 0) return 0;
+  if (D != 256) { set_last_error("conv1_im2col: D=%d unsupported", D); return -1; }
+  dim3 grid(t2_cap, n_desc);
+  conv1_im2col_bf16_kernel<<<grid, 256, 0, st>>>(featbuf, feat_cap, w1, b1, A16, desc, D);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
 // Row tables for the conv2 implicit GEMM (rows = (stream, t2, f2)) and for the output projection
 // (rows = (stream, t2) -> subbuf[stream][sub_off + t2]).
 __global__ void conv2_rows_kernel(const SubDesc* __restrict__ desc, int t1_cap, int sub_cap, int D,

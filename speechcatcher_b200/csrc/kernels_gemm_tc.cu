@@ -21,7 +21,6 @@ namespace scb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 192;
 constexpr int UMMA_K = 16;
 
@@ -96,7 +95,7 @@ struct TcParams {
   const int64_t* c_row_off; int M, N, K, relu; const int* n_rows_dev;
 };
 
-template <int BN>
+template <int BN, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b,
                                                                      TcParams p) {
@@ -269,19 +268,19 @@ static int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CU
   return 0;
 }
 
-template <int BN>
+template <int BN, int TC_STAGES>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = 1024 + TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(smem=%zu) failed", smem);
       return -1;
     }
     attr_set = true;
   }
   dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
-  gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
+  gemm_bf16_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -300,7 +299,11 @@ int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
   if (get_map(A, M, K, lda, TC_BM, &ma)) return -1;
   if (get_map(W, N, K, K, BN, &mb)) return -1;
   TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev};
-  return small ? launch_bn<64>(ma, mb, p, st) : launch_bn<128>(ma, mb, p, st);
+  // K <= 256 has only four K-blocks: two stages (48-64 KB) let three CTAs share an SM so that one CTA's
+  // epilogue overlaps another's main loop; deeper K keeps the four-stage ring
+  const bool shallow = K / TC_BK <= 4;
+  if (small) return shallow ? launch_bn<64, 2>(ma, mb, p, st) : launch_bn<64, 4>(ma, mb, p, st);
+  return shallow ? launch_bn<128, 2>(ma, mb, p, st) : launch_bn<128, 4>(ma, mb, p, st);
 }
 
 int launch_gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,

@@ -424,7 +424,11 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(SearchBuffers sb, c
         for (int b = 0; b < nb; ++b) {
           float d = 0.f;
 #pragma unroll
-          for (int i = 0; i < DK; ++i) d = fmaf(qs[b * DK + i], kreg[i], d);
+          for (int i = 0; i < DK; i += 4) {        // one broadcast LDS.128 per four FMAs, same summation order
+            const float4 qv = *reinterpret_cast<const float4*>(qs + b * DK + i);
+            d = fmaf(qv.x, kreg[i], d); d = fmaf(qv.y, kreg[i + 1], d);
+            d = fmaf(qv.z, kreg[i + 2], d); d = fmaf(qv.w, kreg[i + 3], d);
+          }
           sc[b * TILE + tid] = d / sqrt_dk;
         }
       } else {
@@ -461,13 +465,26 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(SearchBuffers sb, c
       const int b = g + i * G;
       if (b < nb) acc[i] *= sm_f[b];
     }
-#pragma unroll 4
-    for (int jj = 0; jj < jn; ++jj) {
-      const float v = Vs[jj * DK + cdim];
+    {
+      int jj = 0;
+      for (; jj + 4 <= jn; jj += 4) {           // same accumulation order as the scalar loop
+        const float v0 = Vs[jj * DK + cdim], v1 = Vs[(jj + 1) * DK + cdim];
+        const float v2 = Vs[(jj + 2) * DK + cdim], v3 = Vs[(jj + 3) * DK + cdim];
 #pragma unroll
-      for (int i = 0; i < NACC; ++i) {
-        const int b = g + i * G;
-        if (b < nb) acc[i] = fmaf(sc[b * TILE + jj], v, acc[i]);
+        for (int i = 0; i < NACC; ++i) {
+          const int b = g + i * G;
+          if (b < nb) {
+            const float4 p4 = *reinterpret_cast<const float4*>(sc + b * TILE + jj);
+            float a = acc[i];
+            a = fmaf(p4.x, v0, a); a = fmaf(p4.y, v1, a); a = fmaf(p4.z, v2, a); a = fmaf(p4.w, v3, a);
+            acc[i] = a;
+          }
+        }
+      }
+      for (; jj < jn; ++jj) {
+        const float v = Vs[jj * DK + cdim];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) { const int b = g + i * G; if (b < nb) acc[i] = fmaf(sc[b * TILE + jj], v, acc[i]); }
       }
     }
   }
@@ -612,7 +629,11 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(SearchBuffers sb, KV
         for (int b = 0; b < nb; ++b) {
           float d = 0.f;
 #pragma unroll
-          for (int i = 0; i < DK; ++i) d = fmaf(qs[b * DK + i], kreg[i], d);
+          for (int i = 0; i < DK; i += 4) {        // one broadcast LDS.128 per four FMAs, same summation order
+            const float4 qv = *reinterpret_cast<const float4*>(qs + b * DK + i);
+            d = fmaf(qv.x, kreg[i], d); d = fmaf(qv.y, kreg[i + 1], d);
+            d = fmaf(qv.z, kreg[i + 2], d); d = fmaf(qv.w, kreg[i + 3], d);
+          }
           sc[b * TILE + tid] = d / sqrt_dk;
         }
       } else {
@@ -643,11 +664,27 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(SearchBuffers sb, KV
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NACC; ++i) { const int b = g + i * G; if (b < nb) acc[i] *= sm_f[b]; }
-#pragma unroll 4
-    for (int jj = 0; jj < jn; ++jj) {
-      const float v = Vs[jj * DK + cdim];
+    {
+      int jj = 0;
+      for (; jj + 4 <= jn; jj += 4) {           // same accumulation order as the scalar loop
+        const float v0 = Vs[jj * DK + cdim], v1 = Vs[(jj + 1) * DK + cdim];
+        const float v2 = Vs[(jj + 2) * DK + cdim], v3 = Vs[(jj + 3) * DK + cdim];
 #pragma unroll
-      for (int i = 0; i < NACC; ++i) { const int b = g + i * G; if (b < nb) acc[i] = fmaf(sc[b * TILE + jj], v, acc[i]); }
+        for (int i = 0; i < NACC; ++i) {
+          const int b = g + i * G;
+          if (b < nb) {
+            const float4 p4 = *reinterpret_cast<const float4*>(sc + b * TILE + jj);
+            float a = acc[i];
+            a = fmaf(p4.x, v0, a); a = fmaf(p4.y, v1, a); a = fmaf(p4.z, v2, a); a = fmaf(p4.w, v3, a);
+            acc[i] = a;
+          }
+        }
+      }
+      for (; jj < jn; ++jj) {
+        const float v = Vs[jj * DK + cdim];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) { const int b = g + i * G; if (b < nb) acc[i] = fmaf(sc[b * TILE + jj], v, acc[i]); }
+      }
     }
   }
   // ---------------- divergent tail: flat list of (hypothesis, position) pairs, ordered by hypothesis

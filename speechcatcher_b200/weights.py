@@ -90,7 +90,7 @@ def pack_weights(sd: Dict[str, torch.Tensor], enc_layers: int, dec_layers: int, 
 
 # GEMM weights that get a bf16 copy in the tensor-core mode
 def bf16_names(enc_layers: int, dec_layers: int):
-    names = ["enc.out.w", "ctc.w", "dec.out.w"]
+    names = ["enc.out.w", "enc.conv2.w", "ctc.w", "dec.out.w"]
     for l in range(enc_layers):
         names += [f"enc.{l}.{n}.w" for n in ("qkv", "o", "ff1", "ff2")]
     for l in range(dec_layers):

@@ -1,0 +1,58 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (stream sharding + the end-of-run result gather)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from speechcatcher_b200.sharding import owner_of, shard_range
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_streams, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from speechcatcher_b200.sharding import gather_results
+    lo, hi = shard_range(n_streams, world, rank)
+    local = {s: dict(tokens=[s, s + 1], rank=rank) for s in range(lo, hi)}
+    allr = gather_results(local)
+    t = torch.tensor([float(hi - lo)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)          # same pattern as bench.py's max-over-ranks time
+    q.put((rank, sorted(allr), [allr[s]["rank"] for s in sorted(allr)], t.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_streams", [7, 512])
+def test_shard_and_gather_world2(n_streams):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_streams, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, ids, owners, mx in got:
+        assert ids == list(range(n_streams))
+        assert owners == [owner_of(s, n_streams, 2) for s in range(n_streams)]
+        assert mx == float(shard_range(n_streams, 2, 0)[1])
+
+
+def test_shard_range_partitions():
+    for n in (1, 5, 256, 2048):
+        for w in (1, 2, 4, 8):
+            cover = []
+            for r in range(w):
+                lo, hi = shard_range(n, w, r)
+                cover += list(range(lo, hi))
+            assert cover == list(range(n))
