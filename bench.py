@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--breakdown", action="store_true", help="always run the all-kernel timing pass")
+    ap.add_argument("--lazy", type=int, default=int(os.environ.get("SCB_BENCH_LAZY", "-1")),
+                    help="deferred-decode threshold (streams); 0 = strict per-push decoding; -1 = streams/2")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -189,6 +191,8 @@ def main():
         host[s, :n_samples] = torch.from_numpy(synth_audio(rank * S + s, n_samples))
     grp = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype=args.dtype,
                       use_bbd=False, max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
+    lazy = args.lazy if args.lazy >= 0 else S // 2
+    grp.set_option("lazy_threshold", lazy)
     resident = host.to(dev)                           # inputs resident in HBM for `value`
     ids = np.arange(S, dtype=np.int32)
     lens_all = [np.full(S, min(CHUNK, n_samples - c * CHUNK), np.int32) for c in range(n_chunks)]
@@ -294,6 +298,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.dtype == "float32" else "bf16", "data": "synthetic",
                 "config": {"workload": workload, "l2": "inputs larger than L2 (983 MB of waveforms per GPU)",
+                           "decode_scheduling": ("strict: every push drains its decode blocks" if lazy == 0 else
+                                                 f"deferred: a push stops iterating below {lazy} active streams; final calls drain"),
                            "decode_steps_per_pass": stats["steps"] // max(1, args.steps),
                            "encoder_blocks_per_pass": stats["blocks"] // max(1, args.steps)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": stats["launches"],

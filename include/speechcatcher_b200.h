@@ -101,6 +101,13 @@ int sc_engine_last_plan(void* handle, int32_t stream_id, ScStreamPlan* plan);
 /* Named internal device buffer (tests / debugging): pointer, element count and row pitch. */
 int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem);
 
+/* Engine options.  "lazy_threshold" = n > 0: a push stops iterating the beam search once fewer than n streams
+ * are still active and leaves the stragglers' decode blocks queued on the device (they continue during later
+ * pushes; any final call drains everything), which trades per-call completeness of non-final beams for fewer,
+ * fuller search iterations.  0 (default) = strict: every push fully decodes its blocks like the reference.
+ * "mma_attention" = 0/1: CUDA-core or tensor-core decoder attention in the bf16 mode. */
+int sc_engine_set_option(void* handle, const char* name, int32_t value);
+
 /* Live kernel timing with CUDA-event pairs on the launching stream (bench.py roofline and step breakdown).
  * tag > 0: every launch of that kernel; tag = -1: every kernel, decode steps sampled every `stride` steps.
  * Tags: 1 ctc_prefix, 2 dec_self_attn, 3 dec_cross_attn, 4 dec_ffn1, 5 enc_ffn1, 6 prebeam, 7 enc_attn, 8 conv2,

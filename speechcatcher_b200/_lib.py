@@ -45,6 +45,7 @@ SYMBOLS = {
     "sc_engine_read_beam": (C.c_int, [_vp, _i32, _i32, _pi32, _pi32, _pi32, _vp, _vp, _vp, _vp]),
     "sc_engine_last_plan": (C.c_int, [_vp, _i32, C.POINTER(ScStreamPlan)]),
     "sc_engine_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_sz)]),
+    "sc_engine_set_option": (C.c_int, [_vp, C.c_char_p, _i32]),
     "sc_engine_profile_begin": (C.c_int, [_vp, _i32, _i32, _i32]),
     "sc_engine_profile_end": (C.c_int, [_vp, _i32, _pi32, _pd, _pd, C.POINTER(C.c_uint64)]),
     "sc_planner_create": (C.c_int, [_i32, C.POINTER(_vp)]),

@@ -27,7 +27,7 @@ int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Caps {
-  int feat_cap, t1_cap, t2_cap, sub_cap, nb_cap, qcap, Tcap, Lcap, nb_max, rows_max, sub_rows_max, R;
+  int feat_cap, t1_cap, t2_cap, sub_cap, nb_cap, qpush, qcap, Tcap, Lcap, nb_max, rows_max, sub_rows_max, R;
 };
 
 static Caps make_caps(const ScConfig& c) {
@@ -39,7 +39,8 @@ static Caps make_caps(const ScConfig& c) {
   k.t2_cap = std::max(1, (k.t1_cap - 3) / 2 + 1);
   k.sub_cap = 40 + k.t2_cap + 1;
   k.nb_cap = std::max(1, (k.sub_cap - 24 + 15) / 16);
-  k.qcap = k.nb_cap + 2;
+  k.qpush = k.nb_cap + 2;                                // decode blocks one push can queue per stream
+  k.qcap = 16 * k.qpush;                                 // device queue: room for deferred blocks of earlier pushes
   k.Tcap = c.max_frames;
   // hypotheses grow by one token per completed iteration (<= max_length 500) plus one for every block whose
   // first iteration already ends in <eos> (kept without a rewind, beam_search.py:827): bound by the block count
@@ -91,6 +92,10 @@ struct Engine {
   std::vector<ScStreamPlan> last_plan;
   int launches = 0;
   bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
+  // deferred decoding: a push stops iterating once fewer than `lazy_threshold` streams are active and leaves
+  // the stragglers' blocks queued on the device; they continue during later pushes (0 = strict, drain every push)
+  int lazy_threshold = 0;
+  std::vector<int> pending_bound;   // host upper bound of queued blocks per stream
   // live kernel timing (bench.py roofline): CUDA-event pairs around every launch of one tagged kernel
   int prof_tag = 0;                 // 0 off, >0 one tag, -1 every tag (decode steps sampled every prof_stride)
   int prof_stride = 1;
@@ -101,7 +106,7 @@ struct Engine {
   int prof_used = 0;
   double prof_flops = 0.0;          // host-known algorithmic FLOPs of the tagged launches (encoder GEMMs)
 
-  explicit Engine(const ScConfig& c) : cfg(c), cap(make_caps(c)), planner(c.n_streams), last_plan(c.n_streams) {}
+  explicit Engine(const ScConfig& c) : cfg(c), cap(make_caps(c)), planner(c.n_streams), pending_bound(c.n_streams, 0), last_plan(c.n_streams) {}
 };
 
 // ---------------------------------------------------------------- workspace carving
@@ -184,7 +189,7 @@ static void carve(Engine& e, Carver& cv) {
   e.d_en_a = cv.take<int64_t>(S * k.sub_cap); e.d_en_ctc = cv.take<int64_t>(S * k.sub_cap);
   e.d_en_kv = cv.take<int64_t>(S * k.sub_cap); e.d_en_flag = cv.take<int>(S * k.sub_cap);
   e.d_c2_seg = cv.take<int>(16);
-  e.d_q = cv.take<int>(2 * S + 2 * S * k.qcap);
+  e.d_q = cv.take<int>(2 * S + 2 * S * k.qpush);
   e.d_reset = cv.take<int>(S);
 }
 
@@ -350,7 +355,7 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   const Caps& k = e->cap;
   const size_t S = cfg->n_streams;
   e->h_stage_bytes = sizeof(FrontendDesc) * S + sizeof(SubDesc) * S + sizeof(BlockDesc) * k.nb_max + sizeof(int) * (6 * S) +
-                     (sizeof(int64_t) * 3 + sizeof(int)) * S * k.sub_cap + sizeof(int) * (2 * S + 2 * S * k.qcap) + sizeof(int) * S + 4096;
+                     (sizeof(int64_t) * 3 + sizeof(int)) * S * k.sub_cap + sizeof(int) * (2 * S + 2 * S * k.qpush) + sizeof(int) * S + 4096;
   if (cudaMallocHost(&e->h_stage, e->h_stage_bytes) != cudaSuccess || cudaMallocHost(&e->h_flag, 4 * sizeof(int)) != cudaSuccess) {
     set_last_error("pinned host allocation failed"); delete e; return SC_ERR_CUDA;
   }
@@ -460,6 +465,7 @@ int sc_engine_reset(void* handle, const int32_t* streams, int32_t n, void* strea
   for (int i = 0; i < n; ++i) {
     if (streams[i] < 0 || streams[i] >= e->cfg.n_streams) { set_last_error("bad stream id %d", streams[i]); return SC_ERR_ARG; }
     e->planner.reset(streams[i]);
+    e->pending_bound[streams[i]] = 0;
   }
   int* hs = (int*)e->h_stage;
   memcpy(hs, streams, n * sizeof(int));
@@ -518,9 +524,10 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   int64_t* h_en_ctc = (int64_t*)stage(sizeof(int64_t) * S * k.sub_cap);
   int64_t* h_en_kv = (int64_t*)stage(sizeof(int64_t) * S * k.sub_cap);
   int* h_en_flag = (int*)stage(sizeof(int) * S * k.sub_cap);
-  int* h_q = (int*)stage(sizeof(int) * (2 * S + 2 * S * k.qcap));
+  int* h_q = (int*)stage(sizeof(int) * (2 * S + 2 * S * k.qpush));
   int n_fd = 0, n_fd_all = 0, n_sd = 0, n_blk = 0, n_cf = 0, n_cs = 0, n_en = 0, n_q = 0, frame_base = 0, sub_rows = 0;
   int n_feat_total = 0;
+  bool need_drain = false, any_final = false;
   // frontend descriptors: emitting ones first (frame_base indexing), buffer-only ones after
   std::vector<FrontendDesc> buf_only;
   for (int i = 0; i < n; ++i) {
@@ -556,12 +563,14 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
       n_en++;
     }
     if (!p.dq_T.empty()) {
-      if ((int)p.dq_T.size() > k.qcap) { set_last_error("decode queue capacity exceeded"); return SC_ERR_CAPACITY; }
+      if ((int)p.dq_T.size() > k.qpush) { set_last_error("decode queue capacity exceeded"); return SC_ERR_CAPACITY; }
       h_q[n_q] = s; h_q[S + n_q] = (int)p.dq_T.size();
       for (size_t j = 0; j < p.dq_T.size(); ++j) {
-        h_q[2 * S + n_q * k.qcap + j] = p.dq_T[j];
-        h_q[2 * S + S * k.qcap + n_q * k.qcap + j] = p.dq_final[j];
+        h_q[2 * S + n_q * k.qpush + j] = p.dq_T[j];
+        h_q[2 * S + S * k.qpush + n_q * k.qpush + j] = p.dq_final[j];
       }
+      if (e->pending_bound[s] + (int)p.dq_T.size() > k.qcap) need_drain = true;
+      if (is_final[i]) any_final = true;
       n_q++;
     }
   }
@@ -580,7 +589,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   TRY(up(e->d_en_ctc, h_en_ctc, sizeof(int64_t) * n_en));
   TRY(up(e->d_en_kv, h_en_kv, sizeof(int64_t) * n_en));
   TRY(up(e->d_en_flag, h_en_flag, sizeof(int) * n_en));
-  if (n_q) TRY(up(e->d_q, h_q, sizeof(int) * (2 * S + 2 * S * k.qcap)));
+  if (n_q) TRY(up(e->d_q, h_q, sizeof(int) * (2 * S + 2 * S * k.qpush)));
   // ---------------- frontend
 #define e eref
   const bool petot = prof_on(e, T_ENC_TOTAL, false);
@@ -668,13 +677,11 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   if (petot) prof_mark(eref, T_ENC_TOTAL, st, false);
   // ---------------- block-synchronous beam search
   int steps = 0;
-  TRY(launch_search_begin(e->sb, e->d_q, e->d_q + S, e->d_q + 2 * S, e->d_q + 2 * S + S * k.qcap, n_q, st));
-  e->launches += 2;
-  SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[0], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  SCB_CUDA_CHECK(cudaEventRecord(e->ev[0], st));
-  if (n_q == 0) {
-    SCB_CUDA_CHECK(cudaEventSynchronize(e->ev[0]));
-  } else {
+  // the loop stops when fewer than `stop_below` streams are active: 1 = drain (strict mode, final calls)
+  const int stop_below = (e->lazy_threshold > 0 && !any_final) ? e->lazy_threshold : 1;
+  auto decode_loop = [&](int below) -> int {
+    SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[0], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCB_CUDA_CHECK(cudaEventRecord(e->ev[0], st));
     // one step is always in flight ahead of the host's view of n_active (kernels of an empty step exit at once)
     for (int i = 0;; ++i) {
       TRY(run_decode_step(*e, st));
@@ -682,14 +689,31 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
       SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[2 * ((i + 1) & 1)], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
       SCB_CUDA_CHECK(cudaEventRecord(e->ev[(i + 1) & 1], st));
       SCB_CUDA_CHECK(cudaEventSynchronize(e->ev[i & 1]));
-      if (e->h_flag[2 * (i & 1)] == 0) break;
-      if (steps > 4 * kMaxLength + 64) { set_last_error("decode loop did not terminate"); return SC_ERR_STATE; }
+      if (e->h_flag[2 * (i & 1)] < below) break;
+      if (steps > 64 * kMaxLength) { set_last_error("decode loop did not terminate"); return SC_ERR_STATE; }
     }
     SCB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (e->h_flag[1] || e->h_flag[3]) {
-      set_last_error("a hypothesis outgrew the token capacity (%d); raise max_frames", k.Lcap);
+      set_last_error("decode capacity exceeded (flag %d): token capacity %d / queue capacity %d", e->h_flag[1] | e->h_flag[3], k.Lcap, k.qcap);
       return SC_ERR_CAPACITY;
     }
+    return 0;
+  };
+  if (need_drain) {                                   // deferred blocks would overflow a device queue: drain first
+    TRY(decode_loop(1));
+    std::fill(e->pending_bound.begin(), e->pending_bound.end(), 0);
+  }
+  TRY(launch_search_begin(e->sb, e->d_q, e->d_q + S, e->d_q + 2 * S, e->d_q + 2 * S + S * k.qpush, k.qpush, n_q, st));
+  e->launches += 2;
+  for (int i = 0; i < n; ++i) e->pending_bound[streams[i]] += (int)plans[i].dq_T.size();
+  bool pending_any = false;
+  for (int v : e->pending_bound) pending_any |= v > 0;
+  if (!pending_any) {
+    SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+  } else {
+    TRY(decode_loop(stop_below));
+    const int last = e->h_flag[0] < e->h_flag[2] ? e->h_flag[0] : e->h_flag[2];
+    if (stop_below == 1 || last == 0) std::fill(e->pending_bound.begin(), e->pending_bound.end(), 0);
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -735,6 +759,15 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
   if (it == e->named.end()) { set_last_error("unknown buffer %s", name); return SC_ERR_ARG; }
   *ptr = it->second.first; *n_elem = it->second.second;
   return SC_OK;
+}
+
+int sc_engine_set_option(void* handle, const char* name, int32_t value) {
+  Engine* e = (Engine*)handle;
+  if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
+  if (strcmp(name, "lazy_threshold") == 0) { e->lazy_threshold = value < 0 ? 0 : value; return SC_OK; }
+  if (strcmp(name, "mma_attention") == 0) { e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16; return SC_OK; }
+  set_last_error("unknown option %s", name);
+  return SC_ERR_ARG;
 }
 
 // ---------------- live kernel timing

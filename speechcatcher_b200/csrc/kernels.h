@@ -171,9 +171,9 @@ struct SearchBuffers {
 };
 
 int launch_search_reset(const SearchBuffers& sb, const int* streams, int n, cudaStream_t st);
-// q_T / q_final: [n_q][qcap]
+// q_T / q_final: [n_q][q_stride] entries of this push, appended to each stream's pending queue
 int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int* q_n, const int* q_T,
-                        const int* q_final, int n_q, cudaStream_t st);
+                        const int* q_final, int q_stride, int n_q, cudaStream_t st);
 int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, cudaStream_t st);
 // mode 0: self attention over the tree KV store (appends this step's K|V first); mode 1: cross attention
 int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,

@@ -100,22 +100,31 @@ __device__ void advance_blocks(const SearchBuffers& sb, int s, StreamCtl& c) {
   }
 }
 
-// Queue the decode blocks of this push and start the first one.  One CTA per queued stream.
+// Queue the decode blocks of this push (appended behind blocks still pending from earlier pushes when the
+// engine defers decoding) and start the first one if the stream is idle.  One CTA per queued stream.
 __global__ void search_begin_kernel(SearchBuffers sb, const int* __restrict__ q_stream, const int* __restrict__ q_n,
-                                    const int* __restrict__ q_T, const int* __restrict__ q_final) {
+                                    const int* __restrict__ q_T, const int* __restrict__ q_final, int q_stride) {
   __shared__ StreamCtl c;
   const int s = q_stream[blockIdx.x];
   if (threadIdx.x == 0) {
     c = sb.ctl[s];
-    c.blk_count = q_n[blockIdx.x];
-    c.blk_next = 0;
-    for (int i = 0; i < c.blk_count; ++i) {
-      sb.blkq_T[s * sb.qcap + i] = q_T[blockIdx.x * sb.qcap + i];
-      sb.blkq_final[s * sb.qcap + i] = q_final[blockIdx.x * sb.qcap + i];
+    const int rem = c.blk_count - c.blk_next;
+    int* qT = sb.blkq_T + (size_t)s * sb.qcap;
+    int* qF = sb.blkq_final + (size_t)s * sb.qcap;
+    if (c.blk_next > 0)
+      for (int i = 0; i < rem; ++i) { qT[i] = qT[c.blk_next + i]; qF[i] = qF[c.blk_next + i]; }
+    const int n_new = q_n[blockIdx.x];
+    for (int i = 0; i < n_new && rem + i < sb.qcap; ++i) {
+      qT[rem + i] = q_T[blockIdx.x * q_stride + i];
+      qF[rem + i] = q_final[blockIdx.x * q_stride + i];
     }
+    if (rem + n_new > sb.qcap) sb.n_active[1] = 2;          // queue overflow (host keeps a bound; must not happen)
+    c.blk_count = min(rem + n_new, sb.qcap);
+    c.blk_next = 0;
   }
   __syncthreads();
-  advance_blocks(sb, s, c);
+  if (!c.active) advance_blocks(sb, s, c);
+  __syncthreads();
   if (threadIdx.x == 0) sb.ctl[s] = c;
 }
 
@@ -166,9 +175,9 @@ __global__ void compact_rows_kernel(SearchBuffers sb) {
 }
 
 int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int* q_n, const int* q_T,
-                        const int* q_final, int n_q, cudaStream_t st) {
+                        const int* q_final, int q_stride, int n_q, cudaStream_t st) {
   if (n_q > 0) {
-    search_begin_kernel<<<n_q, 64, 0, st>>>(sb, q_stream, q_n, q_T, q_final);
+    search_begin_kernel<<<n_q, 64, 0, st>>>(sb, q_stream, q_n, q_T, q_final, q_stride);
     SCB_LAUNCH_CHECK();
   }
   compact_rows_kernel<<<1, 1024, 0, st>>>(sb);

@@ -131,6 +131,10 @@ class StreamGroup:
         except Exception:
             pass
 
+    def set_option(self, name: str, value: int):
+        """Engine options: "lazy_threshold" (deferred decoding, see include/speechcatcher_b200.h), "mma_attention"."""
+        _lib.check(self.lib.sc_engine_set_option(self.handle, name.encode(), int(value)), f"set_option({name})")
+
     def reset(self, streams: Optional[Sequence[int]] = None):
         ids = np.asarray(list(range(self.n_streams)) if streams is None else list(streams), np.int32)
         with torch.cuda.device(self.device):

@@ -83,3 +83,32 @@ def test_reset_reuses_stream_slot():
             assert [r[2] for r in a] == [r[2] for r in b]
             assert [r[0] for r in a] == [r[0] for r in b]
         assert gpu.beam_state[0] == [list(h.yseq) for h in orc.hyps]
+
+
+def test_deferred_decoding_same_final_results():
+    """Deferred (lazy) decoding only reorders when queued decode blocks run: every stream's final n-best must
+    equal the oracle's exactly (fp32 mode), even though non-final beams lag behind."""
+    from oracle.speech2text import OracleSpeech2Text
+    from speechcatcher_b200 import StreamGroup
+    from speechcatcher_b200.synthetic import synth_audio
+    md = model_dir("m_d2")
+    S, n = 6, 5 * 16000 + 321
+    audio = [synth_audio(70 + s, n) for s in range(S)]
+    grp = StreamGroup(md, n_streams=S, beam_size=5, device="cuda:0", max_seconds=8)
+    grp.set_option("lazy_threshold", 4)
+    total_steps = 0
+    for i in range(0, n, 8192):
+        fin = i + 8192 >= n
+        st = grp.push(list(range(S)), [a[i:i + 8192] for a in audio], [fin] * S)
+        total_steps += st.n_decode_steps
+    for s in range(S):
+        orc = OracleSpeech2Text(md, beam_size=5)
+        for i in range(0, n, 8192):
+            fin = i + 8192 >= n
+            want = orc(audio[s][i:i + 8192], is_final=fin, finalize_all=fin)
+        ys, sc, xp, pidx = grp.beam(s)
+        assert ys == [list(h.yseq) for h in orc.hyps]
+        assert xp == [list(h.xpos) for h in orc.hyps]
+        np.testing.assert_allclose(sc, [h.score for h in orc.hyps], atol=2e-3, rtol=0)
+        assert [r[2] for r in grp.results(s, True, True)] == [r[2] for r in want]
+    assert total_steps > 0
