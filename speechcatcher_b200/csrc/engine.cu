@@ -20,6 +20,8 @@ int launch_gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, co
                      const int* n_rows_dev, cudaStream_t st);
 int launch_dec_attention_mma(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
                              __nv_bfloat16* out16, cudaStream_t st);
+int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
+                             int n_head, int d_model, cudaStream_t st);
 int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
                         int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
                         int K, int relu, const int* n_rows_dev, cudaStream_t st);
@@ -77,7 +79,7 @@ struct Engine {
   // device buffers
   float *wbuf, *featbuf, *h1, *h2, *subbuf, *prev_addin, *enc_ctx, *addin, *X, *Nrm, *QKV, *Att, *FF, *encbuf, *ctcx;
   float *dx, *dn, *dqkv, *dq, *dattn, *dffn, *dlogp;
-  __nv_bfloat16 *Nrm16, *Att16, *FF16, *h2_16, *dn16, *dattn16, *dffn16, *encnew16, *im2col16;
+  __nv_bfloat16 *Nrm16, *Att16, *FF16, *h2_16, *dn16, *dattn16, *dffn16, *encnew16, *im2col16, *QKV16;
   SearchBuffers sb;
   // device descriptor arrays
   FrontendDesc* d_fd; SubDesc* d_sd; BlockDesc* d_blk;
@@ -92,6 +94,7 @@ struct Engine {
   std::vector<ScStreamPlan> last_plan;
   int launches = 0;
   bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
+  bool mma_enc = false;             // bf16 mode: tensor-core encoder block attention
   // deferred decoding: a push stops iterating once fewer than `lazy_threshold` streams are active and leaves
   // the stragglers' blocks queued on the device; they continue during later pushes (0 = strict, drain every push)
   int lazy_threshold = 0;
@@ -153,6 +156,7 @@ static void carve(Engine& e, Carver& cv) {
     e.dffn16 = cv.take<__nv_bfloat16>(R * F);
     e.encnew16 = cv.take<__nv_bfloat16>(S * k.sub_cap * D);
     e.im2col16 = cv.take<__nv_bfloat16>((size_t)k.sub_rows_max * 19 * 9 * D);
+    e.QKV16 = cv.take<__nv_bfloat16>((size_t)k.rows_max * 3 * D);
   }
   SearchBuffers& sb = e.sb;
   sb.S = c.n_streams; sb.B = c.beam; sb.V = c.vocab; sb.D = c.d_model; sb.H = c.dec_heads; sb.Ld = c.dec_layers;
@@ -182,6 +186,8 @@ static void carve(Engine& e, Carver& cv) {
   sb.cand_ctc = cv.take<float>(R * B); sb.cand_psi = cv.take<float>(R * B); sb.cand_col = cv.take<int>(R * B);
   sb.new_parent = cv.take<int>(S * B); sb.new_col = cv.take<int>(S * B); sb.upd_flag = cv.take<int>(S);
   sb.prof = cv.take<unsigned long long>(8);
+  sb.key_cap = (int)(B * k.Lcap);
+  sb.self_keys = cv.take<int>(S * (size_t)sb.key_cap); sb.self_nkeys = cv.take<int>(S);
   // descriptors
   e.d_fd = cv.take<FrontendDesc>(S); e.d_sd = cv.take<SubDesc>(S); e.d_blk = cv.take<BlockDesc>(k.nb_max);
   e.d_carry_f = cv.take<int>(3 * S); e.d_carry_s = cv.take<int>(3 * S);
@@ -251,8 +257,13 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
     const EncLayerW& w = e.enc[l];
     if (tc) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln1w, w.ln1b, e.Nrm16, D, rows, D, nullptr, st));
     else PE(T_ENC_LN, launch_layernorm(e.X, D, w.ln1w, w.ln1b, e.Nrm, D, rows, D, nullptr, st));
-    PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
-    PE(T_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
+    if (e.mma_enc) {
+      PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, nullptr, 3 * D, e.QKV16, rows, 3 * D, D, 0, nullptr}, st));
+      PE(T_ENC_ATTN, launch_enc_attention_mma(e.QKV16, nullptr, e.Att16, e.d_blk, n_blk, c.enc_heads, D, st));
+    } else {
+      PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
+      PE(T_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
+    }
     PE(T_ENC_O, linear(e, Lin{e.Att, D, e.Att16, w.ow, w.ow16, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
     if (tc) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
     else PE(T_ENC_LN, launch_layernorm(e.X, D, w.ln2w, w.ln2b, e.Nrm, D, rows, D, nullptr, st));
@@ -275,6 +286,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   const bool ptot = prof_on(e, T_DEC_STEP_TOTAL, true);
   if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, true);
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, st));
+  if (e.mma_attn) PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
     if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
@@ -365,6 +377,7 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   {
     const char* a = getenv("SCB_ATTN");     // "simt" forces the CUDA-core attention kernels in the bf16 mode (A/B tests)
     e->mma_attn = cfg->precision == 1 && cfg->beam <= 16 && !(a && strcmp(a, "simt") == 0);
+    e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
   }
   *handle = e;
   return SC_OK;
@@ -765,7 +778,11 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   Engine* e = (Engine*)handle;
   if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
   if (strcmp(name, "lazy_threshold") == 0) { e->lazy_threshold = value < 0 ? 0 : value; return SC_OK; }
-  if (strcmp(name, "mma_attention") == 0) { e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16; return SC_OK; }
+  if (strcmp(name, "mma_attention") == 0) {
+    e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16;
+    e->mma_enc = value != 0 && e->cfg.precision == 1;
+    return SC_OK;
+  }
   set_last_error("unknown option %s", name);
   return SC_ERR_ARG;
 }

@@ -101,6 +101,8 @@ int launch_block_assemble(const float* subbuf, int sub_cap, const float* pe, con
                           float* addin, float* prev_addin, float* X, int D, cudaStream_t st);
 int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                          int n_head, int d_model, cudaStream_t st);
+int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
+                             int n_head, int d_model, cudaStream_t st);
 int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const BlockDesc* blk, int n_blk,
                         int D, cudaStream_t st);
 int launch_stitch_norm(const float* X, const BlockDesc* blk, int n_blk, const float* w, const float* b,
@@ -166,6 +168,9 @@ struct SearchBuffers {
   int* new_parent;        // [S][B] parent slot of each new hypothesis (this step)
   int* new_col;           // [S][B]
   int* upd_flag;          // [S] 1 -> the CTC state of the new beam must be written this step
+  int* self_keys;         // [S][key_cap] per-step key list of the self-attention KV tree (see build_self_keys)
+  int* self_nkeys;        // [S]
+  int key_cap;
   unsigned long long* prof;   // [8] device counters: 0 ctc algorithmic bytes, 1 sum of active rows,
                               //     2 cross-attention KV bytes, 3 self-attention KV bytes, 4 search iterations
 };
@@ -180,6 +185,10 @@ int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const flo
                          const float* kv_new, int ldkv, float* out, __nv_bfloat16* out16, cudaStream_t st);
 int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
                               __nv_bfloat16* out16, cudaStream_t st);
+// Key list of the self-attention KV tree, built once per search iteration and shared by all layers and heads:
+// key u < Lc = position u of the beam's common ancestor chain; later keys = (hypothesis, position) pairs of the
+// divergent tail.  Packed as position | slot << 16 | (owner + 1) << 24 (owner 0 = visible to every hypothesis).
+int launch_build_self_keys(const SearchBuffers& sb, cudaStream_t st);
 int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
                                __nv_bfloat16* out16, cudaStream_t st);
 int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st);

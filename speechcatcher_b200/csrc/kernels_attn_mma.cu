@@ -47,6 +47,54 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One CTA per active stream, once per search iteration.
+__global__ void __launch_bounds__(128) build_self_keys_kernel(SearchBuffers sb) {
+  if ((int)blockIdx.x >= *sb.n_active) return;
+  const int s = sb.act_streams[blockIdx.x];
+  const StreamCtl& c = sb.ctl[s];
+  const int nb = c.n_hyp, len = c.len, B = sb.B, tid = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char ancs[];       // [nb][Lcap]
+  __shared__ int s_lc;
+  if (tid == 0) s_lc = len;
+  const int words = sb.Lcap / 4;
+  for (int i = tid; i < nb * words; i += 128) {               // rows are Lcap (multiple of 32) bytes: 4-byte loads
+    const int b = i / words, w = i % words;
+    const unsigned int* src = reinterpret_cast<const unsigned int*>(sb.anc + (((size_t)c.cur * sb.S + s) * B + b) * sb.Lcap);
+    reinterpret_cast<unsigned int*>(ancs + (size_t)b * sb.Lcap)[w] = (4 * w < len) ? src[w] : 0u;
+  }
+  __syncthreads();
+  if (tid < nb) ancs[(size_t)tid * sb.Lcap + len - 1] = (unsigned char)tid;     // the scored token lives at the own slot
+  __syncthreads();
+  for (int j = tid; j < len; j += 128) {
+    const unsigned char a0 = ancs[j];
+    bool same = true;
+    for (int b = 1; b < nb; ++b) same &= (ancs[(size_t)b * sb.Lcap + j] == a0);
+    if (!same) atomicMin(&s_lc, j);
+  }
+  __syncthreads();
+  const int Lc = s_lc, n_div = len - Lc, n_keys = Lc + nb * n_div;
+  int* keys = sb.self_keys + (size_t)s * sb.key_cap;
+  for (int u = tid; u < n_keys && u < sb.key_cap; u += 128) {
+    int j, slot, owner;
+    if (u < Lc) { j = u; slot = ancs[u]; owner = -1; }
+    else { const int p = u - Lc; owner = p / n_div; j = Lc + p % n_div; slot = ancs[(size_t)owner * sb.Lcap + j]; }
+    keys[u] = j | (slot << 16) | ((owner + 1) << 24);
+  }
+  if (tid == 0) sb.self_nkeys[s] = min(n_keys, sb.key_cap);
+}
+
+int launch_build_self_keys(const SearchBuffers& sb, cudaStream_t st) {
+  const size_t smem = (size_t)sb.B * sb.Lcap;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && attr < smem) {
+    cudaFuncSetAttribute(build_self_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  build_self_keys_kernel<<<sb.S, 128, smem, st>>>(sb);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int DK, int MODE>
 __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __nv_bfloat16* kv_layer,
                                                            const float* __restrict__ q, int ldq, int q_off,
@@ -67,8 +115,6 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
   __nv_bfloat16* Kt = Qs + 16 * RS;                                             // [2][TILE][RS]
   __nv_bfloat16* Vt = Kt + 2 * MMA_TILE * RS;                                   // [2][TILE][RS]
   signed char* own = reinterpret_cast<signed char*>(Vt + 2 * MMA_TILE * RS);    // [2][TILE]
-  int* s_lc = reinterpret_cast<int*>(own + 2 * MMA_TILE);
-  unsigned char* ancs = reinterpret_cast<unsigned char*>(s_lc + 4);             // self only: [MMA_ANC_B][Lcap]
   // merge scratch aliases the K tiles after the main loop
   float* mrg_m = reinterpret_cast<float*>(Kt);                                   // [4][16]
   float* mrg_l = mrg_m + 64;                                                     // [4][16]
@@ -86,32 +132,18 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
     const float v = r < nb ? q[(size_t)(row0 + r) * ldq + q_off + head * DK + d] : 0.f;
     Qs[r * RS + d] = __float2bfloat16(v);
   }
-  int Lc = 0, n_div = 0, n_keys;
+  int n_keys;
+  const int* keys = nullptr;
   if (MODE == 0) {
-    if (tid == 0) {
-      *s_lc = len;
-      atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * 2));
-    }
-    for (int i = tid; i < nb * 2 * DK; i += 128) {
+    if (tid == 0) atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * 2));
+    for (int i = tid; i < nb * 2 * DK; i += 128) {        // append K|V of the scored token at [len-1][b]
       const int b = i / (2 * DK), rem = i % (2 * DK), which = rem / DK, cc = rem % DK;
       const float v = q[(size_t)(row0 + b) * ldq + D + which * D + head * DK + cc];
       base[((size_t)(len - 1) * B + b) * row_stride + which * D + cc] = __float2bfloat16(v);
     }
-    for (int i = tid; i < nb * len; i += 128) {
-      const int b = i / len, j = i % len;
-      ancs[b * sb.Lcap + j] = (j == len - 1) ? (unsigned char)b : sb.anc[(((size_t)c.cur * sb.S + s) * B + b) * sb.Lcap + j];
-    }
-    __syncthreads();
-    for (int j = tid; j < len; j += 128) {
-      const unsigned char a0 = ancs[j];
-      bool same = true;
-      for (int b = 1; b < nb; ++b) same &= (ancs[b * sb.Lcap + j] == a0);
-      if (!same) atomicMin(s_lc, j);
-    }
-    __syncthreads();
-    Lc = *s_lc;
-    n_div = len - Lc;
-    n_keys = Lc + nb * n_div;
+    n_keys = sb.self_nkeys[s];
+    keys = sb.self_keys + (size_t)s * sb.key_cap;
+    __syncthreads();                    // appended rows visible to the tile loads below
   } else {
     n_keys = c.Tb;
     if (tid == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 2));
@@ -128,11 +160,10 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
         const __nv_bfloat16* src;
         int owner = -1;
         if (MODE == 1) src = base + (size_t)u * row_stride;
-        else if (u < Lc) src = base + ((size_t)u * B + ancs[u]) * row_stride;
         else {
-          const int p = u - Lc, b = p / n_div, j = Lc + p % n_div;
-          src = base + ((size_t)j * B + ancs[b * sb.Lcap + j]) * row_stride;
-          owner = b;
+          const int kd_ = keys[u];
+          src = base + ((size_t)(kd_ & 0xffff) * B + ((kd_ >> 16) & 0xff)) * row_stride;
+          owner = (kd_ >> 24) - 1;
         }
         cp_async16(kd + r * RS + ch * 8, src + ch * 8);
         cp_async16(vd + r * RS + ch * 8, src + D + ch * 8);
@@ -268,12 +299,139 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
   }
 }
 
+// ---------------------------------------------------------------- encoder block attention on tensor cores (bf16 mode)
+// One CTA (3 warps) per (block, head): the 42 block rows padded to 48 = three m16 tiles, one per warp; each warp
+// holds all 48 keys of its 16 query rows, so the masked softmax needs no cross-warp exchange.
+// Mask as in the fp32 kernel: rows 1..41 attend keys 0..40 (short path: rows/keys < n_rows, no mask).
+template <int DK>
+__global__ void __launch_bounds__(96) enc_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv16, float* __restrict__ out,
+                                                          __nv_bfloat16* __restrict__ out16,
+                                                          const BlockDesc* __restrict__ blk, int D) {
+  const BlockDesc b = blk[blockIdx.x];
+  const int head = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int RS = DK + 8, CPR = DK / 8, KSTEPS = DK / 16, NDT = DK / 8, ROWS = 48;
+  __shared__ __align__(16) __nv_bfloat16 Qs[ROWS * RS];
+  __shared__ __align__(16) __nv_bfloat16 Ks[ROWS * RS];
+  __shared__ __align__(16) __nv_bfloat16 Vs[ROWS * RS];
+  const __nv_bfloat16* base = qkv16 + (size_t)blockIdx.x * kSlots * 3 * D + head * DK;
+  for (int idx = tid; idx < ROWS * CPR; idx += 96) {
+    const int r = idx / CPR, ch = idx % CPR;
+    if (r < kSlots) {
+      const __nv_bfloat16* src = base + (size_t)r * 3 * D + ch * 8;
+      cp_async16(Qs + r * RS + ch * 8, src);
+      cp_async16(Ks + r * RS + ch * 8, src + D);
+      cp_async16(Vs + r * RS + ch * 8, src + 2 * D);
+    } else {
+      *reinterpret_cast<uint4*>(Qs + r * RS + ch * 8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Ks + r * RS + ch * 8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Vs + r * RS + ch * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int q_lo = b.short_path ? 0 : 1, q_hi = b.short_path ? b.n_rows : kSlots;
+  const int k_hi = b.short_path ? b.n_rows : kBlock + 1;
+  uint32_t qa[KSTEPS][4];
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    ldsm_x4(qa[ks], Qs + (16 * warp + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 16 * ks + 8 * (lane >> 4));
+  float sacc[6][4];
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt) {
+    sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      uint32_t bfr[2];
+      ldsm_x2(bfr, Ks + (8 * nt + (lane & 7)) * RS + 16 * ks + 8 * ((lane >> 3) & 1));
+      mma_bf16(sacc[nt], qa[ks], bfr);
+    }
+  }
+  const float inv_sqrt = 1.0f / sqrtf((float)DK);
+  const int r0 = 16 * warp + (lane >> 2), r1 = r0 + 8, qd = lane & 3;
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int key = 8 * nt + 2 * qd + (e & 1);
+      const int row = (e & 2) ? r1 : r0;
+      const bool vis = row >= q_lo && row < q_hi && key < k_hi;
+      const float v = vis ? sacc[nt][e] * inv_sqrt : -INFINITY;
+      sacc[nt][e] = v;
+      mx[e >> 1] = fmaxf(mx[e >> 1], v);
+    }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+  }
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float m = mx[e >> 1];
+      const float p = (m == -INFINITY) ? 0.f : expf(sacc[nt][e] - m);
+      sacc[nt][e] = p;
+      sum[e >> 1] += p;
+    }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 2);
+    sum[h] = sum[h] > 0.f ? 1.0f / sum[h] : 0.f;
+  }
+  uint32_t pa[3][4];
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt) {
+    pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(sacc[nt][0] * sum[0], sacc[nt][1] * sum[0]);
+    pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(sacc[nt][2] * sum[1], sacc[nt][3] * sum[1]);
+  }
+  float o[NDT][4];
+#pragma unroll
+  for (int nd = 0; nd < NDT; ++nd) {
+    o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      uint32_t bfr[2];
+      ldsm_x2_trans(bfr, Vs + (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 8 * nd);
+      mma_bf16(o[nd], pa[kk], bfr);
+    }
+  }
+#pragma unroll
+  for (int nd = 0; nd < NDT; ++nd) {
+    const int col = head * DK + 8 * nd + 2 * qd;
+    if (r0 < kSlots) {
+      const size_t off = ((size_t)blockIdx.x * kSlots + r0) * D + col;
+      *reinterpret_cast<uint32_t*>(out16 + off) = pack_bf16(o[nd][0], o[nd][1]);
+      if (out) { out[off] = o[nd][0]; out[off + 1] = o[nd][1]; }
+    }
+    if (r1 < kSlots) {
+      const size_t off = ((size_t)blockIdx.x * kSlots + r1) * D + col;
+      *reinterpret_cast<uint32_t*>(out16 + off) = pack_bf16(o[nd][2], o[nd][3]);
+      if (out) { out[off] = o[nd][2]; out[off + 1] = o[nd][3]; }
+    }
+  }
+}
+
+int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
+                             int n_head, int d_model, cudaStream_t st) {
+  if (n_blk <= 0) return 0;
+  dim3 grid(n_blk, n_head);
+  const int dk = d_model / n_head;
+  if (dk == 32) enc_attn_mma_kernel<32><<<grid, 96, 0, st>>>(qkv16, out, out16, blk, d_model);
+  else if (dk == 64) enc_attn_mma_kernel<64><<<grid, 96, 0, st>>>(qkv16, out, out16, blk, d_model);
+  else { set_last_error("enc_attn_mma: unsupported head dim %d", dk); return -1; }
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int DK, int MODE>
 static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const float* q, int ldq, int q_off, float* out,
                         __nv_bfloat16* out16, cudaStream_t st) {
   constexpr int RS = DK + 8;
   size_t smem = sizeof(__nv_bfloat16) * ((size_t)16 * RS + 4 * (size_t)MMA_TILE * RS) + 2 * MMA_TILE + 16;
-  if (MODE == 0) smem += (size_t)MMA_ANC_B * sb.Lcap;
   const size_t merge = sizeof(float) * (128 + 4 * 16 * DK);
   if (sizeof(__nv_bfloat16) * 2 * (size_t)MMA_TILE * RS < merge) { set_last_error("attn_mma: merge scratch does not fit"); return -1; }
   static size_t attr = 0;

@@ -19,20 +19,22 @@ def run(kind, arch, beam, n_streams, seconds):
     audio = np.stack([synth_audio(50 + s, n) for s in range(n_streams)])
     grp = StreamGroup(md, n_streams=n_streams, beam_size=beam, device="cuda:0", dtype="bfloat16", max_seconds=seconds + 2)
     ids = np.arange(n_streams, dtype=np.int32)
-    logs, beams = [], []
+    logs, beams, encs = [], [], []
     for i in range(0, n, 8192):
         fin = i + 8192 >= n
         ch = [audio[s, i:i + 8192] for s in range(n_streams)]
         grp.push(ids, ch, [fin] * n_streams)
         logs.append(grp.buffer("dlogp").view(-1, 1024)[: n_streams * beam].clone().cpu())
         beams.append([grp.beam(s)[0] for s in range(n_streams)])
-    return logs, beams
+    encs = grp.buffer("encbuf").view(n_streams, -1, 256)[:, : int(seconds * 25) - 8].clone().cpu()
+    return logs, beams, encs
 
 
 def main():
     for arch, beam in (("xl_d4", 10), ("m_d2", 5)):
-        a_logs, a_beams = run("simt", arch, beam, 4, 5.0)
-        b_logs, b_beams = run("mma", arch, beam, 4, 5.0)
+        a_logs, a_beams, a_enc = run("simt", arch, beam, 4, 5.0)
+        b_logs, b_beams, b_enc = run("mma", arch, beam, 4, 5.0)
+        print(f"{arch}: encoder output max |simt - mma| = {float((a_enc - b_enc).abs().max()):.5f} (scale {float(a_enc.abs().max()):.2f})")
         first_div = None
         for i, (x, y) in enumerate(zip(a_beams, b_beams)):
             if x != y and first_div is None:
