@@ -105,7 +105,8 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
  * are still active and leaves the stragglers' decode blocks queued on the device (they continue during later
  * pushes; any final call drains everything), which trades per-call completeness of non-final beams for fewer,
  * fuller search iterations.  0 (default) = strict: every push fully decodes its blocks like the reference.
- * "mma_attention" = 0/1: CUDA-core or tensor-core decoder attention in the bf16 mode. */
+ * "mma_attention" = 0/1: CUDA-core or tensor-core attention in the bf16 mode.  "pdl" = 0/1: programmatic dependent
+ * launch of the decode-step kernel chain (process-wide).  "fuse_layernorm" = 0/1: experimental LN-in-epilogue GEMMs. */
 int sc_engine_set_option(void* handle, const char* name, int32_t value);
 
 /* Live kernel timing with CUDA-event pairs on the launching stream (bench.py roofline and step breakdown).
@@ -136,6 +137,11 @@ int sc_linear_f32(const float* x, const float* w, const float* bias, const float
 /* same contract on the tcgen05 tensor-core path: bf16 operands, fp32 accumulate */
 int sc_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual,
                    float* y_f32, void* y_bf16, int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
+
+/* y = x W^T + bias + residual (N = 256) with the LayerNorm of every finished row fused into the epilogue:
+ * ln_out = bf16(LayerNorm(y) * ln_w + ln_b), eps 1e-12 */
+int sc_linear_bf16_ln(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual, float* y_f32,
+                      const float* ln_w, const float* ln_b, void* ln_out_bf16, int32_t m, int32_t k, void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,4 +60,25 @@ __device__ __forceinline__ float lse2(float a, float b) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): the decode step is a chain of ~170 small dependent kernels, so the launch
+// and CTA-scheduling latency of kernel N+1 is overlapped with the execution of kernel N.  Every kernel launched
+// through launch_k() MUST call pdl_sync() as its first statement (before any early exit): griddepcontrol.wait
+// blocks until the preceding grid has completed and its writes are visible, so ordering is exactly that of a
+// plain stream; launch_dependents then lets the next grid's CTAs be scheduled while this one runs.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+extern bool g_use_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace scb

@@ -22,9 +22,10 @@ int launch_dec_attention_mma(const SearchBuffers& sb, int mode, int layer, const
                              __nv_bfloat16* out16, cudaStream_t st);
 int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                              int n_head, int d_model, cudaStream_t st);
-int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
+int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
                         int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
-                        int K, int relu, const int* n_rows_dev, cudaStream_t st);
+                        int K, int relu, const int* n_rows_dev, const float* ln_w, const float* ln_b,
+                        __nv_bfloat16* ln_out, cudaStream_t st);
 
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -95,6 +96,10 @@ struct Engine {
   int launches = 0;
   bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
   bool mma_enc = false;             // bf16 mode: tensor-core encoder block attention
+  // bf16 mode, experimental: fuse every LayerNorm into the epilogue of the GEMM producing its input (BN = 256 tiles).
+  // Correct (tests/test_gpu_gemm_tc.py) but currently slower than separate LayerNorm kernels: the one-row-per-thread
+  // epilogue over 256 columns serialises too much and BN = 256 leaves few CTAs; off by default.
+  bool fuse_ln = false;
   // deferred decoding: a push stops iterating once fewer than `lazy_threshold` streams are active and leaves
   // the stragglers' blocks queued on the device; they continue during later pushes (0 = strict, drain every push)
   int lazy_threshold = 0;
@@ -204,14 +209,17 @@ struct Lin {
   const float* A; int lda; const __nv_bfloat16* A16; const float* W; const __nv_bfloat16* W16; const float* bias;
   const float* R; int ldr; float* C; int ldc; __nv_bfloat16* C16; int M, N, K, relu; const int* n_rows_dev;
   const int64_t* c_row_off = nullptr;
+  const float* ln_w = nullptr; const float* ln_b = nullptr; __nv_bfloat16* ln_out = nullptr;   // bf16 mode: fused LayerNorm
 };
+
+static Lin with_ln(Lin l, const float* w, const float* b, __nv_bfloat16* out) { l.ln_w = w; l.ln_b = b; l.ln_out = out; return l; }
 
 static int linear(Engine& e, const Lin& l, cudaStream_t st) {
   e.launches++;
   if (e.cfg.precision == 1) {
     if (!l.A16 || !l.W16) { set_last_error("bf16 mode: missing bf16 operand for a %dx%dx%d linear", l.M, l.N, l.K); return -1; }
-    return launch_gemm_bf16_ex(l.A16, l.lda, l.W16, l.bias, l.R, l.ldr, l.C, l.ldc, l.C16, l.ldc, l.c_row_off, l.M, l.N,
-                               l.K, l.relu, l.n_rows_dev, st);
+    return launch_gemm_bf16_ln(l.A16, l.lda, l.W16, l.bias, l.R, l.ldr, l.C, l.ldc, l.C16, l.ldc, l.c_row_off, l.M, l.N,
+                               l.K, l.relu, l.n_rows_dev, l.ln_w, l.ln_b, l.ln_out, st);
   }
   GemmArgs g;
   g.A = l.A; g.lda = l.lda; g.W = l.W; g.bias = l.bias; g.R = l.R; g.ldr = l.ldr; g.C = l.C; g.ldc = l.ldc;
@@ -253,10 +261,18 @@ static inline void prof_mark(Engine& e, int tag, cudaStream_t st, bool begin) {
 static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, rows = n_blk * kSlots;
   const bool tc = c.precision == 1;
+  const bool fl = tc && e.fuse_ln;
+  // fused mode: only the first LayerNorm is a kernel of its own; every other norm rides in the epilogue of the GEMM
+  // that produces its input (O-proj -> norm2, FFN2 -> next layer's norm1; the hand-over re-normalises slot 0)
+  if (fl) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, e.enc[0].ln1w, e.enc[0].ln1b, e.Nrm16, D, rows, D, nullptr, st));
+  auto ln = [&](const float* w, const float* b) -> int {
+    if (tc) return launch_layernorm_bf16(e.X, D, w, b, e.Nrm16, D, rows, D, nullptr, st);
+    return launch_layernorm(e.X, D, w, b, e.Nrm, D, rows, D, nullptr, st);
+  };
   for (int l = 0; l < c.enc_layers; ++l) {
     const EncLayerW& w = e.enc[l];
-    if (tc) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln1w, w.ln1b, e.Nrm16, D, rows, D, nullptr, st));
-    else PE(T_ENC_LN, launch_layernorm(e.X, D, w.ln1w, w.ln1b, e.Nrm, D, rows, D, nullptr, st));
+    const EncLayerW* nx = l + 1 < c.enc_layers ? &e.enc[l + 1] : nullptr;
+    if (!fl) PE(T_ENC_LN, ln(w.ln1w, w.ln1b));
     if (e.mma_enc) {
       PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, nullptr, 3 * D, e.QKV16, rows, 3 * D, D, 0, nullptr}, st));
       PE(T_ENC_ATTN, launch_enc_attention_mma(e.QKV16, nullptr, e.Att16, e.d_blk, n_blk, c.enc_heads, D, st));
@@ -264,14 +280,22 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
       PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
       PE(T_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
     }
-    PE(T_ENC_O, linear(e, Lin{e.Att, D, e.Att16, w.ow, w.ow16, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr}, st));
-    if (tc) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
-    else PE(T_ENC_LN, launch_layernorm(e.X, D, w.ln2w, w.ln2b, e.Nrm, D, rows, D, nullptr, st));
+    {
+      Lin o{e.Att, D, e.Att16, w.ow, w.ow16, w.ob, e.X, D, e.X, D, nullptr, rows, D, D, 0, nullptr};
+      if (fl) o = with_ln(o, w.ln2w, w.ln2b, e.Nrm16);
+      PE(T_ENC_O, linear(e, o, st));
+    }
+    if (!fl) PE(T_ENC_LN, ln(w.ln2w, w.ln2b));
     if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
     PE(T_ENC_FFN1, linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
-    PE(T_ENC_FFN2, linear(e, Lin{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr}, st));
-    PE(T_ENC_HANDOVER, launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, st));
-    e.launches += 4;
+    {
+      Lin f2{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr};
+      if (fl && nx) f2 = with_ln(f2, nx->ln1w, nx->ln1b, e.Nrm16);
+      PE(T_ENC_FFN2, linear(e, f2, st));
+    }
+    PE(T_ENC_HANDOVER, launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, (fl && nx) ? nx->ln1w : nullptr,
+                                           (fl && nx) ? nx->ln1b : nullptr, e.Nrm16, st));
+    e.launches += fl ? 2 : 4;
   }
   return 0;
 }
@@ -285,30 +309,44 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   e.prof_sample = (e.step_seq++ % e.prof_stride) == 0;
   const bool ptot = prof_on(e, T_DEC_STEP_TOTAL, true);
   if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, true);
-  PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, st));
+  const bool fl = tc && e.fuse_ln;
+  auto ln = [&](const float* w, const float* b) -> int {
+    if (tc) return launch_layernorm_bf16(e.dx, D, w, b, e.dn16, D, R, D, nr, st);
+    return launch_layernorm(e.dx, D, w, b, e.dn, D, R, D, nr, st);
+  };
+  PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, fl ? e.dec[0].ln1w : nullptr, fl ? e.dec[0].ln1b : nullptr, e.dn16, st));
   if (e.mma_attn) PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
-    if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln1w, w.ln1b, e.dn16, D, R, D, nr, st));
-    else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln1w, w.ln1b, e.dn, D, R, D, nr, st));
+    // bf16 mode: norm1 comes fused from dec_embed / the previous layer's FFN2, norm2 from self-O, norm3 from cross-O
+    if (!fl) PD(T_DEC_LN, ln(w.ln1w, w.ln1b));
     PD(T_DEC_QKV, linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_SELF_ATTN, launch_dec_attention_mma(sb, 0, l, e.dqkv, 3 * D, e.dattn, e.dattn16, st));
     else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
-    PD(T_DEC_SO, linear(e, Lin{e.dattn, D, e.dattn16, w.sow, w.sow16, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
-    if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln2w, w.ln2b, e.dn16, D, R, D, nr, st));
-    else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln2w, w.ln2b, e.dn, D, R, D, nr, st));
+    {
+      Lin o{e.dattn, D, e.dattn16, w.sow, w.sow16, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr};
+      if (fl) o = with_ln(o, w.ln2w, w.ln2b, e.dn16);
+      PD(T_DEC_SO, linear(e, o, st));
+    }
+    if (!fl) PD(T_DEC_LN, ln(w.ln2w, w.ln2b));
     PD(T_DEC_CQ, linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_CROSS_ATTN, launch_dec_attention_mma(sb, 1, l, e.dq, D, e.dattn, e.dattn16, st));
     else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, e.dattn, tc ? e.dattn16 : nullptr, st));
-    PD(T_DEC_CO, linear(e, Lin{e.dattn, D, e.dattn16, w.cow, w.cow16, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr}, st));
-    if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
-    else PD(T_DEC_LN, launch_layernorm(e.dx, D, w.ln3w, w.ln3b, e.dn, D, R, D, nr, st));
+    {
+      Lin o{e.dattn, D, e.dattn16, w.cow, w.cow16, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr};
+      if (fl) o = with_ln(o, w.ln3w, w.ln3b, e.dn16);
+      PD(T_DEC_CO, linear(e, o, st));
+    }
+    if (!fl) PD(T_DEC_LN, ln(w.ln3w, w.ln3b));
     PD(T_DEC_FFN1, linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
-    PD(T_DEC_FFN2, linear(e, Lin{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr}, st));
-    e.launches += 5;
+    {
+      Lin f2{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr};
+      if (fl) f2 = (l + 1 < c.dec_layers) ? with_ln(f2, e.dec[l + 1].ln1w, e.dec[l + 1].ln1b, e.dn16) : with_ln(f2, e.daw, e.dab, e.dn16);
+      PD(T_DEC_FFN2, linear(e, f2, st));
+    }
+    e.launches += fl ? 2 : 5;
   }
-  if (tc) PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, e.daw, e.dab, e.dn16, D, R, D, nr, st));
-  else PD(T_DEC_LN, launch_layernorm(e.dx, D, e.daw, e.dab, e.dn, D, R, D, nr, st));
+  if (!fl) PD(T_DEC_LN, ln(e.daw, e.dab));
   PD(T_DEC_OUT, linear(e, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
   PD(T_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
   PD(T_CTC_PREFIX, launch_ctc_prefix(sb, st));
@@ -378,6 +416,8 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     const char* a = getenv("SCB_ATTN");     // "simt" forces the CUDA-core attention kernels in the bf16 mode (A/B tests)
     e->mma_attn = cfg->precision == 1 && cfg->beam <= 16 && !(a && strcmp(a, "simt") == 0);
     e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
+    const char* pdl = getenv("SCB_PDL");     // programmatic dependent launch of the decode-step kernel chain (default on)
+    g_use_pdl = !(pdl && strcmp(pdl, "0") == 0);
   }
   *handle = e;
   return SC_OK;
@@ -778,6 +818,8 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   Engine* e = (Engine*)handle;
   if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
   if (strcmp(name, "lazy_threshold") == 0) { e->lazy_threshold = value < 0 ? 0 : value; return SC_OK; }
+  if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
+  if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = value != 0 && e->cfg.precision == 1; return SC_OK; }
   if (strcmp(name, "mma_attention") == 0) {
     e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16;
     e->mma_enc = value != 0 && e->cfg.precision == 1;
@@ -858,6 +900,12 @@ int sc_linear_bf16(const void* x, const void* w, const float* bias, const float*
                    int32_t n, int32_t k, int32_t relu, void* stream) {
   return launch_gemm_bf16((const __nv_bfloat16*)x, k, (const __nv_bfloat16*)w, bias, residual, n, y, n, (__nv_bfloat16*)y16, n,
                           m, n, k, relu, nullptr, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+
+int sc_linear_bf16_ln(const void* x, const void* w, const float* bias, const float* residual, float* y, const float* ln_w,
+                      const float* ln_b, void* ln_out_bf16, int32_t m, int32_t k, void* stream) {
+  return launch_gemm_bf16_ln((const __nv_bfloat16*)x, k, (const __nv_bfloat16*)w, bias, residual, 256, y, 256, nullptr, 0, nullptr,
+                             m, 256, k, 0, nullptr, ln_w, ln_b, (__nv_bfloat16*)ln_out_bf16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }
 
 }  // extern "C"

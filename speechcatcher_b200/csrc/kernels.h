@@ -104,7 +104,7 @@ int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, con
 int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                              int n_head, int d_model, cudaStream_t st);
 int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const BlockDesc* blk, int n_blk,
-                        int D, cudaStream_t st);
+                        int D, const float* ln_w, const float* ln_b, __nv_bfloat16* nrm16, cudaStream_t st);
 int launch_stitch_norm(const float* X, const BlockDesc* blk, int n_blk, const float* w, const float* b,
                        float* encbuf, int t_cap, int D, __nv_bfloat16* dense16, cudaStream_t st);
 
@@ -179,10 +179,8 @@ int launch_search_reset(const SearchBuffers& sb, const int* streams, int n, cuda
 // q_T / q_final: [n_q][q_stride] entries of this push, appended to each stream's pending queue
 int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int* q_n, const int* q_T,
                         const int* q_final, int q_stride, int n_q, cudaStream_t st);
-int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, cudaStream_t st);
-// mode 0: self attention over the tree KV store (appends this step's K|V first); mode 1: cross attention
-int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
-                         const float* kv_new, int ldkv, float* out, __nv_bfloat16* out16, cudaStream_t st);
+int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, const float* ln_w,
+                     const float* ln_b, __nv_bfloat16* out16, cudaStream_t st);
 int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
                               __nv_bfloat16* out16, cudaStream_t st);
 // Key list of the self-attention KV tree, built once per search iteration and shared by all layers and heads:

@@ -49,6 +49,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 // One CTA per active stream, once per search iteration.
 __global__ void __launch_bounds__(128) build_self_keys_kernel(SearchBuffers sb) {
+  pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   const StreamCtl& c = sb.ctl[s];
@@ -90,7 +91,7 @@ int launch_build_self_keys(const SearchBuffers& sb, cudaStream_t st) {
     cudaFuncSetAttribute(build_self_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  build_self_keys_kernel<<<sb.S, 128, smem, st>>>(sb);
+  launch_k(build_self_keys_kernel, dim3(sb.S), dim3(128), smem, st, sb);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -99,6 +100,7 @@ template <int DK, int MODE>
 __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __nv_bfloat16* kv_layer,
                                                            const float* __restrict__ q, int ldq, int q_off,
                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+  pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   const int head = blockIdx.y;
@@ -443,7 +445,7 @@ static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const 
     attr = smem;
   }
   dim3 grid(sb.S, sb.H);
-  dec_attn_mma_kernel<DK, MODE><<<grid, 128, smem, st>>>(sb, kv_layer, q, ldq, q_off, out, out16);
+  launch_k(dec_attn_mma_kernel<DK, MODE>, grid, dim3(128), smem, st, sb, kv_layer, q, ldq, q_off, out, out16);
   SCB_LAUNCH_CHECK();
   return 0;
 }

@@ -285,16 +285,38 @@ int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, con
 // descriptor array): slot 0 of block i <- slot 41 of block i-1 (or the carried context / own slot 41
 // for the first block), and the last slot 41 becomes the context carried to the next call.
 __global__ void ctx_handover_kernel(float* __restrict__ X, float* __restrict__ enc_ctx, int layer, int n_layers,
-                                    const BlockDesc* __restrict__ blk, int D) {
+                                    const BlockDesc* __restrict__ blk, int D, const float* __restrict__ ln_w,
+                                    const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ nrm16) {
   const BlockDesc b = blk[blockIdx.x];
   if (b.short_path || b.prev_blk >= 0) return;
   const int d = threadIdx.x;
+  __shared__ float red[32];
+  const int warp = d >> 5, lane = d & 31, nwarp = blockDim.x >> 5;
   float* ctx = enc_ctx + ((size_t)b.stream * n_layers + layer) * D + d;
   float carry = b.has_past_ctx ? *ctx : X[((size_t)blockIdx.x * kSlots + kBlock + 1) * D + d];
   for (int i = blockIdx.x;; ++i) {
     float* xb = X + (size_t)i * kSlots * D;
     const float own = xb[(size_t)(kBlock + 1) * D + d];
     xb[d] = carry;
+    if (ln_w) {
+      // bf16 mode: the next layer's norm1 of this slot-0 row (the GEMM epilogue normalised the value it replaced)
+      float sm = warp_sum(carry);
+      if (lane == 0) red[warp] = sm;
+      __syncthreads();
+      float tot = 0.f;
+      for (int w = 0; w < nwarp; ++w) tot += red[w];
+      const float mean = tot / (float)D;
+      const float dd = carry - mean;
+      float q = warp_sum(dd * dd);
+      __syncthreads();
+      if (lane == 0) red[warp] = q;
+      __syncthreads();
+      float qt = 0.f;
+      for (int w = 0; w < nwarp; ++w) qt += red[w];
+      const float rstd = 1.0f / sqrtf(qt / (float)D + 1e-12f);
+      nrm16[(size_t)i * kSlots * D + d] = __float2bfloat16(dd * rstd * ln_w[d] + ln_b[d]);
+      __syncthreads();
+    }
     carry = own;
     if (blk[i].is_last) break;
   }
@@ -302,9 +324,9 @@ __global__ void ctx_handover_kernel(float* __restrict__ X, float* __restrict__ e
 }
 
 int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const BlockDesc* blk, int n_blk,
-                        int D, cudaStream_t st) {
+                        int D, const float* ln_w, const float* ln_b, __nv_bfloat16* nrm16, cudaStream_t st) {
   if (n_blk <= 0) return 0;
-  ctx_handover_kernel<<<n_blk, D, 0, st>>>(X, enc_ctx, layer, n_layers, blk, D);
+  ctx_handover_kernel<<<n_blk, D, 0, st>>>(X, enc_ctx, layer, n_layers, blk, D, ln_w, ln_b, nrm16);
   SCB_LAUNCH_CHECK();
   return 0;
 }

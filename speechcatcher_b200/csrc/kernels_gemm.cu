@@ -20,6 +20,7 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_last_error() { return g_err; }
+bool g_use_pdl = false;
 
 // ------------------------------------------------------------------ LayerNorm
 // One warp per row; the row stays in registers between the mean and variance passes.
@@ -27,6 +28,7 @@ template <typename OutT, int MAXV>
 __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                  const float* __restrict__ b, OutT* __restrict__ y, int ldy, int rows,
                                  int D, const int* __restrict__ n_rows_dev) {
+  pdl_sync();
   if (n_rows_dev) rows = min(rows, *n_rows_dev);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -61,8 +63,7 @@ static int ln_launch(const float* x, int ldx, const float* w, const float* b, Ou
   if (rows <= 0) return 0;
   if (D % 32 != 0 || D > 512) { set_last_error("layernorm: unsupported D=%d", D); return -1; }
   const int warps = 8;
-  layernorm_kernel<OutT, 16><<<cdiv(rows, warps), warps * 32, 0, st>>>(x, ldx, w, b, y, ldy, rows, D,
-                                                                        n_rows_dev);
+  launch_k(layernorm_kernel<OutT, 16>, dim3(cdiv(rows, warps)), dim3(warps * 32), 0, st, x, ldx, w, b, y, ldy, rows, D, n_rows_dev);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -87,6 +88,7 @@ struct GemmParams {
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
+  pdl_sync();
   int M = p.M;
   if (p.n_rows_dev) M = min(M, *p.n_rows_dev);
   const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
@@ -193,7 +195,7 @@ int launch_gemm_f32(const GemmArgs& g, cudaStream_t st) {
   GemmParams p{g.A, g.lda, g.a_row_off, g.a_seg_off, g.seg_len, g.W, g.bias, g.R, g.ldr, g.C, g.ldc,
                g.c_row_off, g.M, g.N, g.K, g.relu, g.n_rows_dev, g.Cb, g.ldcb};
   dim3 grid(cdiv(g.N, GBN), cdiv(g.M, GBM));
-  gemm_f32_kernel<<<grid, 256, 0, st>>>(p);
+  launch_k(gemm_f32_kernel, grid, dim3(256), 0, st, p);
   SCB_LAUNCH_CHECK();
   return 0;
 }

@@ -93,12 +93,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 struct TcParams {
   const float* bias; const float* R; int ldr; float* C; int ldc; __nv_bfloat16* Cb; int ldcb;
   const int64_t* c_row_off; int M, N, K, relu; const int* n_rows_dev;
+  // optional fused LayerNorm of the output rows (needs BN == N): y = LN(C_row) * ln_w + ln_b -> bf16 ln_out[M][N]
+  const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out;
 };
 
 template <int BN, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b,
                                                                      TcParams p) {
+  pdl_sync();
   int M = p.M;
   if (p.n_rows_dev) M = min(M, *p.n_rows_dev);
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
       if (p.Cb) cbrow = p.c_row_off ? p.Cb + p.c_row_off[m] : p.Cb + (size_t)m * p.ldcb;
       if (p.R) rrow = p.R + (size_t)m * p.ldr;
     }
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -202,6 +206,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
             o[j] += r4.x; o[j + 1] += r4.y; o[j + 2] += r4.z; o[j + 3] += r4.w;
           }
         }
+        if (p.ln_w) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1 += o[j]; s2 = fmaf(o[j], o[j], s2); }
+        }
         if (crow) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -220,6 +228,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
             *reinterpret_cast<uint4*>(cbrow + n + j) = u;
           }
         }
+      }
+    }
+    if (p.ln_w && row_ok) {
+      // fused LayerNorm of the finished row (this thread wrote it above, so its own global stores are visible):
+      // single-pass moments in fp32, eps 1e-12 as in the reference's LayerNorm
+      const float mean = s1 / (float)BN;
+      const float var = fmaxf(s2 / (float)BN - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + 1e-12f);
+      __nv_bfloat16* lrow = p.ln_out + (size_t)m * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(crow + c0);
+        const float4 b = *reinterpret_cast<const float4*>(crow + c0 + 4);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ln_w + c0)), w1 = __ldg(reinterpret_cast<const float4*>(p.ln_w + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0 + 4));
+        __nv_bfloat162 h0 = __floats2bfloat162_rn((a.x - mean) * rstd * w0.x + b0.x, (a.y - mean) * rstd * w0.y + b0.y);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn((a.z - mean) * rstd * w0.z + b0.z, (a.w - mean) * rstd * w0.w + b0.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn((b.x - mean) * rstd * w1.x + b1.x, (b.y - mean) * rstd * w1.y + b1.y);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn((b.z - mean) * rstd * w1.z + b1.z, (b.w - mean) * rstd * w1.w + b1.w);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(lrow + c0) = u;
       }
     }
     tc_fence_before();
@@ -280,30 +311,44 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     attr_set = true;
   }
   dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
-  gemm_bf16_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
+  launch_k(gemm_bf16_tc_kernel<BN, TC_STAGES>, grid, dim3(TC_THREADS), smem, st, ma, mb, p);
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
+int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
                         int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
-                        int K, int relu, const int* n_rows_dev, cudaStream_t st) {
+                        int K, int relu, const int* n_rows_dev, const float* ln_w, const float* ln_b,
+                        __nv_bfloat16* ln_out, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   if (K % TC_BK != 0 || N % 64 != 0 || lda % 8 != 0) {
     set_last_error("gemm_bf16: unsupported shape M=%d N=%d K=%d lda=%d", M, N, K, lda);
     return -1;
   }
-  const bool small = (N % 128 != 0) || ((long)cdiv(M, TC_BM) * (N / 128) < kNumSMs);
-  const int BN = small ? 64 : 128;
+  const bool ln = ln_w != nullptr;
+  if (ln && (N != 256 || !C || c_row_off || !ln_b || !ln_out || ldc != N)) {
+    set_last_error("gemm_bf16: fused LayerNorm needs N == 256 and a dense fp32 output (N=%d)", N);
+    return -1;
+  }
+  const bool small = !ln && ((N % 128 != 0) || ((long)cdiv(M, TC_BM) * (N / 128) < kNumSMs));
+  const int BN = ln ? 256 : (small ? 64 : 128);
   CUtensorMap ma, mb;
   if (get_map(A, M, K, lda, TC_BM, &ma)) return -1;
   if (get_map(W, N, K, K, BN, &mb)) return -1;
-  TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev};
-  // K <= 256 has only four K-blocks: two stages (48-64 KB) let three CTAs share an SM so that one CTA's
-  // epilogue overlaps another's main loop; deeper K keeps the four-stage ring
+  TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev, ln_w, ln_b, ln_out};
+  // K <= 256 has only four K-blocks: two stages let several CTAs share an SM so that one CTA's epilogue
+  // overlaps another's main loop; deeper K keeps the four-stage ring
   const bool shallow = K / TC_BK <= 4;
+  if (ln) return shallow ? launch_bn<256, 2>(ma, mb, p, st) : launch_bn<256, 4>(ma, mb, p, st);
   if (small) return shallow ? launch_bn<64, 2>(ma, mb, p, st) : launch_bn<64, 4>(ma, mb, p, st);
   return shallow ? launch_bn<128, 2>(ma, mb, p, st) : launch_bn<128, 4>(ma, mb, p, st);
+}
+
+int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
+                        int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
+                        int K, int relu, const int* n_rows_dev, cudaStream_t st) {
+  return launch_gemm_bf16_ln(A, lda, W, bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev, nullptr,
+                             nullptr, nullptr, st);
 }
 
 int launch_gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,

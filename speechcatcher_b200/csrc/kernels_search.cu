@@ -130,6 +130,7 @@ __global__ void search_begin_kernel(SearchBuffers sb, const int* __restrict__ q_
 
 // ---------------------------------------------------------------- compaction of active rows
 __global__ void compact_rows_kernel(SearchBuffers sb) {
+  pdl_sync();
   __shared__ int s_scan[1024];
   __shared__ int s_base, s_nact;
   if (threadIdx.x == 0) { s_base = 0; s_nact = 0; }
@@ -186,179 +187,55 @@ int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int*
 }
 
 // ---------------------------------------------------------------- decoder input: sqrt(D)*Emb[y_last] + pe[len-1]
-__global__ void dec_embed_kernel(SearchBuffers sb, const float* __restrict__ emb, const float* __restrict__ pe,
-                                 float* __restrict__ x) {
+__global__ void __launch_bounds__(128) dec_embed_kernel(SearchBuffers sb, const float* __restrict__ emb, const float* __restrict__ pe,
+                                                        float* __restrict__ x, const float* __restrict__ ln_w,
+                                                        const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out16) {
+  pdl_sync();
   const int r = blockIdx.x;
   if (r >= *sb.n_rows) return;
   const int sh = sb.row_sh[r], s = sh / sb.B, h = sh % sb.B;
   const StreamCtl& c = sb.ctl[s];
   const int tok = sb.yseq[beam_off(sb, c.cur, s, h) * sb.Lcap + c.len - 1];
   const float scale = sqrtf((float)sb.D);
-  for (int d = threadIdx.x; d < sb.D; d += blockDim.x)
-    x[(size_t)r * sb.D + d] = emb[(size_t)tok * sb.D + d] * scale + pe[(size_t)(c.len - 1) * sb.D + d];
+  float v[4];                                   // D <= 512 with 128 threads
+  const int nv = sb.D / 128;
+  float sum = 0.f;
+  for (int i = 0; i < nv; ++i) {
+    const int d = threadIdx.x + 128 * i;
+    v[i] = emb[(size_t)tok * sb.D + d] * scale + pe[(size_t)(c.len - 1) * sb.D + d];
+    x[(size_t)r * sb.D + d] = v[i];
+    sum += v[i];
+  }
+  if (!ln_w) return;
+  // fused LayerNorm (first decoder layer's norm1) -> bf16 operand of the QKV GEMM
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  const float mean = (red[0] + red[1] + red[2] + red[3]) / (float)sb.D;
+  float q = 0.f;
+  for (int i = 0; i < nv; ++i) { const float dd = v[i] - mean; q += dd * dd; }
+  q = warp_sum(q);
+  if (lane == 0) red[4 + warp] = q;
+  __syncthreads();
+  const float rstd = 1.0f / sqrtf((red[4] + red[5] + red[6] + red[7]) / (float)sb.D + 1e-12f);
+  for (int i = 0; i < nv; ++i) {
+    const int d = threadIdx.x + 128 * i;
+    out16[(size_t)r * sb.D + d] = __float2bfloat16((v[i] - mean) * rstd * ln_w[d] + ln_b[d]);
+  }
 }
 
-int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, cudaStream_t st) {
-  dec_embed_kernel<<<sb.S * sb.B, 128, 0, st>>>(sb, emb, pe, x);
+int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, const float* ln_w,
+                     const float* ln_b, __nv_bfloat16* out16, cudaStream_t st) {
+  if (sb.D > 512 || sb.D % 128 != 0) { set_last_error("dec_embed: D=%d unsupported", sb.D); return -1; }
+  launch_k(dec_embed_kernel, dim3(sb.S * sb.B), dim3(128), 0, st, sb, emb, pe, x, ln_w, ln_b, out16);
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
-// ---------------------------------------------------------------- decoder attention (self over the KV tree / cross over memory)
-// One CTA per (active stream, head) serves all hypotheses of the stream so that keys/values shared by
-// the beam are read once.  Flash-style online softmax over tiles of 128 positions.
-//   mode 0 (self):  position j of hypothesis b lives in skv[layer][s][j][anc_b[j]]; this step's K|V
-//                   (columns D..3D of the fused QKV GEMM output) is first appended at [len-1][b].
-//   mode 1 (cross): position j lives in xkv[layer][s][j]; all hypotheses see frames [0, Tb).
-constexpr int ATILE = 128;
-constexpr int AMAXB = 20;     // beam capacity of the attention kernel
-
-template <int DK>
-__global__ void __launch_bounds__(128) dec_attention_kernel(SearchBuffers sb, int mode, int layer,
-                                                            const float* __restrict__ q, int ldq,
-                                                            const float* __restrict__ kv_new, int ldkv,
-                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
-  if ((int)blockIdx.x >= *sb.n_active) return;
-  const int s = sb.act_streams[blockIdx.x];
-  const int head = blockIdx.y;
-  const StreamCtl& c = sb.ctl[s];
-  const int nb = c.n_hyp, row0 = sb.row_base[s], D = sb.D;
-  const int npos = mode == 0 ? c.len : c.Tb;
-  const int tid = threadIdx.x;
-
-  extern __shared__ unsigned char smem_raw[];
-  float* qs = reinterpret_cast<float*>(smem_raw);            // [AMAXB][DK]
-  float* sc = qs + AMAXB * DK;                               // [AMAXB][ATILE]
-  float* sm_m = sc + AMAXB * ATILE;                          // [AMAXB] running max
-  float* sm_l = sm_m + AMAXB;                                // [AMAXB] running sum
-  float* sm_f = sm_l + AMAXB;                                // [AMAXB] rescale factor of the tile
-  unsigned char* ancs = reinterpret_cast<unsigned char*>(sm_f + AMAXB);   // [AMAXB][Lcap] (self only)
-
-  for (int i = tid; i < nb * DK; i += blockDim.x) qs[i] = q[(size_t)(row0 + i / DK) * ldq + head * DK + i % DK];
-  if (tid < AMAXB) { sm_m[tid] = -INFINITY; sm_l[tid] = 0.f; }
-  const size_t row_stride = 2 * (size_t)D;                  // K|V row
-  if (tid == 0)   // cross K|V read once per stream, self K|V once per hypothesis
-    atomicAdd(&sb.prof[mode == 1 ? 2 : 3], (unsigned long long)((mode == 1 ? 1 : nb) * 2ll * npos * DK * 4));
-  const float* base;
-  if (mode == 0) {
-    float* store = sb.skv + ((size_t)layer * sb.S + s) * sb.Lcap * sb.B * row_stride;
-    // append this step's K|V for every hypothesis (this head's slice)
-    for (int i = tid; i < nb * 2 * DK; i += blockDim.x) {
-      int b = i / (2 * DK), rem = i % (2 * DK), which = rem / DK, cc = rem % DK;
-      store[((size_t)(c.len - 1) * sb.B + b) * row_stride + which * D + head * DK + cc] =
-          kv_new[(size_t)(row0 + b) * ldkv + which * D + head * DK + cc];
-    }
-    for (int i = tid; i < nb * npos; i += blockDim.x) {
-      int b = i / npos, j = i % npos;
-      ancs[b * sb.Lcap + j] = (j == npos - 1) ? (unsigned char)b
-                                              : sb.anc[beam_off(sb, c.cur, s, b) * sb.Lcap + j];
-    }
-    base = store;
-  } else {
-    base = sb.xkv + ((size_t)layer * sb.S + s) * sb.Tcap * row_stride;
-  }
-  __syncthreads();
-
-  const float sqrt_dk = sqrtf((float)DK);
-  // accumulators: thread (g, cdim) owns hypotheses b = g, g+G, ... for output dim cdim
-  constexpr int G = 128 / DK;                 // 4 for DK=32, 2 for DK=64
-  constexpr int NACC = (AMAXB + G - 1) / G;
-  const int g = tid / DK, cdim = tid % DK;
-  float acc[NACC];
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-
-  for (int t0 = 0; t0 < npos; t0 += ATILE) {
-    // ---- scores for position j = t0 + tid
-    const int j = t0 + tid;
-    if (j < npos) {
-      float kreg[DK];
-      int loaded = -1;
-      for (int b = 0; b < nb; ++b) {
-        int slot = mode == 0 ? (int)ancs[b * sb.Lcap + j] : 0;
-        if (slot != loaded) {
-          const float* kp = mode == 0 ? base + ((size_t)j * sb.B + slot) * row_stride + head * DK
-                                      : base + (size_t)j * row_stride + head * DK;
-#pragma unroll
-          for (int i = 0; i < DK; i += 4) {
-            float4 v = *reinterpret_cast<const float4*>(kp + i);
-            kreg[i] = v.x; kreg[i + 1] = v.y; kreg[i + 2] = v.z; kreg[i + 3] = v.w;
-          }
-          loaded = slot;
-        }
-        float d = 0.f;
-#pragma unroll
-        for (int i = 0; i < DK; ++i) d = fmaf(qs[b * DK + i], kreg[i], d);
-        sc[b * ATILE + tid] = d / sqrt_dk;
-      }
-    } else {
-      for (int b = 0; b < nb; ++b) sc[b * ATILE + tid] = -INFINITY;
-    }
-    __syncthreads();
-    // ---- online softmax bookkeeping: warp w handles hypotheses w, w+4, ...
-    {
-      const int warp = tid >> 5, lane = tid & 31;
-      for (int b = warp; b < nb; b += 4) {
-        float m = -INFINITY;
-        for (int i = lane; i < ATILE; i += 32) m = fmaxf(m, sc[b * ATILE + i]);
-        m = warp_max(m);
-        float m_old = sm_m[b];
-        float m_new = fmaxf(m_old, m);
-        float ssum = 0.f;
-        for (int i = lane; i < ATILE; i += 32) {
-          float e = expf(sc[b * ATILE + i] - m_new);
-          sc[b * ATILE + i] = e;
-          ssum += e;
-        }
-        ssum = warp_sum(ssum);
-        if (lane == 0) {
-          float f = expf(m_old - m_new);       // 0 on the first tile (m_old = -inf)
-          sm_f[b] = f;
-          sm_l[b] = sm_l[b] * f + ssum;
-          sm_m[b] = m_new;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- P * V for the tile
-    {
-      const int jn = min(ATILE, npos - t0);
-#pragma unroll
-      for (int i = 0; i < NACC; ++i) {
-        int b = g + i * G;
-        if (b < nb) acc[i] *= sm_f[b];
-      }
-      for (int jj = 0; jj < jn; ++jj) {
-        const int jp = t0 + jj;
-        float vreg = 0.f;
-        int loaded = -1;
-#pragma unroll
-        for (int i = 0; i < NACC; ++i) {
-          int b = g + i * G;
-          if (b < nb) {
-            int slot = mode == 0 ? (int)ancs[b * sb.Lcap + jp] : 0;
-            if (slot != loaded) {
-              vreg = mode == 0 ? base[((size_t)jp * sb.B + slot) * row_stride + D + head * DK + cdim]
-                               : base[(size_t)jp * row_stride + D + head * DK + cdim];
-              loaded = slot;
-            }
-            acc[i] = fmaf(sc[b * ATILE + jj], vreg, acc[i]);
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) {
-    int b = g + i * G;
-    if (b < nb) {
-      const float o = acc[i] / sm_l[b];
-      out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
-      if (out16) out16[(size_t)(row0 + b) * D + head * DK + cdim] = __float2bfloat16(o);
-    }
-  }
-}
+// ---------------------------------------------------------------- decoder attention (fp32 mode / beam > 16)
+constexpr int AMAXB = 20;     // beam capacity of the attention and pruning kernels
 
 // ---------------------------------------------------------------- cross attention, shared-memory staged
 // One CTA per (active stream, head).  All hypotheses of a stream see the same memory, so each K|V tile is
@@ -368,6 +245,7 @@ template <int DK, typename KVT>
 __global__ void __launch_bounds__(128) dec_cross_attn_kernel(SearchBuffers sb, const KVT* __restrict__ xkv_layer,
                                                              const float* __restrict__ q, int ldq,
                                                              float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+  pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   const int head = blockIdx.y;
@@ -519,11 +397,11 @@ static int launch_cross_t(const SearchBuffers& sb, int layer, const float* q, in
   if (dk == 32) {
     static bool a = false;
     if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
-    dec_cross_attn_kernel<32, KVT><<<grid, 128, smem, st>>>(sb, base, q, ldq, out, out16);
+    launch_k(dec_cross_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16);
   } else if (dk == 64) {
     static bool a = false;
     if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
-    dec_cross_attn_kernel<64, KVT><<<grid, 128, smem, st>>>(sb, base, q, ldq, out, out16);
+    launch_k(dec_cross_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16);
   } else { set_last_error("cross attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;
@@ -546,6 +424,7 @@ template <int DK, typename KVT>
 __global__ void __launch_bounds__(128) dec_self_attn_kernel(SearchBuffers sb, KVT* skv_layer,
                                                             const float* __restrict__ qkv, int ldq,
                                                             float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+  pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   const int head = blockIdx.y;
@@ -776,11 +655,11 @@ static int launch_self_t(const SearchBuffers& sb, int layer, const float* qkv, i
   if (dk == 32) {
     static size_t a = 0;
     if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
-    dec_self_attn_kernel<32, KVT><<<grid, 128, smem, st>>>(sb, base, qkv, ldq, out, out16);
+    launch_k(dec_self_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16);
   } else if (dk == 64) {
     static size_t a = 0;
     if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
-    dec_self_attn_kernel<64, KVT><<<grid, 128, smem, st>>>(sb, base, qkv, ldq, out, out16);
+    launch_k(dec_self_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16);
   } else { set_last_error("self attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;
@@ -793,25 +672,13 @@ int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* q
                     : launch_self_t<float>(sb, layer, qkv, ldq, out, out16, st);
 }
 
-int launch_dec_attention(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq,
-                         const float* kv_new, int ldkv, float* out, __nv_bfloat16* out16, cudaStream_t st) {
-  if (sb.B > AMAXB) { set_last_error("dec_attention: beam %d > %d", sb.B, AMAXB); return -1; }
-  const int dk = sb.D / sb.H;
-  dim3 grid(sb.S, sb.H);
-  size_t smem = sizeof(float) * (AMAXB * dk + AMAXB * ATILE + 3 * AMAXB) + (mode == 0 ? (size_t)AMAXB * sb.Lcap : 0);
-  if (dk == 32) dec_attention_kernel<32><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out, out16);
-  else if (dk == 64) dec_attention_kernel<64><<<grid, 128, smem, st>>>(sb, mode, layer, q, ldq, kv_new, ldkv, out, out16);
-  else { set_last_error("dec_attention: unsupported head dim %d", dk); return -1; }
-  SCB_LAUNCH_CHECK();
-  return 0;
-}
-
 // ---------------------------------------------------------------- log-softmax + pre-beam top-40
 // One warp per row (V = 1024 -> 32 values per lane).  Writes log-probs in place and the 40 best ids of
 // w_dec * logp in descending order (lowest index first on ties).   (beam_search.py:121-154)
 constexpr int VMAX_PER_LANE = 32;
 
 __global__ void __launch_bounds__(128) logsoftmax_prebeam_kernel(SearchBuffers sb, float* __restrict__ logits) {
+  pdl_sync();
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= *sb.n_rows) return;
   const int lane = threadIdx.x & 31, V = sb.V;
@@ -860,7 +727,7 @@ __global__ void __launch_bounds__(128) logsoftmax_prebeam_kernel(SearchBuffers s
 
 int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st) {
   if (sb.V != 1024) { set_last_error("logsoftmax_prebeam: V=%d unsupported (1024 only)", sb.V); return -1; }
-  logsoftmax_prebeam_kernel<<<cdiv(sb.S * sb.B, 4), 128, 0, st>>>(sb, logits);
+  launch_k(logsoftmax_prebeam_kernel, dim3(cdiv(sb.S * sb.B, 4)), dim3(128), 0, st, sb, logits);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -922,6 +789,7 @@ __device__ __forceinline__ void ctc_forward_column(const float* __restrict__ x, 
 }
 
 __global__ void __launch_bounds__(64) ctc_prefix_kernel(SearchBuffers sb) {
+  pdl_sync();
   const int r = blockIdx.x;
   if (r >= *sb.n_rows) return;
   const int sh = sb.row_sh[r], s = sh / sb.B, h = sh % sb.B;
@@ -944,7 +812,7 @@ __global__ void __launch_bounds__(64) ctc_prefix_kernel(SearchBuffers sb) {
 }
 
 int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st) {
-  ctc_prefix_kernel<<<sb.S * sb.B, 64, 0, st>>>(sb);
+  launch_k(ctc_prefix_kernel, dim3(sb.S * sb.B), dim3(64), 0, st, sb);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -953,6 +821,7 @@ int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st) {
 // One warp per row.  Only the 40 candidates and <eos> can carry a real CTC score; every other token
 // scores w_ctc * (logzero - s_prev) and can never reach the top-B (B <= 20 < 39).
 __global__ void __launch_bounds__(128) combine_topk_kernel(SearchBuffers sb, const float* __restrict__ logp) {
+  pdl_sync();
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= *sb.n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -1015,7 +884,7 @@ __global__ void __launch_bounds__(128) combine_topk_kernel(SearchBuffers sb, con
 }
 
 int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st) {
-  combine_topk_kernel<<<cdiv(sb.S * sb.B, 4), 128, 0, st>>>(sb, logp);
+  launch_k(combine_topk_kernel, dim3(cdiv(sb.S * sb.B, 4)), dim3(128), 0, st, sb, logp);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -1025,6 +894,7 @@ int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t
 constexpr int PMAXC = 13;   // ceil(20*20 / 32)
 
 __global__ void __launch_bounds__(128) beam_prune_kernel(SearchBuffers sb) {
+  pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   StreamCtl& c = sb.ctl[s];
@@ -1121,7 +991,7 @@ __global__ void __launch_bounds__(128) beam_prune_kernel(SearchBuffers sb) {
 
 int launch_beam_prune(const SearchBuffers& sb, cudaStream_t st) {
   if (sb.B > AMAXB) { set_last_error("beam_prune: beam %d > %d", sb.B, AMAXB); return -1; }
-  beam_prune_kernel<<<sb.S, 128, 0, st>>>(sb);
+  launch_k(beam_prune_kernel, dim3(sb.S), dim3(128), 0, st, sb);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -1130,6 +1000,7 @@ int launch_beam_prune(const SearchBuffers& sb, cudaStream_t st) {
 // One thread per (active stream, new hypothesis): rebuild the inherited forward column into the other
 // beam buffer.  Wasted (but harmless) when the step is later discarded by a rewind.
 __global__ void __launch_bounds__(32) ctc_state_update_kernel(SearchBuffers sb) {
+  pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   const StreamCtl& c = sb.ctl[s];
@@ -1145,13 +1016,14 @@ __global__ void __launch_bounds__(32) ctc_state_update_kernel(SearchBuffers sb) 
 }
 
 int launch_ctc_state_update(const SearchBuffers& sb, cudaStream_t st) {
-  ctc_state_update_kernel<<<sb.S, 32, 0, st>>>(sb);
+  launch_k(ctc_state_update_kernel, dim3(sb.S), dim3(32), 0, st, sb);
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
 // ---------------------------------------------------------------- commit the step: block end / rewind / next block
 __global__ void __launch_bounds__(64) step_commit_kernel(SearchBuffers sb) {
+  pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
   __shared__ StreamCtl c;
@@ -1184,9 +1056,9 @@ __global__ void __launch_bounds__(64) step_commit_kernel(SearchBuffers sb) {
 }
 
 int launch_step_finish(const SearchBuffers& sb, cudaStream_t st) {
-  step_commit_kernel<<<sb.S, 64, 0, st>>>(sb);
+  launch_k(step_commit_kernel, dim3(sb.S), dim3(64), 0, st, sb);
   SCB_LAUNCH_CHECK();
-  compact_rows_kernel<<<1, 1024, 0, st>>>(sb);
+  launch_k(compact_rows_kernel, dim3(1), dim3(1024), 0, st, sb);
   SCB_LAUNCH_CHECK();
   return 0;
 }

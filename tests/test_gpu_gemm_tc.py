@@ -49,3 +49,26 @@ def test_linear_bf16_matches_fp32_reference(M, N, K, relu, res, bf16_out):
     if bf16_out:
         err16 = (y16.float() - want).abs().max().item()
         assert err16 <= 1e-2 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("M,K", [(77, 256), (2560, 256), (1000, 2048), (10752, 256)])
+def test_linear_bf16_fused_layernorm(M, K):
+    """GEMM + bias + in-place residual with the next LayerNorm fused into the epilogue (BN = N = 256)."""
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(256, K, generator=g, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(256, generator=g, device="cuda")
+    r = torch.randn(M, 256, generator=g, device="cuda")
+    lw = 1.0 + 0.1 * torch.randn(256, generator=g, device="cuda")
+    lb = 0.1 * torch.randn(256, generator=g, device="cuda")
+    y = r.clone()
+    ln = torch.zeros(M, 256, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.sc_linear_bf16_ln(a.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), y.data_ptr(), lw.data_ptr(),
+                                     lb.data_ptr(), ln.data_ptr(), M, K, None), "linear_bf16_ln")
+    torch.cuda.synchronize()
+    want = a.float() @ w.float().t() + bias + r
+    assert (y - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+    want_ln = torch.nn.functional.layer_norm(want, (256,), lw, lb, 1e-12)
+    assert (ln.float() - want_ln).abs().max().item() <= 3e-2
