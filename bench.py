@@ -120,14 +120,17 @@ def main():
     ap.add_argument("--streams", type=int, default=256, help="streams per GPU")
     ap.add_argument("--beam", type=int, default=10)
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--dtype", default=os.environ.get("SCB_BENCH_DTYPE", "float32"), choices=["float32", "bfloat16"])
+    ap.add_argument("--dtype", default=os.environ.get("SCB_BENCH_DTYPE", "bfloat16"), choices=["float32", "bfloat16"],
+                    help="bfloat16: tensor-core GEMMs/attention with fp32 accumulation (throughput mode, north_star); "
+                         "float32: CUDA-core parity mode (n-best identical to the reference)")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the extra fp32 parity-mode measurement")
     ap.add_argument("--cpu-sample-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--breakdown", action="store_true", help="always run the all-kernel timing pass")
     ap.add_argument("--lazy", type=int, default=int(os.environ.get("SCB_BENCH_LAZY", "-1")),
-                    help="deferred-decode threshold (streams); 0 = strict per-push decoding; -1 = streams/2")
+                    help="deferred-decode threshold (streams); 0 = strict per-push decoding; -1 = streams - streams/32")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +194,7 @@ def main():
         host[s, :n_samples] = torch.from_numpy(synth_audio(rank * S + s, n_samples))
     grp = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype=args.dtype,
                       use_bbd=False, max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
-    lazy = args.lazy if args.lazy >= 0 else S // 2
+    lazy = args.lazy if args.lazy >= 0 else max(1, S - S // 32)
     grp.set_option("lazy_threshold", lazy)
     resident = host.to(dev)                           # inputs resident in HBM for `value`
     ids = np.arange(S, dtype=np.int32)
@@ -285,6 +288,38 @@ def main():
                "h2d_bytes_per_step": int(S * n_samples * 4), "d2h_bytes_per_step": int(d2h),
                "p50_chunk_ms": float(statistics.median(lat_ms)), "p95_chunk_ms": float(np.percentile(lat_ms, 95))}
 
+    # the fp32 parity mode (CUDA-core GEMMs, results identical to the reference) measured on the same workload
+    fp32_mode = None
+    if args.dtype == "bfloat16" and not args.no_fp32:
+        grp.close()
+        del grp, resident
+        torch.cuda.empty_cache()
+        g32 = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype="float32",
+                          use_bbd=False, max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
+        g32.set_option("lazy_threshold", lazy)
+        res32 = host.to(dev)
+
+        def pass32():
+            g32.reset()
+            for c in range(n_chunks):
+                g32.push_device(ids, res32, lens_all[c], fin_all[c], col_offset=c * CHUNK)
+
+        pass32()
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        pass32()
+        a1.record()
+        sync_all()
+        ms32 = a0.elapsed_time(a1)
+        if world > 1:
+            t = torch.tensor([ms32], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms32 = float(t.item())
+        fp32_mode = {"value": world * S * args.seconds / (ms32 / 1000.0), "unit": "audio-s/s", "ms_per_step": ms32,
+                     "steps": 1, "warmup": 1, "note": "parity mode: true-fp32 CUDA-core GEMMs, n-best identical to the reference"}
+        g32.close()
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, p50, wall = cpu_baseline_pass(md, args.beam, args.cpu_sample_seconds, cores)
@@ -303,7 +338,8 @@ def main():
                            "decode_steps_per_pass": stats["steps"] // max(1, args.steps),
                            "encoder_blocks_per_pass": stats["blocks"] // max(1, args.steps)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": stats["launches"],
-                "roofline": roof, "cpu_baseline": cpu_base, "kernel_breakdown_sampled": breakdown}
+                "roofline": roof, "cpu_baseline": cpu_base, "fp32_mode": fp32_mode,
+                "kernel_breakdown_sampled": breakdown}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

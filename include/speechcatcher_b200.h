@@ -143,6 +143,11 @@ int sc_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, co
 int sc_linear_bf16_ln(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual, float* y_f32,
                       const float* ln_w, const float* ln_b, void* ln_out_bf16, int32_t m, int32_t k, void* stream);
 
+/* y = act(LayerNorm(x) W^T + bias) with the LayerNorm of the fp32 rows x [m][256] computed inside the GEMM
+ * (the normalised bf16 A tile is written directly into the swizzled shared-memory operand layout) */
+int sc_linear_bf16_lnA(const float* x_f32, const float* ln_w, const float* ln_b, const void* w_bf16, const float* bias,
+                       float* y_f32, void* y_bf16, int32_t m, int32_t n, int32_t relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

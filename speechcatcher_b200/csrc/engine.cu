@@ -22,6 +22,9 @@ int launch_dec_attention_mma(const SearchBuffers& sb, int mode, int layer, const
                              __nv_bfloat16* out16, cudaStream_t st);
 int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                              int n_head, int d_model, cudaStream_t st);
+int launch_gemm_bf16_lnA(const float* X, int ldx, const float* lna_w, const float* lna_b, const __nv_bfloat16* W,
+                         const float* bias, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int relu,
+                         const int* n_rows_dev, cudaStream_t st);
 int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,
                         int ldr, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, const int64_t* c_row_off, int M, int N,
                         int K, int relu, const int* n_rows_dev, const float* ln_w, const float* ln_b,
@@ -100,6 +103,8 @@ struct Engine {
   // Correct (tests/test_gpu_gemm_tc.py) but currently slower than separate LayerNorm kernels: the one-row-per-thread
   // epilogue over 256 columns serialises too much and BN = 256 leaves few CTAs; off by default.
   bool fuse_ln = false;
+  // bf16 mode: compute every LayerNorm inside the GEMM that consumes it (LayerNorm-prologue GEMM, K = 256)
+  bool ln_prologue = false;
   // deferred decoding: a push stops iterating once fewer than `lazy_threshold` streams are active and leaves
   // the stragglers' blocks queued on the device; they continue during later pushes (0 = strict, drain every push)
   int lazy_threshold = 0;
@@ -229,6 +234,23 @@ static int linear(Engine& e, const Lin& l, cudaStream_t st) {
 
 #define TRY(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
 
+// LayerNorm(X) followed by a Linear.  bf16 mode with ln_prologue: one kernel (the GEMM normalises its own A tile);
+// otherwise a LayerNorm kernel (fp32 or bf16 output into l.A / l.A16) followed by the GEMM.
+static int ln_linear(Engine& e, const float* X, int ldx, const float* ln_w, const float* ln_b, int rows_max,
+                     const Lin& l, cudaStream_t st) {
+  const bool tc = e.cfg.precision == 1;
+  if (tc && e.ln_prologue && !e.fuse_ln) {
+    e.launches++;
+    return launch_gemm_bf16_lnA(X, ldx, ln_w, ln_b, l.W16, l.bias, l.C, l.ldc, l.C16, l.ldc, l.M, l.N, l.relu, l.n_rows_dev, st);
+  }
+  if (!(tc && e.fuse_ln)) {
+    e.launches++;
+    if (tc) TRY(launch_layernorm_bf16(X, ldx, ln_w, ln_b, const_cast<__nv_bfloat16*>(l.A16), l.lda, rows_max, l.K, l.n_rows_dev, st));
+    else TRY(launch_layernorm(X, ldx, ln_w, ln_b, const_cast<float*>(l.A), l.lda, rows_max, l.K, l.n_rows_dev, st));
+  }
+  return linear(e, l, st);
+}
+
 enum ProfTag { T_NONE = 0, T_CTC_PREFIX = 1, T_DEC_SELF_ATTN = 2, T_DEC_CROSS_ATTN = 3, T_DEC_FFN1 = 4, T_ENC_FFN1 = 5,
                T_PREBEAM = 6, T_ENC_ATTN = 7, T_CONV2 = 8, T_DEC_FFN2 = 9, T_ENC_FFN2 = 10, T_CTC_UPDATE = 11,
                T_FRONTEND = 12, T_CONV1 = 13, T_SUBOUT = 14, T_BLOCK_ASM = 15, T_ENC_LN = 16, T_ENC_QKV = 17, T_ENC_O = 18,
@@ -265,19 +287,14 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
   // fused mode: only the first LayerNorm is a kernel of its own; every other norm rides in the epilogue of the GEMM
   // that produces its input (O-proj -> norm2, FFN2 -> next layer's norm1; the hand-over re-normalises slot 0)
   if (fl) PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, e.enc[0].ln1w, e.enc[0].ln1b, e.Nrm16, D, rows, D, nullptr, st));
-  auto ln = [&](const float* w, const float* b) -> int {
-    if (tc) return launch_layernorm_bf16(e.X, D, w, b, e.Nrm16, D, rows, D, nullptr, st);
-    return launch_layernorm(e.X, D, w, b, e.Nrm, D, rows, D, nullptr, st);
-  };
   for (int l = 0; l < c.enc_layers; ++l) {
     const EncLayerW& w = e.enc[l];
     const EncLayerW* nx = l + 1 < c.enc_layers ? &e.enc[l + 1] : nullptr;
-    if (!fl) PE(T_ENC_LN, ln(w.ln1w, w.ln1b));
     if (e.mma_enc) {
-      PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, nullptr, 3 * D, e.QKV16, rows, 3 * D, D, 0, nullptr}, st));
+      PE(T_ENC_QKV, ln_linear(e, e.X, D, w.ln1w, w.ln1b, rows, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, nullptr, 3 * D, e.QKV16, rows, 3 * D, D, 0, nullptr}, st));
       PE(T_ENC_ATTN, launch_enc_attention_mma(e.QKV16, nullptr, e.Att16, e.d_blk, n_blk, c.enc_heads, D, st));
     } else {
-      PE(T_ENC_QKV, linear(e, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
+      PE(T_ENC_QKV, ln_linear(e, e.X, D, w.ln1w, w.ln1b, rows, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
       PE(T_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
     }
     {
@@ -285,9 +302,8 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
       if (fl) o = with_ln(o, w.ln2w, w.ln2b, e.Nrm16);
       PE(T_ENC_O, linear(e, o, st));
     }
-    if (!fl) PE(T_ENC_LN, ln(w.ln2w, w.ln2b));
     if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
-    PE(T_ENC_FFN1, linear(e, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
+    PE(T_ENC_FFN1, ln_linear(e, e.X, D, w.ln2w, w.ln2b, rows, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
     {
       Lin f2{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr};
       if (fl && nx) f2 = with_ln(f2, nx->ln1w, nx->ln1b, e.Nrm16);
@@ -310,17 +326,12 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   const bool ptot = prof_on(e, T_DEC_STEP_TOTAL, true);
   if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, true);
   const bool fl = tc && e.fuse_ln;
-  auto ln = [&](const float* w, const float* b) -> int {
-    if (tc) return launch_layernorm_bf16(e.dx, D, w, b, e.dn16, D, R, D, nr, st);
-    return launch_layernorm(e.dx, D, w, b, e.dn, D, R, D, nr, st);
-  };
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, fl ? e.dec[0].ln1w : nullptr, fl ? e.dec[0].ln1b : nullptr, e.dn16, st));
   if (e.mma_attn) PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
     // bf16 mode: norm1 comes fused from dec_embed / the previous layer's FFN2, norm2 from self-O, norm3 from cross-O
-    if (!fl) PD(T_DEC_LN, ln(w.ln1w, w.ln1b));
-    PD(T_DEC_QKV, linear(e, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
+    PD(T_DEC_QKV, ln_linear(e, e.dx, D, w.ln1w, w.ln1b, R, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_SELF_ATTN, launch_dec_attention_mma(sb, 0, l, e.dqkv, 3 * D, e.dattn, e.dattn16, st));
     else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
     {
@@ -328,8 +339,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
       if (fl) o = with_ln(o, w.ln2w, w.ln2b, e.dn16);
       PD(T_DEC_SO, linear(e, o, st));
     }
-    if (!fl) PD(T_DEC_LN, ln(w.ln2w, w.ln2b));
-    PD(T_DEC_CQ, linear(e, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
+    PD(T_DEC_CQ, ln_linear(e, e.dx, D, w.ln2w, w.ln2b, R, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_CROSS_ATTN, launch_dec_attention_mma(sb, 1, l, e.dq, D, e.dattn, e.dattn16, st));
     else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, e.dattn, tc ? e.dattn16 : nullptr, st));
     {
@@ -337,8 +347,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
       if (fl) o = with_ln(o, w.ln3w, w.ln3b, e.dn16);
       PD(T_DEC_CO, linear(e, o, st));
     }
-    if (!fl) PD(T_DEC_LN, ln(w.ln3w, w.ln3b));
-    PD(T_DEC_FFN1, linear(e, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
+    PD(T_DEC_FFN1, ln_linear(e, e.dx, D, w.ln3w, w.ln3b, R, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
     {
       Lin f2{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr};
       if (fl) f2 = (l + 1 < c.dec_layers) ? with_ln(f2, e.dec[l + 1].ln1w, e.dec[l + 1].ln1b, e.dn16) : with_ln(f2, e.daw, e.dab, e.dn16);
@@ -346,8 +355,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
     }
     e.launches += fl ? 2 : 5;
   }
-  if (!fl) PD(T_DEC_LN, ln(e.daw, e.dab));
-  PD(T_DEC_OUT, linear(e, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
+  PD(T_DEC_OUT, ln_linear(e, e.dx, D, e.daw, e.dab, R, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
   PD(T_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
   PD(T_CTC_PREFIX, launch_ctc_prefix(sb, st));
   PD(T_COMBINE, launch_combine_topk(sb, e.dlogp, st));
@@ -416,6 +424,8 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     const char* a = getenv("SCB_ATTN");     // "simt" forces the CUDA-core attention kernels in the bf16 mode (A/B tests)
     e->mma_attn = cfg->precision == 1 && cfg->beam <= 16 && !(a && strcmp(a, "simt") == 0);
     e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
+    const char* lp = getenv("SCB_LN_PROLOGUE");
+    e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && !(lp && strcmp(lp, "0") == 0);
     const char* pdl = getenv("SCB_PDL");     // programmatic dependent launch of the decode-step kernel chain (default on)
     g_use_pdl = !(pdl && strcmp(pdl, "0") == 0);
   }
@@ -819,6 +829,7 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
   if (strcmp(name, "lazy_threshold") == 0) { e->lazy_threshold = value < 0 ? 0 : value; return SC_OK; }
   if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
+  if (strcmp(name, "ln_prologue") == 0) { e->ln_prologue = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
   if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = value != 0 && e->cfg.precision == 1; return SC_OK; }
   if (strcmp(name, "mma_attention") == 0) {
     e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16;
@@ -906,6 +917,12 @@ int sc_linear_bf16_ln(const void* x, const void* w, const float* bias, const flo
                       const float* ln_b, void* ln_out_bf16, int32_t m, int32_t k, void* stream) {
   return launch_gemm_bf16_ln((const __nv_bfloat16*)x, k, (const __nv_bfloat16*)w, bias, residual, 256, y, 256, nullptr, 0, nullptr,
                              m, 256, k, 0, nullptr, ln_w, ln_b, (__nv_bfloat16*)ln_out_bf16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+
+int sc_linear_bf16_lnA(const float* x_f32, const float* ln_w, const float* ln_b, const void* w, const float* bias, float* y,
+                       void* y16, int32_t m, int32_t n, int32_t relu, void* stream) {
+  return launch_gemm_bf16_lnA(x_f32, 256, ln_w, ln_b, (const __nv_bfloat16*)w, bias, y, n, (__nv_bfloat16*)y16, n, m, n, relu,
+                              nullptr, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }
 
 }  // extern "C"

@@ -13,6 +13,7 @@ constexpr int NFFT = 512, HOPS = 160, WINL = 400, NBIN = 257, NMEL = 80;
 
 __constant__ float c_window[NFFT];        // hann(400) zero-padded to 512 (offset 56)
 __constant__ float2 c_twiddle[NFFT / 2];  // exp(-2*pi*i*k/512)
+__constant__ int2 c_melrange[NMEL];       // [k_lo, k_hi) of the non-zero taps of every (triangular) mel filter
 static float* g_melfb = nullptr;          // [257][80] device copy (owned by the library, 82 KB)
 
 int frontend_upload_tables(const float* window400, const float* mel_fb) {
@@ -26,6 +27,15 @@ int frontend_upload_tables(const float* window400, const float* mel_fb) {
     tw[k] = make_float2((float)cos(a), (float)sin(a));
   }
   SCB_CUDA_CHECK(cudaMemcpyToSymbol(c_twiddle, tw, sizeof(tw)));
+  int2 rng[NMEL];
+  for (int m = 0; m < NMEL; ++m) {
+    int lo = NBIN, hi = 0;
+    for (int k = 0; k < NBIN; ++k)
+      if (mel_fb[k * NMEL + m] != 0.f) { if (k < lo) lo = k; hi = k + 1; }
+    if (lo >= hi) { lo = 0; hi = 0; }
+    rng[m] = make_int2(lo, hi);
+  }
+  SCB_CUDA_CHECK(cudaMemcpyToSymbol(c_melrange, rng, sizeof(rng)));
   if (!g_melfb) SCB_CUDA_CHECK(cudaMalloc(&g_melfb, sizeof(float) * NBIN * NMEL));
   SCB_CUDA_CHECK(cudaMemcpy(g_melfb, mel_fb, sizeof(float) * NBIN * NMEL, cudaMemcpyHostToDevice));
   return 0;
@@ -90,8 +100,10 @@ __global__ void __launch_bounds__(128) frontend_kernel(
   __syncwarp();
   float* out = featbuf + ((size_t)d.stream * feat_cap + d.feat_off + (f - d.emit0)) * NMEL;
   for (int m = lane; m < NMEL; m += 32) {
+    // taps outside [k_lo, k_hi) are exactly zero, and fma(p, 0, acc) == acc, so skipping them is bit-identical
     float acc = 0.f;
-    for (int k = 0; k < NBIN; ++k) acc = fmaf(p[k], melfb[k * NMEL + m], acc);
+    const int2 rg = c_melrange[m];
+    for (int k = rg.x; k < rg.y; ++k) acc = fmaf(p[k], melfb[k * NMEL + m], acc);
     float lg = logf(fmaxf(acc, 1e-10f));
     if (mean) lg = (float)(((double)lg - mean[m]) / std_[m]);   // numpy fp64 round trip, :355-358
     out[m] = lg;

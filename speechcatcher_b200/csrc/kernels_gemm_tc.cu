@@ -95,18 +95,17 @@ struct TcParams {
   const int64_t* c_row_off; int M, N, K, relu; const int* n_rows_dev;
   // optional fused LayerNorm of the output rows (needs BN == N): y = LN(C_row) * ln_w + ln_b -> bf16 ln_out[M][N]
   const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out;
+  // LNA variant: the A operand is LayerNorm(X) computed in the kernel from fp32 rows (K == 256 == all four K-blocks)
+  const float* lna_x; int lna_ldx; const float* lna_w; const float* lna_b;
 };
 
-template <int BN, int TC_STAGES>
+template <int BN, int TC_STAGES, bool LNA>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b,
                                                                      TcParams p) {
-  pdl_sync();
-  int M = p.M;
-  if (p.n_rows_dev) M = min(M, *p.n_rows_dev);
+  // Everything up to pdl_sync() is independent of the preceding kernel (barrier init, TMEM allocation, tensor-map
+  // prefetch), so under programmatic dependent launch it overlaps with that kernel's tail.
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  if (m0 >= M) return;                       // uniform for the whole CTA, before any barrier / allocation
-
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
@@ -115,7 +114,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
   uint64_t* full_bar = (uint64_t*)(sB + TC_STAGES * B_BYTES);
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full = empty_bar + TC_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* a_ready = tmem_full + 1;         // LNA: the four epilogue warps have written the normalised A tile
+  uint32_t* tmem_slot = (uint32_t*)(a_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.K / TC_BK;
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(tmem_full, 1);
+    mbar_init(a_ready, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {                           // TMEM allocation: BN fp32 columns (power of two >= 32)
@@ -136,14 +137,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_sync();                                // from here on the producer kernel's writes (A, n_rows) are visible
+  int M = p.M;
+  if (p.n_rows_dev) M = min(M, *p.n_rows_dev);
+  const bool cta_active = m0 < M;            // uniform for the whole CTA; inactive CTAs only tear down
+
+  if (!cta_active) {
+    // nothing to compute
+  } else
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-        tma_load_2d(&map_a, &full_bar[s], sA + s * A_BYTES, kb * TC_BK, m0);
+        if (LNA) {
+          mbar_expect_tx(&full_bar[s], B_BYTES);
+        } else {
+          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          tma_load_2d(&map_a, &full_bar[s], sA + s * A_BYTES, kb * TC_BK, m0);
+        }
         tma_load_2d(&map_b, &full_bar[s], sB + s * B_BYTES, kb * TC_BK, n0);
       }
     }
@@ -153,6 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      if (LNA) mbar_wait(a_ready, 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
@@ -172,6 +186,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    if (LNA) {
+      // A tile = bf16(LayerNorm(X rows)) written straight into the 128-byte-swizzled K-major layout TMA would
+      // produce: K-block kb = lane / 8, 16-byte chunk c = lane % 8 of tile row R lands at chunk (c ^ (R & 7)).
+      // Same arithmetic as layernorm_kernel (two-pass moments, eps 1e-12), so results are bit-identical to the
+      // unfused LayerNorm -> GEMM pair.
+      float w8[8], b8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { w8[i] = __ldg(p.lna_w + lane * 8 + i); b8[i] = __ldg(p.lna_b + lane * 8 + i); }
+      const int kbl = lane >> 3, ch = lane & 7;
+      for (int rl = 0; rl < 32; ++rl) {
+        const int R = q * 32 + rl, m = m0 + R;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (m < M) {
+          const float* xr = p.lna_x + (size_t)m * p.lna_ldx + lane * 8;
+          const float4 a = *reinterpret_cast<const float4*>(xr), b = *reinterpret_cast<const float4*>(xr + 4);
+          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          float sm = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sm += v[i];
+          const float mean = warp_sum(sm) / 256.f;
+          float qq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; qq += d * d; }
+          const float rstd = 1.0f / sqrtf(warp_sum(qq) / 256.f + 1e-12f);
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * w8[i] + b8[i];
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(y[4], y[5]), h3 = __floats2bfloat162_rn(y[6], y[7]);
+          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+        *reinterpret_cast<uint4*>(sA + kbl * A_BYTES + R * 128 + ((ch ^ (R & 7)) << 4)) = u;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready)) : "memory");
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int m = m0 + q * 32 + lane;
@@ -299,19 +350,19 @@ static int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CU
   return 0;
 }
 
-template <int BN, int TC_STAGES>
+template <int BN, int TC_STAGES, bool LNA = false>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = 1024 + TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TC_STAGES, LNA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(smem=%zu) failed", smem);
       return -1;
     }
     attr_set = true;
   }
   dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
-  launch_k(gemm_bf16_tc_kernel<BN, TC_STAGES>, grid, dim3(TC_THREADS), smem, st, ma, mb, p);
+  launch_k(gemm_bf16_tc_kernel<BN, TC_STAGES, LNA>, grid, dim3(TC_THREADS), smem, st, ma, mb, p);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -335,13 +386,28 @@ int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
   CUtensorMap ma, mb;
   if (get_map(A, M, K, lda, TC_BM, &ma)) return -1;
   if (get_map(W, N, K, K, BN, &mb)) return -1;
-  TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev, ln_w, ln_b, ln_out};
+  TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev, ln_w, ln_b, ln_out, nullptr, 0, nullptr, nullptr};
   // K <= 256 has only four K-blocks: two stages let several CTAs share an SM so that one CTA's epilogue
   // overlaps another's main loop; deeper K keeps the four-stage ring
   const bool shallow = K / TC_BK <= 4;
   if (ln) return shallow ? launch_bn<256, 2>(ma, mb, p, st) : launch_bn<256, 4>(ma, mb, p, st);
   if (small) return shallow ? launch_bn<64, 2>(ma, mb, p, st) : launch_bn<64, 4>(ma, mb, p, st);
   return shallow ? launch_bn<128, 2>(ma, mb, p, st) : launch_bn<128, 4>(ma, mb, p, st);
+}
+
+// C = act(LayerNorm(X) * W^T + bias): the LayerNorm of the fp32 rows X [M][256] is computed inside the GEMM (K = 256).
+int launch_gemm_bf16_lnA(const float* X, int ldx, const float* lna_w, const float* lna_b, const __nv_bfloat16* W,
+                         const float* bias, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int relu,
+                         const int* n_rows_dev, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  const int K = 256;
+  if (N % 64 != 0 || ldx % 4 != 0) { set_last_error("gemm_bf16_lnA: unsupported shape M=%d N=%d ldx=%d", M, N, ldx); return -1; }
+  const bool small = (N % 128 != 0) || ((long)cdiv(M, TC_BM) * (N / 128) < kNumSMs);
+  const int BN = small ? 64 : 128;
+  CUtensorMap mb;
+  if (get_map(W, N, K, K, BN, &mb)) return -1;
+  TcParams p{bias, nullptr, 0, C, ldc, Cb, ldcb, nullptr, M, N, K, relu, n_rows_dev, nullptr, nullptr, nullptr, X, ldx, lna_w, lna_b};
+  return small ? launch_bn<64, 4, true>(mb, mb, p, st) : launch_bn<128, 4, true>(mb, mb, p, st);
 }
 
 int launch_gemm_bf16_ex(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, const float* R,

@@ -72,3 +72,32 @@ def test_linear_bf16_fused_layernorm(M, K):
     assert (y - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
     want_ln = torch.nn.functional.layer_norm(want, (256,), lw, lb, 1e-12)
     assert (ln.float() - want_ln).abs().max().item() <= 3e-2
+
+
+@pytest.mark.parametrize("M,N,relu,bf16_out", [(77, 768, 0, False), (2560, 256, 0, False), (2340, 2048, 1, True),
+                                                (10752, 768, 0, True), (300, 1024, 0, False)])
+def test_linear_bf16_layernorm_prologue(M, N, relu, bf16_out):
+    """LayerNorm computed inside the GEMM (A tile written in the swizzled operand layout by the epilogue warps):
+    must equal the unfused LayerNorm(bf16) -> tensor-core GEMM pair."""
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = 2.0 * torch.randn(M, 256, generator=g, device="cuda") + 0.3
+    lw = 1.0 + 0.1 * torch.randn(256, generator=g, device="cuda")
+    lb = 0.1 * torch.randn(256, generator=g, device="cuda")
+    w = (torch.randn(N, 256, generator=g, device="cuda") / 16).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda")
+    y = torch.full((M, N), float("nan"), device="cuda")
+    y16 = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda") if bf16_out else None
+    _lib.check(lib.sc_linear_bf16_lnA(x.data_ptr(), lw.data_ptr(), lb.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                      y.data_ptr(), y16.data_ptr() if bf16_out else None, M, N, relu, None), "lnA")
+    torch.cuda.synchronize()
+    a = torch.nn.functional.layer_norm(x, (256,), lw, lb, 1e-12).to(torch.bfloat16)
+    want = a.float() @ w.float().t() + bias
+    if relu:
+        want = want.relu()
+    # a one-ulp difference in a bf16 A element (LayerNorm rounding) moves an output by at most ~|a| * |w| * 2^-8
+    assert (y - want).abs().max().item() <= 2e-2
+    assert (y - want).abs().mean().item() <= 1e-3
+    if bf16_out:
+        assert (y16.float() - want).abs().max().item() <= 5e-2

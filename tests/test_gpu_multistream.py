@@ -112,3 +112,21 @@ def test_deferred_decoding_same_final_results():
         np.testing.assert_allclose(sc, [h.score for h in orc.hyps], atol=2e-3, rtol=0)
         assert [r[2] for r in grp.results(s, True, True)] == [r[2] for r in want]
     assert total_steps > 0
+
+
+def test_beam20_fp32_and_bf16_smoke():
+    """BASELINE config 5 shape (beam 20): exact parity in fp32; the bf16 mode (CUDA-core attention for beam > 16)
+    must run and produce a full beam of finite scores."""
+    grp = _run("xl_d4", 20, [3 * 16000 + 50, 3 * 16000], {0: 8192, 1: 8192})
+    assert grp.beam_size == 20
+    from speechcatcher_b200 import StreamGroup
+    from speechcatcher_b200.synthetic import synth_audio
+    g16 = StreamGroup(model_dir("xl_d4"), n_streams=2, beam_size=20, device="cuda:0", dtype="bfloat16", max_seconds=6)
+    n = 3 * 16000
+    audio = [synth_audio(90 + s, n) for s in range(2)]
+    for i in range(0, n, 8192):
+        fin = i + 8192 >= n
+        g16.push([0, 1], [a[i:i + 8192] for a in audio], [fin, fin])
+    for s in range(2):
+        ys, sc, xp, _ = g16.beam(s)
+        assert len(ys) == 20 and all(np.isfinite(sc)) and len(ys[0]) > 3
