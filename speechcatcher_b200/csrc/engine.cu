@@ -425,7 +425,8 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     e->mma_attn = cfg->precision == 1 && cfg->beam <= 16 && !(a && strcmp(a, "simt") == 0);
     e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
     const char* lp = getenv("SCB_LN_PROLOGUE");
-    e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && !(lp && strcmp(lp, "0") == 0);
+    // measured slower than a separate LayerNorm kernel (every N-tile CTA re-normalises its 128 rows): opt-in only
+    e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && lp && strcmp(lp, "1") == 0;
     const char* pdl = getenv("SCB_PDL");     // programmatic dependent launch of the decode-step kernel chain (default on)
     g_use_pdl = !(pdl && strcmp(pdl, "0") == 0);
   }

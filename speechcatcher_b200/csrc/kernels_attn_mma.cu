@@ -14,7 +14,11 @@
 
 namespace scb {
 
-constexpr int MMA_TILE = 128;      // keys per tile (32 per warp)
+constexpr int MMA_TILE = 64;       // keys per tile: small tiles keep ~10 CTAs per SM resident, which hides the
+                                   // dependent global-load latency of these short (2-12 tile) kernels
+constexpr int MMA_KPW = MMA_TILE / 4;   // keys per warp
+constexpr int MMA_NT = MMA_KPW / 8;     // score n-tiles per warp
+constexpr int MMA_KK = MMA_KPW / 16;    // k-steps of the P*V product per warp
 constexpr int MMA_MAXB = 16;       // rows of the m16 tile
 constexpr int MMA_ANC_B = 20;
 
@@ -197,13 +201,13 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
     const int buf = t & 1;
     if (t + 1 < n_tiles) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    const __nv_bfloat16* kb = Kt + (size_t)buf * MMA_TILE * RS + (size_t)(32 * warp) * RS;
-    const __nv_bfloat16* vb = Vt + (size_t)buf * MMA_TILE * RS + (size_t)(32 * warp) * RS;
-    const signed char* ob = own + buf * MMA_TILE + 32 * warp;
-    // ---- S = Q K^T for this warp's 32 keys
-    float sacc[4][4];
+    const __nv_bfloat16* kb = Kt + (size_t)buf * MMA_TILE * RS + (size_t)(MMA_KPW * warp) * RS;
+    const __nv_bfloat16* vb = Vt + (size_t)buf * MMA_TILE * RS + (size_t)(MMA_KPW * warp) * RS;
+    const signed char* ob = own + buf * MMA_TILE + MMA_KPW * warp;
+    // ---- S = Q K^T for this warp's MMA_KPW keys
+    float sacc[MMA_NT][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < MMA_NT; ++nt) {
       sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
 #pragma unroll
       for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
     // ---- mask + online softmax (rows r0, r1 of this thread)
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < MMA_NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = 8 * nt + 2 * qd + (e & 1);
@@ -236,9 +240,9 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
       scale[h] = (m_new == -INFINITY) ? 1.f : expf(m_run[h] - m_new);
       m_run[h] = m_new;
     }
-    uint32_t pa[2][4];
+    uint32_t pa[MMA_KK][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < MMA_NT; ++nt) {
       float p[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
     for (int nd = 0; nd < NDT; ++nd) { o[nd][0] *= scale[0]; o[nd][1] *= scale[0]; o[nd][2] *= scale[1]; o[nd][3] *= scale[1]; }
     // ---- O += P V
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
+    for (int kk = 0; kk < MMA_KK; ++kk) {
 #pragma unroll
       for (int nd = 0; nd < NDT; ++nd) {
         uint32_t bfr[2];

@@ -195,30 +195,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < 8; ++i) { w8[i] = __ldg(p.lna_w + lane * 8 + i); b8[i] = __ldg(p.lna_b + lane * 8 + i); }
       const int kbl = lane >> 3, ch = lane & 7;
-      for (int rl = 0; rl < 32; ++rl) {
-        const int R = q * 32 + rl, m = m0 + R;
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (m < M) {
-          const float* xr = p.lna_x + (size_t)m * p.lna_ldx + lane * 8;
-          const float4 a = *reinterpret_cast<const float4*>(xr), b = *reinterpret_cast<const float4*>(xr + 4);
-          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      constexpr int RB = 8;                   // rows per batch: all loads of a batch are in flight together
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += RB) {
+        float v[RB][8];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          const int m = m0 + q * 32 + r0 + j;
+          if (m < M) {
+            const float* xr = p.lna_x + (size_t)m * p.lna_ldx + lane * 8;
+            const float4 a = *reinterpret_cast<const float4*>(xr), b = *reinterpret_cast<const float4*>(xr + 4);
+            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w; v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          const int R = q * 32 + r0 + j, m = m0 + R;
           float sm = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sm += v[i];
+          for (int i = 0; i < 8; ++i) sm += v[j][i];
           const float mean = warp_sum(sm) / 256.f;
           float qq = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; qq += d * d; }
+          for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; qq += d * d; }
           const float rstd = 1.0f / sqrtf(warp_sum(qq) / 256.f + 1e-12f);
-          float y[8];
+          uint4 u = make_uint4(0u, 0u, 0u, 0u);
+          if (m < M) {
+            float y[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * w8[i] + b8[i];
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(y[4], y[5]), h3 = __floats2bfloat162_rn(y[6], y[7]);
-          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            for (int i = 0; i < 8; ++i) y[i] = (v[j][i] - mean) * rstd * w8[i] + b8[i];
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(y[4], y[5]), h3 = __floats2bfloat162_rn(y[6], y[7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+          }
+          *reinterpret_cast<uint4*>(sA + kbl * A_BYTES + R * 128 + ((ch ^ (R & 7)) << 4)) = u;
         }
-        *reinterpret_cast<uint4*>(sA + kbl * A_BYTES + R * 128 + ((ch ^ (R & 7)) << 4)) = u;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready)) : "memory");
