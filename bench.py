@@ -332,7 +332,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.dtype == "float32" else "bf16", "data": "synthetic",
-                "config": {"workload": workload, "l2": "inputs larger than L2 (983 MB of waveforms per GPU)",
+                "config": {"workload": workload, "l2": f"inputs larger than L2 ({S * n_chunks * CHUNK * 4 / 1e6:.0f} MB of waveforms per GPU)",
                            "decode_scheduling": ("strict: every push drains its decode blocks" if lazy == 0 else
                                                  f"deferred: a push stops iterating below {lazy} active streams; final calls drain"),
                            "decode_steps_per_pass": stats["steps"] // max(1, args.steps),

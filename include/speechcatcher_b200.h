@@ -105,6 +105,8 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
  * are still active and leaves the stragglers' decode blocks queued on the device (they continue during later
  * pushes; any final call drains everything), which trades per-call completeness of non-final beams for fewer,
  * fuller search iterations.  0 (default) = strict: every push fully decodes its blocks like the reference.
+ * "overlap" = 0/1 (default 1): in deferred mode run a push's frontend/encoder on a second CUDA stream while the
+ * caller's stream keeps iterating the search for blocks queued by earlier pushes.
  * "mma_attention" = 0/1: CUDA-core or tensor-core attention in the bf16 mode.  "pdl" = 0/1: programmatic dependent
  * launch of the decode-step kernel chain (process-wide).  "fuse_layernorm" = 0/1: experimental LN-in-epilogue GEMMs. */
 int sc_engine_set_option(void* handle, const char* name, int32_t value);

@@ -108,6 +108,12 @@ struct Engine {
   // deferred decoding: a push stops iterating once fewer than `lazy_threshold` streams are active and leaves
   // the stragglers' blocks queued on the device; they continue during later pushes (0 = strict, drain every push)
   int lazy_threshold = 0;
+  // deferred mode: the frontend/encoder part of a push runs on its own stream while the caller's stream keeps
+  // iterating the search for blocks queued by earlier pushes (they touch disjoint rows of the append-only buffers)
+  bool overlap = true;
+  cudaStream_t st_enc = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_wave = nullptr, ev_enc = nullptr;
+  bool enc_pending = false;
   std::vector<int> pending_bound;   // host upper bound of queued blocks per stream
   // live kernel timing (bench.py roofline): CUDA-event pairs around every launch of one tagged kernel
   int prof_tag = 0;                 // 0 off, >0 one tag, -1 every tag (decode steps sampled every prof_stride)
@@ -419,6 +425,10 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   }
   cudaEventCreateWithFlags(&e->ev[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev[1], cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&e->st_enc, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_wave, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_enc, cudaEventDisableTiming);
   e->enc.resize(cfg->enc_layers); e->dec.resize(cfg->dec_layers);
   {
     const char* a = getenv("SCB_ATTN");     // "simt" forces the CUDA-core attention kernels in the bf16 mode (A/B tests)
@@ -440,6 +450,8 @@ int sc_engine_destroy(void* handle) {
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->h_flag) cudaFreeHost(e->h_flag);
   cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
+  if (e->st_enc) { cudaStreamSynchronize(e->st_enc); cudaStreamDestroy(e->st_enc); }
+  if (e->ev_in) { cudaEventDestroy(e->ev_in); cudaEventDestroy(e->ev_wave); cudaEventDestroy(e->ev_enc); }
   delete e;
   return SC_OK;
 }
@@ -526,6 +538,7 @@ int sc_engine_reset(void* handle, const int32_t* streams, int32_t n, void* strea
   Engine* e = (Engine*)handle;
   if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->enc_pending) { SCB_CUDA_CHECK(cudaEventSynchronize(e->ev_enc)); e->enc_pending = false; }
   for (int i = 0; i < n; ++i) {
     if (streams[i] < 0 || streams[i] >= e->cfg.n_streams) { set_last_error("bad stream id %d", streams[i]); return SC_ERR_ARG; }
     e->planner.reset(streams[i]);
@@ -544,10 +557,18 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   Engine* e = (Engine*)handle;
   if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
   const ScConfig& c = e->cfg; const Caps& k = e->cap;
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t sd = (cudaStream_t)stream;          // caller's stream: the search runs here
+  const bool use_enc_stream = e->overlap && e->lazy_threshold > 0;
+  cudaStream_t st = use_enc_stream ? e->st_enc : sd;  // frontend + encoder part of this push
   const int S = c.n_streams, D = c.d_model, V = c.vocab;
   e->launches = 0;
   Engine& eref = *e;
+  // the pinned descriptor staging is reused: the previous push's uploads (on the encoder stream) must be done
+  if (e->enc_pending) { SCB_CUDA_CHECK(cudaEventSynchronize(e->ev_enc)); e->enc_pending = false; }
+  if (use_enc_stream) {                             // the encoder stream starts after the caller's H2D of the waveforms
+    SCB_CUDA_CHECK(cudaEventRecord(e->ev_in, sd));
+    SCB_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_in, 0));
+  }
   if (n < 0 || n > S) { set_last_error("push: n=%d out of range", n); return SC_ERR_ARG; }
   // ---------------- plan on the host
   std::vector<StreamPush> plans(n);
@@ -605,6 +626,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   for (int i = 0; i < n; ++i) {
     StreamPush& p = plans[i];
     const int s = streams[i];
+    if (is_final[i]) any_final = true;
     if (p.run_sub) {
       p.sd.row0 = sub_rows; sub_rows += p.sd.t2;
       h_sd[n_sd++] = p.sd;
@@ -634,7 +656,6 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
         h_q[2 * S + S * k.qpush + n_q * k.qpush + j] = p.dq_final[j];
       }
       if (e->pending_bound[s] + (int)p.dq_T.size() > k.qcap) need_drain = true;
-      if (is_final[i]) any_final = true;
       n_q++;
     }
   }
@@ -663,6 +684,10 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
 #undef e
   TRY(launch_wavebuf_update(wave_dev, ld_wave, e->wbuf, 512, e->d_fd, n_fd_all, st));
   e->launches += 2;
+  if (use_enc_stream) {                             // later work on the caller's stream (e.g. the next H2D into wave_dev)
+    SCB_CUDA_CHECK(cudaEventRecord(e->ev_wave, st));   // is ordered after the waveforms have been consumed
+    SCB_CUDA_CHECK(cudaStreamWaitEvent(sd, e->ev_wave, 0));
+  }
   // ---------------- conv2d sub-sampling
   const bool tc = c.precision == 1;
   if (n_sd > 0) {
@@ -739,45 +764,51 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     e->launches += 2 + c.dec_layers;
   }
   if (petot) prof_mark(eref, T_ENC_TOTAL, st, false);
-  // ---------------- block-synchronous beam search
+  if (use_enc_stream) { SCB_CUDA_CHECK(cudaEventRecord(e->ev_enc, st)); e->enc_pending = true; }
+  // ---------------- block-synchronous beam search (caller's stream)
   int steps = 0;
   // the loop stops when fewer than `stop_below` streams are active: 1 = drain (strict mode, final calls)
   const int stop_below = (e->lazy_threshold > 0 && !any_final) ? e->lazy_threshold : 1;
   auto decode_loop = [&](int below) -> int {
-    SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[0], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    SCB_CUDA_CHECK(cudaEventRecord(e->ev[0], st));
+    SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[0], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, sd));
+    SCB_CUDA_CHECK(cudaEventRecord(e->ev[0], sd));
     // one step is always in flight ahead of the host's view of n_active (kernels of an empty step exit at once)
     for (int i = 0;; ++i) {
-      TRY(run_decode_step(*e, st));
+      TRY(run_decode_step(*e, sd));
       steps++;
-      SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[2 * ((i + 1) & 1)], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-      SCB_CUDA_CHECK(cudaEventRecord(e->ev[(i + 1) & 1], st));
+      SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[2 * ((i + 1) & 1)], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, sd));
+      SCB_CUDA_CHECK(cudaEventRecord(e->ev[(i + 1) & 1], sd));
       SCB_CUDA_CHECK(cudaEventSynchronize(e->ev[i & 1]));
       if (e->h_flag[2 * (i & 1)] < below) break;
       if (steps > 64 * kMaxLength) { set_last_error("decode loop did not terminate"); return SC_ERR_STATE; }
     }
-    SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+    SCB_CUDA_CHECK(cudaStreamSynchronize(sd));
     if (e->h_flag[1] || e->h_flag[3]) {
       set_last_error("decode capacity exceeded (flag %d): token capacity %d / queue capacity %d", e->h_flag[1] | e->h_flag[3], k.Lcap, k.qcap);
       return SC_ERR_CAPACITY;
     }
+    const int last = e->h_flag[0] < e->h_flag[2] ? e->h_flag[0] : e->h_flag[2];
+    if (below == 1 || last == 0) std::fill(e->pending_bound.begin(), e->pending_bound.end(), 0);
     return 0;
   };
-  if (need_drain) {                                   // deferred blocks would overflow a device queue: drain first
-    TRY(decode_loop(1));
-    std::fill(e->pending_bound.begin(), e->pending_bound.end(), 0);
-  }
-  TRY(launch_search_begin(e->sb, e->d_q, e->d_q + S, e->d_q + 2 * S, e->d_q + 2 * S + S * k.qpush, k.qpush, n_q, st));
-  e->launches += 2;
-  for (int i = 0; i < n; ++i) e->pending_bound[streams[i]] += (int)plans[i].dq_T.size();
-  bool pending_any = false;
-  for (int v : e->pending_bound) pending_any |= v > 0;
-  if (!pending_any) {
-    SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+  auto any_pending = [&]() { for (int v : e->pending_bound) if (v > 0) return true; return false; };
+  auto enqueue = [&]() -> int {                      // this push's decode blocks -> device queues (needs the encoder output)
+    if (use_enc_stream) SCB_CUDA_CHECK(cudaStreamWaitEvent(sd, e->ev_enc, 0));
+    TRY(launch_search_begin(e->sb, e->d_q, e->d_q + S, e->d_q + 2 * S, e->d_q + 2 * S + S * k.qpush, k.qpush, n_q, sd));
+    e->launches += 2;
+    for (int i = 0; i < n; ++i) e->pending_bound[streams[i]] += (int)plans[i].dq_T.size();
+    return 0;
+  };
+  if (use_enc_stream && !any_final && !need_drain) {
+    // overlapped: keep iterating blocks queued by earlier pushes while this push's encoder runs on its own stream,
+    // then queue the new blocks (they are decoded during the next push, or by the final drain)
+    if (any_pending()) TRY(decode_loop(stop_below));
+    TRY(enqueue());
   } else {
-    TRY(decode_loop(stop_below));
-    const int last = e->h_flag[0] < e->h_flag[2] ? e->h_flag[0] : e->h_flag[2];
-    if (stop_below == 1 || last == 0) std::fill(e->pending_bound.begin(), e->pending_bound.end(), 0);
+    if (need_drain && any_pending()) TRY(decode_loop(1));   // deferred blocks would overflow a device queue: drain first
+    TRY(enqueue());
+    if (!any_pending()) { SCB_CUDA_CHECK(cudaStreamSynchronize(sd)); }
+    else TRY(decode_loop(stop_below));
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -829,6 +860,7 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   Engine* e = (Engine*)handle;
   if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
   if (strcmp(name, "lazy_threshold") == 0) { e->lazy_threshold = value < 0 ? 0 : value; return SC_OK; }
+  if (strcmp(name, "overlap") == 0) { e->overlap = value != 0; return SC_OK; }
   if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
   if (strcmp(name, "ln_prologue") == 0) { e->ln_prologue = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
   if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = value != 0 && e->cfg.precision == 1; return SC_OK; }
