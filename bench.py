@@ -129,6 +129,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--breakdown", action="store_true", help="always run the all-kernel timing pass")
+    ap.add_argument("--shards", type=int, default=int(os.environ.get("SCB_BENCH_SHARDS", "4")),
+                    help="split the GPU's streams into this many concurrently driven groups (own CUDA stream + host thread)")
     ap.add_argument("--lazy", type=int, default=int(os.environ.get("SCB_BENCH_LAZY", "-1")),
                     help="deferred-decode threshold (streams); 0 = strict per-push decoding; -1 = streams - streams/32")
     args = ap.parse_args()
@@ -192,34 +194,68 @@ def main():
     host.zero_()
     for s in range(S):
         host[s, :n_samples] = torch.from_numpy(synth_audio(rank * S + s, n_samples))
-    grp = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype=args.dtype,
-                      use_bbd=False, max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
-    lazy = args.lazy if args.lazy >= 0 else max(1, S - S // 32)
-    grp.set_option("lazy_threshold", lazy)
+    from speechcatcher_b200.sharded_group import ShardedStreamGroup
+    G = max(1, args.shards)
+    assert S % G == 0, "--streams must be a multiple of --shards"
+    per = S // G
+    lazy = args.lazy if args.lazy >= 0 else max(1, per - per // 32)
+
+    def make_groups(dtype):
+        kw = dict(beam_size=args.beam, ctc_weight=0.3, dtype=dtype, use_bbd=False, max_chunk=CHUNK,
+                  max_seconds=args.seconds + 1.0)
+        if G == 1:
+            g = StreamGroup(md, n_streams=S, device=dev, **kw)
+            g.set_option("lazy_threshold", lazy)
+            return None, [g]
+        sg_ = ShardedStreamGroup(md, S, G, device=dev, **kw)
+        sg_.set_option("lazy_threshold", lazy)
+        return sg_, sg_.shards
+
+    sg, groups = make_groups(args.dtype)
+    grp = groups[0]                                   # kernel timing / roofline are taken on shard 0
     resident = host.to(dev)                           # inputs resident in HBM for `value`
-    ids = np.arange(S, dtype=np.int32)
-    lens_all = [np.full(S, min(CHUNK, n_samples - c * CHUNK), np.int32) for c in range(n_chunks)]
-    fin_all = [np.full(S, 1 if c == n_chunks - 1 else 0, np.int32) for c in range(n_chunks)]
+    ids = np.arange(per, dtype=np.int32)
+    lens_all = [np.full(per, min(CHUNK, n_samples - c * CHUNK), np.int32) for c in range(n_chunks)]
+    fin_all = [np.full(per, 1 if c == n_chunks - 1 else 0, np.int32) for c in range(n_chunks)]
     stats = {"steps": 0, "launches": 0, "blocks": 0}
+    stats_lock = threading.Lock()
+
+    def run_shards(sgroup, glist, fn):
+        if sgroup is None:
+            return [fn(0, glist[0], 0, S)]
+        return sgroup.run_pass(fn)
+
+    def shard_pass_resident(i, g, lo, hi, res=None):
+        res = resident if res is None else res
+        g.reset()
+        loc = [0, 0, 0]
+        for c in range(n_chunks):
+            st = g.push_device(ids, res[lo:hi], lens_all[c], fin_all[c], col_offset=c * CHUNK)
+            loc[0] += st.n_decode_steps; loc[1] += st.n_kernel_launches; loc[2] += st.n_encoder_blocks
+        with stats_lock:
+            stats["steps"] = max(stats["steps"], 0) + (loc[0] if i == 0 else 0)
+            stats["launches"] += loc[1]; stats["blocks"] += loc[2]
 
     def one_pass_resident():
-        grp.reset()
-        for c in range(n_chunks):
-            st = grp.push_device(ids, resident, lens_all[c], fin_all[c], col_offset=c * CHUNK)
-            stats["steps"] += st.n_decode_steps; stats["launches"] += st.n_kernel_launches
-            stats["blocks"] += st.n_encoder_blocks
+        run_shards(sg, groups, shard_pass_resident)
 
     lat_ms = []
 
-    def one_pass_e2e():
+    def shard_pass_e2e(i, g, lo, hi):
         """Public API with host buffers: per-chunk H2D from pinned memory inside, results read back."""
-        grp.reset()
+        g.reset()
+        lat = []
         for c in range(n_chunks):
             t1 = time.perf_counter()
-            grp.push_batch(ids, host[:, c * CHUNK: c * CHUNK + int(lens_all[c][0])], lens_all[c], fin_all[c])
-            lat_ms.append(1000.0 * (time.perf_counter() - t1))
-        out = [grp.results(s, True, True) for s in range(S)]
+            g.push_batch(ids, host[lo:hi, c * CHUNK: c * CHUNK + int(lens_all[c][0])], lens_all[c], fin_all[c])
+            lat.append(1000.0 * (time.perf_counter() - t1))
+        out = [g.results(s, True, True) for s in range(hi - lo)]
+        with stats_lock:
+            lat_ms.extend(lat)
         return out
+
+    def one_pass_e2e():
+        return [r for part in run_shards(sg, groups, shard_pass_e2e) for r in part]
 
     def sync_all():
         if world > 1:
@@ -255,6 +291,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         one_pass_resident()
+    torch.cuda.synchronize()          # shards run on their own streams: all of them must be done before the stop event
     e1.record()
     sync_all()
     clocks = sampler.stop()
@@ -291,24 +328,24 @@ def main():
     # the fp32 parity mode (CUDA-core GEMMs, results identical to the reference) measured on the same workload
     fp32_mode = None
     if args.dtype == "bfloat16" and not args.no_fp32:
-        grp.close()
-        del grp, resident
+        for g_ in groups:
+            g_.close()
+        if sg is not None:
+            sg.pool.shutdown(wait=True)
+        del grp, groups, sg, resident
         torch.cuda.empty_cache()
-        g32 = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype="float32",
-                          use_bbd=False, max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
-        g32.set_option("lazy_threshold", lazy)
+        sg32, groups32 = make_groups("float32")
         res32 = host.to(dev)
 
         def pass32():
-            g32.reset()
-            for c in range(n_chunks):
-                g32.push_device(ids, res32, lens_all[c], fin_all[c], col_offset=c * CHUNK)
+            run_shards(sg32, groups32, lambda i, g, lo, hi: shard_pass_resident(i, g, lo, hi, res32))
 
         pass32()
         sync_all()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         pass32()
+        sync_all()
         a1.record()
         sync_all()
         ms32 = a0.elapsed_time(a1)
@@ -316,9 +353,10 @@ def main():
             t = torch.tensor([ms32], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms32 = float(t.item())
+        for g_ in groups32:
+            g_.close()
         fp32_mode = {"value": world * S * args.seconds / (ms32 / 1000.0), "unit": "audio-s/s", "ms_per_step": ms32,
                      "steps": 1, "warmup": 1, "note": "parity mode: true-fp32 CUDA-core GEMMs, n-best identical to the reference"}
-        g32.close()
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -333,6 +371,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.dtype == "float32" else "bf16", "data": "synthetic",
                 "config": {"workload": workload, "l2": f"inputs larger than L2 ({S * n_chunks * CHUNK * 4 / 1e6:.0f} MB of waveforms per GPU)",
+                           "shards_per_gpu": G,
                            "decode_scheduling": ("strict: every push drains its decode blocks" if lazy == 0 else
                                                  f"deferred: a push stops iterating below {lazy} active streams; final calls drain"),
                            "decode_steps_per_pass": stats["steps"] // max(1, args.steps),

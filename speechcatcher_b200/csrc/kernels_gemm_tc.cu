@@ -12,6 +12,7 @@
 // (speechcatcher/model/attention/multi_head_attention.py:79-83,133, layers/feed_forward.py:50,
 //  decoder/transformer_decoder.py:249, ctc.py:40).
 #include <cuda.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -404,7 +405,11 @@ int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
   TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev, ln_w, ln_b, ln_out, nullptr, 0, nullptr, nullptr};
   // K <= 256 has only four K-blocks: two stages let several CTAs share an SM so that one CTA's epilogue
   // overlaps another's main loop; deeper K keeps the four-stage ring
-  const bool shallow = K / TC_BK <= 4;
+  // ... unless the grid is so small (decoder GEMMs) that no two CTAs share an SM anyway: then the deeper ring
+  // loads all four K-blocks at once and exposes the TMA latency once instead of twice
+  const long n_cta = (long)cdiv(M, TC_BM) * (N / BN);
+  static const bool deep_small = [] { const char* v = getenv("SCB_GEMM_DEEP_SMALL"); return !(v && v[0] == '0'); }();
+  const bool shallow = K / TC_BK <= 4 && (n_cta > 2 * kNumSMs || !deep_small);
   if (ln) return shallow ? launch_bn<256, 2>(ma, mb, p, st) : launch_bn<256, 4>(ma, mb, p, st);
   if (small) return shallow ? launch_bn<64, 2>(ma, mb, p, st) : launch_bn<64, 4>(ma, mb, p, st);
   return shallow ? launch_bn<128, 2>(ma, mb, p, st) : launch_bn<128, 4>(ma, mb, p, st);

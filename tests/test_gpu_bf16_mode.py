@@ -38,19 +38,17 @@ def test_bf16_encoder_close_to_reference(case):
     assert ys[0][:4] == want[:4]
 
 
-def test_bf16_first_decode_logprobs_match_oracle_within_1e2():
-    """First decode step: decoder log-probs of the bf16 mode against the oracle trace."""
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_decoder_rows_are_normalised_log_probs(dtype):
+    """After some decode steps the engine's decoder-score buffer holds log-softmax rows in both modes."""
     from speechcatcher_b200 import Speech2TextStreaming
     from speechcatcher_b200.synthetic import synth_audio
-    meta, calls, trace = load_golden("xl_d4_b10_cli")
+    meta, calls, _ = load_golden("xl_d4_b10_cli")
     md = model_dir(meta["arch"], meta["seed"], meta["sharpen"])
     audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
-    for dtype, tol in (("float32", 1e-3), ("bfloat16", 5e-2)):
-        gpu = Speech2TextStreaming(md, beam_size=1, device="cuda:0", dtype=dtype)
-        # beam 1 never changes the first step's single row: run until the first decode happened
-        for (s, e, fin) in meta["calls"][:5]:
-            gpu(audio[s:e], is_final=False)
-        # the engine's last decoded step is not the first; re-run with a fresh object stopping right after call 5's
-        # first iteration is not exposed, so compare the first-step row through a 1-step beam: rows are log-softmax
-        logp = gpu.group.buffer("dlogp").view(-1, 1024)[0].cpu().numpy()
-        assert np.isfinite(logp).all() and abs(np.exp(logp).sum() - 1.0) < 1e-3, dtype
+    gpu = Speech2TextStreaming(md, beam_size=4, device="cuda:0", dtype=dtype)
+    for (s, e, fin) in meta["calls"][:6]:
+        gpu(audio[s:e], is_final=False)
+    logp = gpu.group.buffer("dlogp").view(-1, 1024)[:4].cpu().numpy()
+    assert np.isfinite(logp).all()
+    np.testing.assert_allclose(np.exp(logp.astype(np.float64)).sum(axis=1), 1.0, atol=1e-3)
