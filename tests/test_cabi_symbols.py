@@ -9,7 +9,7 @@ def test_header_symbols_exported_and_bound():
     from speechcatcher_b200 import _lib
     lib = _lib.load()
     header = (REPO / "include" / "speechcatcher_b200.h").read_text()
-    declared = set(re.findall(r"\b(sc_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(sc_[A-Za-z0-9_]+)\s*\(", header))
     assert declared, "no declarations found"
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
