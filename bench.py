@@ -294,6 +294,7 @@ def main():
     torch.cuda.synchronize()          # shards run on their own streams: all of them must be done before the stop event
     e1.record()
     sync_all()
+    timed_stats = dict(stats)         # later passes (e2e, fp32 mode) must not leak into the timed region's counts
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     roof = grp.profile_end(prof)
@@ -374,9 +375,9 @@ def main():
                            "shards_per_gpu": G,
                            "decode_scheduling": ("strict: every push drains its decode blocks" if lazy == 0 else
                                                  f"deferred: a push stops iterating below {lazy} active streams; final calls drain"),
-                           "decode_steps_per_pass": stats["steps"] // max(1, args.steps),
-                           "encoder_blocks_per_pass": stats["blocks"] // max(1, args.steps)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": stats["launches"],
+                           "decode_steps_per_pass": timed_stats["steps"] // max(1, args.steps),
+                           "encoder_blocks_per_pass": timed_stats["blocks"] // max(1, args.steps)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": timed_stats["launches"],
                 "roofline": roof, "cpu_baseline": cpu_base, "fp32_mode": fp32_mode,
                 "kernel_breakdown_sampled": breakdown}
         print(json.dumps(line))

@@ -20,7 +20,7 @@ constexpr int MMA_KPW = MMA_TILE / 4;   // keys per warp
 constexpr int MMA_NT = MMA_KPW / 8;     // score n-tiles per warp
 constexpr int MMA_KK = MMA_KPW / 16;    // k-steps of the P*V product per warp
 constexpr int MMA_MAXB = 16;       // rows of the m16 tile
-constexpr int MMA_ANC_B = 20;
+constexpr int MMA_KEYS_SMEM = 768;  // self-attention key list entries staged in shared memory (longer lists spill to global)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
   __nv_bfloat16* Kt = Qs + 16 * RS;                                             // [2][TILE][RS]
   __nv_bfloat16* Vt = Kt + 2 * MMA_TILE * RS;                                   // [2][TILE][RS]
   signed char* own = reinterpret_cast<signed char*>(Vt + 2 * MMA_TILE * RS);    // [2][TILE]
+  int* keys_s = reinterpret_cast<int*>(own + 2 * MMA_TILE);                      // self only: [MMA_KEYS_SMEM]
   // merge scratch aliases the K tiles after the main loop
   float* mrg_m = reinterpret_cast<float*>(Kt);                                   // [4][16]
   float* mrg_l = mrg_m + 64;                                                     // [4][16]
@@ -149,7 +150,9 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
     }
     n_keys = sb.self_nkeys[s];
     keys = sb.self_keys + (size_t)s * sb.key_cap;
-    __syncthreads();                    // appended rows visible to the tile loads below
+    // the key list is read once, coalesced, instead of one dependent global load in front of every tile
+    for (int i = tid; i < n_keys && i < MMA_KEYS_SMEM; i += 128) keys_s[i] = keys[i];
+    __syncthreads();                    // key list staged; appended rows visible to the tile loads below
   } else {
     n_keys = c.Tb;
     if (tid == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 2));
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
         int owner = -1;
         if (MODE == 1) src = base + (size_t)u * row_stride;
         else {
-          const int kd_ = keys[u];
+          const int kd_ = u < MMA_KEYS_SMEM ? keys_s[u] : keys[u];
           src = base + ((size_t)(kd_ & 0xffff) * B + ((kd_ >> 16) & 0xff)) * row_stride;
           owner = (kd_ >> 24) - 1;
         }
@@ -438,6 +441,7 @@ static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const 
                         __nv_bfloat16* out16, cudaStream_t st) {
   constexpr int RS = DK + 8;
   size_t smem = sizeof(__nv_bfloat16) * ((size_t)16 * RS + 4 * (size_t)MMA_TILE * RS) + 2 * MMA_TILE + 16;
+  if (MODE == 0) smem += sizeof(int) * MMA_KEYS_SMEM;
   const size_t merge = sizeof(float) * (128 + 4 * 16 * DK);
   if (sizeof(__nv_bfloat16) * 2 * (size_t)MMA_TILE * RS < merge) { set_last_error("attn_mma: merge scratch does not fit"); return -1; }
   static size_t attr = 0;

@@ -130,3 +130,36 @@ def test_beam20_fp32_and_bf16_smoke():
     for s in range(2):
         ys, sc, xp, _ = g16.beam(s)
         assert len(ys) == 20 and all(np.isfinite(sc)) and len(ys[0]) > 3
+
+
+def test_sharded_group_matches_oracle():
+    """Two engines on one GPU, each on its own CUDA stream and host thread, deferred decoding + encoder overlap:
+    every stream's final n-best equals the oracle's (fp32 mode)."""
+    from oracle.speech2text import OracleSpeech2Text
+    from speechcatcher_b200.sharded_group import ShardedStreamGroup
+    from speechcatcher_b200.synthetic import synth_audio
+    md = model_dir("m_d2")
+    S, n = 4, 4 * 16000 + 777
+    audio = np.stack([synth_audio(80 + s, n) for s in range(S)])
+    sg = ShardedStreamGroup(md, S, 2, device="cuda:0", beam_size=5, max_seconds=7)
+    sg.set_option("lazy_threshold", 2)
+    ids = np.arange(2, dtype=np.int32)
+
+    def work(i, g, lo, hi):
+        g.reset()
+        for c in range(0, n, 8192):
+            fin = c + 8192 >= n
+            g.push(list(ids), [audio[s, c:c + 8192] for s in range(lo, hi)], [fin] * (hi - lo))
+
+    sg.run_pass(work)
+    sg.synchronize()
+    for s in range(S):
+        orc = OracleSpeech2Text(md, beam_size=5)
+        for c in range(0, n, 8192):
+            fin = c + 8192 >= n
+            want = orc(audio[s, c:c + 8192], is_final=fin, finalize_all=fin)
+        ys, sc, xp, _ = sg.beam(s)
+        assert ys == [list(h.yseq) for h in orc.hyps], f"stream {s}"
+        assert xp == [list(h.xpos) for h in orc.hyps]
+        assert [r[2] for r in sg.results(s, True, True)] == [r[2] for r in want]
+    sg.close()
