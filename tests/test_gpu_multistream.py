@@ -163,3 +163,50 @@ def test_sharded_group_matches_oracle():
         assert xp == [list(h.xpos) for h in orc.hyps]
         assert [r[2] for r in sg.results(s, True, True)] == [r[2] for r in want]
     sg.close()
+
+
+def test_odd_chunk_sizes_against_oracle():
+    """Chunk sizes that exercise the buffering corners: tiny chunks (frontend emits 5-8 frames, the encoder buffers
+    for many calls), chunks that are not multiples of the hop, and chunks larger than the default."""
+    _run("m_d2", 5, [3 * 16000, 3 * 16000 + 1234, 4 * 16000], {0: 1600, 1: 3000, 2: 12000})
+
+
+def test_batch_invariance_large_group():
+    """Size-independent property at a scale the CPU oracle cannot cover: a stream decoded inside a 24-stream group
+    (deferred decoding, two shards, ragged lengths) gives exactly the beam it gives when decoded alone."""
+    from speechcatcher_b200 import StreamGroup
+    from speechcatcher_b200.sharded_group import ShardedStreamGroup
+    from speechcatcher_b200.synthetic import synth_audio
+    md = model_dir("xl_d4")
+    S = 24
+    lens = [int((8 + (s % 5)) * 16000 + 137 * s) for s in range(S)]
+    audio = [synth_audio(200 + s, n) for s, n in enumerate(lens)]
+    sg = ShardedStreamGroup(md, S, 2, device="cuda:0", beam_size=10, max_seconds=15)
+    sg.set_option("lazy_threshold", 10)
+
+    def work(i, g, lo, hi):
+        g.reset()
+        pos = 0
+        live = list(range(lo, hi))
+        while live:
+            ids, chunks, fins = [], [], []
+            for s in list(live):
+                a = audio[s][pos: pos + 8192]
+                fin = pos + 8192 >= lens[s]
+                ids.append(s - lo); chunks.append(a); fins.append(fin)
+                if fin:
+                    live.remove(s)
+            g.push(ids, chunks, fins)
+            pos += 8192
+
+    sg.run_pass(work)
+    sg.synchronize()
+    solo = StreamGroup(md, n_streams=1, beam_size=10, device="cuda:0", max_seconds=15)
+    for s in (0, 5, 11, 12, 17, 23):
+        solo.reset()
+        for pos in range(0, lens[s], 8192):
+            solo.push([0], [audio[s][pos: pos + 8192]], [pos + 8192 >= lens[s]])
+        a, b = sg.beam(s), solo.beam(0)
+        assert a[0] == b[0] and a[2] == b[2] and a[3] == b[3], f"stream {s}"
+        np.testing.assert_array_equal(np.asarray(a[1]), np.asarray(b[1]))     # fp64 scores bit-identical
+    sg.close()
