@@ -774,16 +774,45 @@ __device__ __forceinline__ void ctc_forward_column(const float* __restrict__ x, 
   // online logsumexp over {r[start-1, n]} U {phi[t-1] + x[t, c]}
   float mx = rn, sum = 1.f;
   float p_n = rprev[2 * (start - 1)], p_b = rprev[2 * (start - 1) + 1];
-  for (int t = start; t < T; ++t) {
-    const float phi = same_as_last ? p_b : lse2(p_n, p_b);
-    const float xc = x[(size_t)t * V + c], xb = x[(size_t)t * V];
-    const float nn = lse2(rn, phi) + xc;
-    const float nb = lse2(rn, rb) + xb;
-    rn = nn; rb = nb;
-    if (r_out) { r_out[2 * t] = rn; r_out[2 * t + 1] = rb; }
-    const float e = phi + xc;
-    if (e > mx) { sum = sum * expf(mx - e) + 1.f; mx = e; } else { sum += expf(e - mx); }
-    p_n = rprev[2 * t]; p_b = rprev[2 * t + 1];
+  // The recursion over t is sequential, but its inputs (x[t, c], x[t, blank], r_prev[t]) are not: they are
+  // fetched eight time steps ahead into registers (two alternating batches) so that the dependent chain only
+  // contains the log-sum-exp arithmetic.  Same operations in the same order as the plain loop (bit-identical).
+  constexpr int CB = 8;
+  struct Batch { float xc[CB], xb[CB]; float2 rp[CB]; };
+  auto load = [&](Batch& b, int t0) {
+#pragma unroll
+    for (int i = 0; i < CB; ++i) {
+      const int t = t0 + i;
+      if (t < T) {
+        b.xc[i] = x[(size_t)t * V + c];
+        b.xb[i] = x[(size_t)t * V];
+        b.rp[i] = *reinterpret_cast<const float2*>(rprev + 2 * t);
+      }
+    }
+  };
+  auto process = [&](const Batch& b, int t0) {
+#pragma unroll
+    for (int i = 0; i < CB; ++i) {
+      const int t = t0 + i;
+      if (t < T) {
+        const float phi = same_as_last ? p_b : lse2(p_n, p_b);
+        const float nn = lse2(rn, phi) + b.xc[i];
+        const float nb = lse2(rn, rb) + b.xb[i];
+        rn = nn; rb = nb;
+        if (r_out) *reinterpret_cast<float2*>(r_out + 2 * t) = make_float2(rn, rb);
+        const float e = phi + b.xc[i];
+        if (e > mx) { sum = sum * expf(mx - e) + 1.f; mx = e; } else { sum += expf(e - mx); }
+        p_n = b.rp[i].x; p_b = b.rp[i].y;
+      }
+    }
+  };
+  Batch A, B;
+  load(A, start);
+  for (int t0 = start; t0 < T; t0 += 2 * CB) {
+    load(B, t0 + CB);
+    process(A, t0);
+    load(A, t0 + 2 * CB);
+    process(B, t0 + CB);
   }
   psi = logf(sum) + mx;
 }
