@@ -96,6 +96,11 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
  * yseq/xpos: [beam][max_len] int32, score: [beam] fp64. */
 int sc_engine_read_beam(void* handle, int32_t stream_id, int32_t max_len, int32_t* n_hyp, int32_t* len,
                         int32_t* process_idx, int32_t* yseq, int32_t* xpos, double* score, void* stream);
+/* Beams of ALL streams in four bulk copies (results of a whole batch): ctl16 [S][16] int32 control words
+ * (0 = current ping-pong buffer, 1 = n_hyp, 2 = len, 3 = process_idx), yseq / xpos [2][S][beam][token_capacity] int32,
+ * score [2][S][beam] fp64.  Host buffers should be pinned.  Synchronises the stream. */
+int sc_engine_read_all(void* handle, int32_t* ctl16, int32_t* yseq, int32_t* xpos, double* score, void* stream);
+int sc_engine_token_capacity(void* handle, int32_t* token_capacity);
 /* Host plan of the last push for stream `stream_id`. */
 int sc_engine_last_plan(void* handle, int32_t stream_id, ScStreamPlan* plan);
 /* Named internal device buffer (tests / debugging): pointer, element count and row pitch. */

@@ -43,6 +43,8 @@ SYMBOLS = {
     "sc_engine_reset": (C.c_int, [_vp, _vp, _i32, _vp]),
     "sc_engine_push": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, C.POINTER(ScPushStats)]),
     "sc_engine_read_beam": (C.c_int, [_vp, _i32, _i32, _pi32, _pi32, _pi32, _vp, _vp, _vp, _vp]),
+    "sc_engine_read_all": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "sc_engine_token_capacity": (C.c_int, [_vp, _pi32]),
     "sc_engine_last_plan": (C.c_int, [_vp, _i32, C.POINTER(ScStreamPlan)]),
     "sc_engine_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_sz)]),
     "sc_engine_set_option": (C.c_int, [_vp, C.c_char_p, _i32]),

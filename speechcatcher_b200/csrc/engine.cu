@@ -840,6 +840,27 @@ int sc_engine_read_beam(void* handle, int32_t s, int32_t max_len, int32_t* n_hyp
   return SC_OK;
 }
 
+int sc_engine_read_all(void* handle, int32_t* ctl16, int32_t* yseq, int32_t* xpos, double* score, void* stream) {
+  Engine* e = (Engine*)handle;
+  if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const SearchBuffers& sb = e->sb;
+  const size_t S = sb.S, B = sb.B, L = sb.Lcap;
+  SCB_CUDA_CHECK(cudaMemcpyAsync(ctl16, sb.ctl, S * sizeof(StreamCtl), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaMemcpyAsync(yseq, sb.yseq, 2 * S * B * L * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaMemcpyAsync(xpos, sb.xpos, 2 * S * B * L * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaMemcpyAsync(score, sb.score, 2 * S * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SCB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SC_OK;
+}
+
+int sc_engine_token_capacity(void* handle, int32_t* lcap) {
+  Engine* e = (Engine*)handle;
+  if (!e || !lcap) { set_last_error("token_capacity: bad argument"); return SC_ERR_ARG; }
+  *lcap = e->cap.Lcap;
+  return SC_OK;
+}
+
 int sc_engine_last_plan(void* handle, int32_t s, ScStreamPlan* plan) {
   Engine* e = (Engine*)handle;
   if (!e || s < 0 || s >= e->cfg.n_streams || !plan) { set_last_error("last_plan: bad argument"); return SC_ERR_ARG; }

@@ -253,6 +253,35 @@ class StreamGroup:
                     "traffic": None, "search_iterations": int(cnt[4]), "active_rows_total": int(cnt[1])})
         return out
 
+    def beams_all(self):
+        """Beams of every stream with four bulk D2H copies into pinned buffers:
+        list over streams of (yseq per hyp, scores, xpos per hyp, process_idx)."""
+        S, B = self.n_streams, self.beam_size
+        if not hasattr(self, "_bulk"):
+            lcap = C.c_int32()
+            _lib.check(self.lib.sc_engine_token_capacity(self.handle, C.byref(lcap)), "token_capacity")
+            L = lcap.value
+            self._bulk = (L, torch.empty(S, 16, dtype=torch.int32).pin_memory(),
+                          torch.empty(2, S, B, L, dtype=torch.int32).pin_memory(),
+                          torch.empty(2, S, B, L, dtype=torch.int32).pin_memory(),
+                          torch.empty(2, S, B, dtype=torch.float64).pin_memory())
+        L, ctl, ys, xp, sc = self._bulk
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sc_engine_read_all(self.handle, C.c_void_p(ctl.data_ptr()), C.c_void_p(ys.data_ptr()),
+                                                   C.c_void_p(xp.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                                   C.c_void_p(self.stream.cuda_stream)), "read_all")
+        ctl_n, ys_n, xp_n, sc_n = ctl.numpy(), ys.numpy(), xp.numpy(), sc.numpy()
+        out = []
+        for s in range(S):
+            cur, n, ln, pidx = (int(v) for v in ctl_n[s, :4])
+            out.append(([ys_n[cur, s, h, :ln].tolist() for h in range(n)], sc_n[cur, s, :n].tolist(),
+                        [xp_n[cur, s, h, :ln].tolist() for h in range(n)], pidx))
+        return out
+
+    def results_all(self, is_final: bool, finalize_all: bool, token_list=None):
+        """`results` for every stream from one bulk read-back."""
+        return [self._assemble(b, is_final, finalize_all, token_list) for b in self.beams_all()]
+
     def last_plan(self, stream: int) -> ScStreamPlan:
         p = ScStreamPlan()
         _lib.check(self.lib.sc_engine_last_plan(self.handle, stream, C.byref(p)), "last_plan")
@@ -269,7 +298,11 @@ class StreamGroup:
 
     def results(self, stream: int, is_final: bool, finalize_all: bool, token_list=None):
         """Output assembly of Speech2TextStreaming.__call__ (speech2text_streaming.py:466-539)."""
-        yseqs, scores, xposs, _ = self.beam(stream)
+        return self._assemble(self.beam(stream), is_final, finalize_all, token_list)
+
+    @staticmethod
+    def _assemble(beam, is_final: bool, finalize_all: bool, token_list=None):
+        yseqs, scores, xposs, _ = beam
         out = []
         for y, sc, xp in zip(yseqs, scores, xposs):
             if (not is_final or not finalize_all) and y[-1] != EOS_FILTER_ID:

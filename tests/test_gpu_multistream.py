@@ -111,6 +111,9 @@ def test_deferred_decoding_same_final_results():
         assert xp == [list(h.xpos) for h in orc.hyps]
         np.testing.assert_allclose(sc, [h.score for h in orc.hyps], atol=2e-3, rtol=0)
         assert [r[2] for r in grp.results(s, True, True)] == [r[2] for r in want]
+    bulk = grp.results_all(True, True)                 # one bulk read-back == per-stream reads
+    for s in range(S):
+        assert bulk[s] == grp.results(s, True, True)
     assert total_steps > 0
 
 
