@@ -124,6 +124,8 @@ def main():
                     help="bfloat16: tensor-core GEMMs/attention with fp32 accumulation (throughput mode, north_star); "
                          "float32: CUDA-core parity mode (n-best identical to the reference)")
     ap.add_argument("--no-fp32", action="store_true", help="skip the extra fp32 parity-mode measurement")
+    ap.add_argument("--no-extra-rooflines", action="store_true",
+                    help="skip the per-kernel roofline passes on a dedicated single 256-stream group")
     ap.add_argument("--cpu-sample-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -330,6 +332,33 @@ def main():
                "h2d_bytes_per_step": int(S * n_samples * 4), "d2h_bytes_per_step": int(d2h),
                "p50_chunk_ms": float(statistics.median(lat_ms)), "p95_chunk_ms": float(np.percentile(lat_ms, 95))}
 
+    # per-kernel rooflines without cross-shard interference: one dedicated group holding all S streams, one full pass
+    # per kernel with CUDA-event pairs around every launch of that kernel (same workload, same deferred scheduling)
+    extra_roof = None
+    if not args.no_extra_rooflines and rank == 0:
+        g1 = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype=args.dtype, use_bbd=False,
+                         max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
+        g1.set_option("lazy_threshold", max(1, S - S // 32))
+        ids1 = np.arange(S, dtype=np.int32)
+        lens1 = [np.full(S, int(l[0]), np.int32) for l in lens_all]
+        fin1 = [np.full(S, int(f[0]), np.int32) for f in fin_all]
+
+        def pass1():
+            g1.reset()
+            for c in range(n_chunks):
+                g1.push_device(ids1, resident, lens1[c], fin1[c], col_offset=c * CHUNK)
+
+        pass1()
+        extra_roof = []
+        for kname in ("ctc_prefix", "dec_cross_attn", "dec_self_attn", "enc_ffn1", "enc_ffn2"):
+            tag = g1.profile_begin(kname)
+            pass1()
+            torch.cuda.synchronize()
+            extra_roof.append(g1.profile_end(tag))
+        g1.close()
+        del g1
+        torch.cuda.empty_cache()
+
     # the fp32 parity mode (CUDA-core GEMMs, results identical to the reference) measured on the same workload
     fp32_mode = None
     if args.dtype == "bfloat16" and not args.no_fp32:
@@ -382,7 +411,7 @@ def main():
                            "decode_steps_per_pass": timed_stats["steps"] // max(1, args.steps),
                            "encoder_blocks_per_pass": timed_stats["blocks"] // max(1, args.steps)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": timed_stats["launches"],
-                "roofline": roof, "cpu_baseline": cpu_base, "fp32_mode": fp32_mode,
+                "roofline": roof, "roofline_single_group": extra_roof, "cpu_baseline": cpu_base, "fp32_mode": fp32_mode,
                 "kernel_breakdown_sampled": breakdown}
         print(json.dumps(line))
     if world > 1:

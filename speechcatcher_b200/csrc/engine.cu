@@ -240,23 +240,6 @@ static int linear(Engine& e, const Lin& l, cudaStream_t st) {
 
 #define TRY(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
 
-// LayerNorm(X) followed by a Linear.  bf16 mode with ln_prologue: one kernel (the GEMM normalises its own A tile);
-// otherwise a LayerNorm kernel (fp32 or bf16 output into l.A / l.A16) followed by the GEMM.
-static int ln_linear(Engine& e, const float* X, int ldx, const float* ln_w, const float* ln_b, int rows_max,
-                     const Lin& l, cudaStream_t st) {
-  const bool tc = e.cfg.precision == 1;
-  if (tc && e.ln_prologue && !e.fuse_ln) {
-    e.launches++;
-    return launch_gemm_bf16_lnA(X, ldx, ln_w, ln_b, l.W16, l.bias, l.C, l.ldc, l.C16, l.ldc, l.M, l.N, l.relu, l.n_rows_dev, st);
-  }
-  if (!(tc && e.fuse_ln)) {
-    e.launches++;
-    if (tc) TRY(launch_layernorm_bf16(X, ldx, ln_w, ln_b, const_cast<__nv_bfloat16*>(l.A16), l.lda, rows_max, l.K, l.n_rows_dev, st));
-    else TRY(launch_layernorm(X, ldx, ln_w, ln_b, const_cast<float*>(l.A), l.lda, rows_max, l.K, l.n_rows_dev, st));
-  }
-  return linear(e, l, st);
-}
-
 enum ProfTag { T_NONE = 0, T_CTC_PREFIX = 1, T_DEC_SELF_ATTN = 2, T_DEC_CROSS_ATTN = 3, T_DEC_FFN1 = 4, T_ENC_FFN1 = 5,
                T_PREBEAM = 6, T_ENC_ATTN = 7, T_CONV2 = 8, T_DEC_FFN2 = 9, T_ENC_FFN2 = 10, T_CTC_UPDATE = 11,
                T_FRONTEND = 12, T_CONV1 = 13, T_SUBOUT = 14, T_BLOCK_ASM = 15, T_ENC_LN = 16, T_ENC_QKV = 17, T_ENC_O = 18,
@@ -285,6 +268,26 @@ static inline void prof_mark(Engine& e, int tag, cudaStream_t st, bool begin) {
 #define PD(tag, expr) PROFX(tag, true, expr)
 #define PE(tag, expr) PROFX(tag, false, expr)
 
+// LayerNorm(X) followed by a Linear.  bf16 mode with ln_prologue: one kernel (the GEMM normalises its own A tile);
+// otherwise a LayerNorm kernel (fp32 or bf16 output into l.A / l.A16) followed by the GEMM, each under its own tag.
+static int ln_linear(Engine& e, int ln_tag, int gemm_tag, bool dec, const float* X, int ldx, const float* ln_w,
+                     const float* ln_b, int rows_max, const Lin& l, cudaStream_t st) {
+  const bool tc = e.cfg.precision == 1;
+  if (tc && e.ln_prologue && !e.fuse_ln) {
+    e.launches++;
+    PROFX(gemm_tag, dec, launch_gemm_bf16_lnA(X, ldx, ln_w, ln_b, l.W16, l.bias, l.C, l.ldc, l.C16, l.ldc, l.M, l.N, l.relu,
+                                             l.n_rows_dev, st));
+    return 0;
+  }
+  if (!(tc && e.fuse_ln)) {
+    e.launches++;
+    if (tc) PROFX(ln_tag, dec, launch_layernorm_bf16(X, ldx, ln_w, ln_b, const_cast<__nv_bfloat16*>(l.A16), l.lda, rows_max, l.K, l.n_rows_dev, st));
+    else PROFX(ln_tag, dec, launch_layernorm(X, ldx, ln_w, ln_b, const_cast<float*>(l.A), l.lda, rows_max, l.K, l.n_rows_dev, st));
+  }
+  PROFX(gemm_tag, dec, linear(e, l, st));
+  return 0;
+}
+
 // ---------------------------------------------------------------- encoder layers over all blocks of the push
 static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, rows = n_blk * kSlots;
@@ -297,10 +300,10 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
     const EncLayerW& w = e.enc[l];
     const EncLayerW* nx = l + 1 < c.enc_layers ? &e.enc[l + 1] : nullptr;
     if (e.mma_enc) {
-      PE(T_ENC_QKV, ln_linear(e, e.X, D, w.ln1w, w.ln1b, rows, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, nullptr, 3 * D, e.QKV16, rows, 3 * D, D, 0, nullptr}, st));
+      TRY(ln_linear(e, T_ENC_LN, T_ENC_QKV, false, e.X, D, w.ln1w, w.ln1b, rows, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, nullptr, 3 * D, e.QKV16, rows, 3 * D, D, 0, nullptr}, st));
       PE(T_ENC_ATTN, launch_enc_attention_mma(e.QKV16, nullptr, e.Att16, e.d_blk, n_blk, c.enc_heads, D, st));
     } else {
-      PE(T_ENC_QKV, ln_linear(e, e.X, D, w.ln1w, w.ln1b, rows, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
+      TRY(ln_linear(e, T_ENC_LN, T_ENC_QKV, false, e.X, D, w.ln1w, w.ln1b, rows, Lin{e.Nrm, D, e.Nrm16, w.qkvw, w.qkvw16, w.qkvb, nullptr, 0, e.QKV, 3 * D, nullptr, rows, 3 * D, D, 0, nullptr}, st));
       PE(T_ENC_ATTN, launch_enc_attention(e.QKV, e.Att, tc ? e.Att16 : nullptr, e.d_blk, n_blk, c.enc_heads, D, st));
     }
     {
@@ -309,7 +312,7 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
       PE(T_ENC_O, linear(e, o, st));
     }
     if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
-    PE(T_ENC_FFN1, ln_linear(e, e.X, D, w.ln2w, w.ln2b, rows, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
+    TRY(ln_linear(e, T_ENC_LN, T_ENC_FFN1, false, e.X, D, w.ln2w, w.ln2b, rows, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
     {
       Lin f2{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr};
       if (fl && nx) f2 = with_ln(f2, nx->ln1w, nx->ln1b, e.Nrm16);
@@ -337,7 +340,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
     // bf16 mode: norm1 comes fused from dec_embed / the previous layer's FFN2, norm2 from self-O, norm3 from cross-O
-    PD(T_DEC_QKV, ln_linear(e, e.dx, D, w.ln1w, w.ln1b, R, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
+    TRY(ln_linear(e, T_DEC_LN, T_DEC_QKV, true, e.dx, D, w.ln1w, w.ln1b, R, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_SELF_ATTN, launch_dec_attention_mma(sb, 0, l, e.dqkv, 3 * D, e.dattn, e.dattn16, st));
     else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
     {
@@ -345,7 +348,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
       if (fl) o = with_ln(o, w.ln2w, w.ln2b, e.dn16);
       PD(T_DEC_SO, linear(e, o, st));
     }
-    PD(T_DEC_CQ, ln_linear(e, e.dx, D, w.ln2w, w.ln2b, R, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
+    TRY(ln_linear(e, T_DEC_LN, T_DEC_CQ, true, e.dx, D, w.ln2w, w.ln2b, R, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_CROSS_ATTN, launch_dec_attention_mma(sb, 1, l, e.dq, D, e.dattn, e.dattn16, st));
     else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, e.dattn, tc ? e.dattn16 : nullptr, st));
     {
@@ -353,7 +356,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
       if (fl) o = with_ln(o, w.ln3w, w.ln3b, e.dn16);
       PD(T_DEC_CO, linear(e, o, st));
     }
-    PD(T_DEC_FFN1, ln_linear(e, e.dx, D, w.ln3w, w.ln3b, R, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
+    TRY(ln_linear(e, T_DEC_LN, T_DEC_FFN1, true, e.dx, D, w.ln3w, w.ln3b, R, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
     {
       Lin f2{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr};
       if (fl) f2 = (l + 1 < c.dec_layers) ? with_ln(f2, e.dec[l + 1].ln1w, e.dec[l + 1].ln1b, e.dn16) : with_ln(f2, e.daw, e.dab, e.dn16);
@@ -361,7 +364,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
     }
     e.launches += fl ? 2 : 5;
   }
-  PD(T_DEC_OUT, ln_linear(e, e.dx, D, e.daw, e.dab, R, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
+  TRY(ln_linear(e, T_DEC_LN, T_DEC_OUT, true, e.dx, D, e.daw, e.dab, R, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
   PD(T_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
   PD(T_CTC_PREFIX, launch_ctc_prefix(sb, st));
   PD(T_COMBINE, launch_combine_topk(sb, e.dlogp, st));
