@@ -26,13 +26,16 @@ class Speech2TextStreaming:
                  device: str = "cuda", dtype: str = "float32", use_bbd: bool = False,
                  group: Optional[StreamGroup] = None, stream_id: int = 0, max_chunk: int = 8192,
                  max_seconds: float = 61.0):
+        self._owns_group = group is None
         if group is None:
             if device == "cuda":
                 device = "cuda:0"
-            group = StreamGroup(model_dir, n_streams=1, beam_size=beam_size, ctc_weight=ctc_weight, device=device,
-                                dtype=dtype, use_bbd=use_bbd, max_chunk=max_chunk, max_seconds=max_seconds)
+            self._group_args = dict(model_dir=model_dir, n_streams=1, beam_size=beam_size, ctc_weight=ctc_weight,
+                                    device=device, dtype=dtype, use_bbd=use_bbd, max_seconds=max_seconds)
+            group = StreamGroup(max_chunk=max_chunk, **self._group_args)
             stream_id = 0
         self.group, self.stream_id = group, stream_id
+        self._calls_since_reset = 0
         self.model_dir = Path(group.model_dir)
         self.beam_size, self.ctc_weight, self.use_bbd = group.beam_size, group.ctc_weight, group.use_bbd
         self.device, self.dtype = str(group.device), dtype
@@ -57,6 +60,7 @@ class Speech2TextStreaming:
         self.beam_state = None
         self.processed_frames = 0
         self.frontend_states = None
+        self._calls_since_reset = 0
         self.group.reset([self.stream_id])
 
     def __call__(self, speech: Union[np.ndarray, torch.Tensor], is_final: bool = False, finalize_all: bool = False,
@@ -66,6 +70,17 @@ class Speech2TextStreaming:
         speech = np.asarray(speech, np.float32)
         if speech.ndim != 1:
             raise NotImplementedError("the B200 path takes raw 1-D waveforms (pre-computed features are not supported)")
+        if len(speech) > self.group.max_chunk:
+            # the engine's buffers are sized for a maximum chunk; a facade that owns its engine re-creates it with a
+            # larger capacity, which is only possible while the stream holds no state (right after reset)
+            if not self._owns_group or self._calls_since_reset > 0:
+                raise ValueError(f"chunk of {len(speech)} samples exceeds the engine capacity max_chunk="
+                                 f"{self.group.max_chunk}; construct with a larger max_chunk")
+            self.group.close()
+            need = (len(speech) + 159999) // 160000 * 160000
+            secs = max(self._group_args["max_seconds"], need / 16000.0 + 2.0)
+            self.group = StreamGroup(max_chunk=need, **{**self._group_args, "max_seconds": secs})
+        self._calls_since_reset += 1
         self.group.push([self.stream_id], [speech], [is_final])
         plan = self.group.last_plan(self.stream_id)
         if not plan.called:
