@@ -302,24 +302,27 @@ class StreamGroup:
 
     @staticmethod
     def _assemble(beam, is_final: bool, finalize_all: bool, token_list=None):
+        """Output assembly of Speech2TextStreaming.__call__ (speech2text_streaming.py:466-539), vectorised with numpy
+        (a 60 s hypothesis holds ~600 tokens; per-token Python loops would dominate the end-to-end time)."""
         yseqs, scores, xposs, _ = beam
         out = []
+        drop = np.array([0, 1, EOS_FILTER_ID])
         for y, sc, xp in zip(yseqs, scores, xposs):
             if (not is_final or not finalize_all) and y[-1] != EOS_FILTER_ID:
                 continue
             if is_final:
-                ids, pos = y[1:], xp[1:]
-                if ids and ids[-1] == EOS_FILTER_ID:
+                ids, pos = np.asarray(y[1:], dtype=np.int64), np.asarray(xp[1:], dtype=np.int64)
+                if ids.size and ids[-1] == EOS_FILTER_ID:
                     ids, pos = ids[:-1], pos[:-1]
             else:
-                ids, pos = [], []            # output_index is always 0 in the reference
-            keep = [(t, p) for t, p in zip(ids, pos) if t not in (0, 1, EOS_FILTER_ID)]
-            ids_f = [t for t, _ in keep]
+                ids = pos = np.zeros(0, np.int64)  # output_index is always 0 in the reference (SURVEY.md Q8)
+            keep = ~np.isin(ids, drop)
+            ids_f, pos_f = ids[keep].tolist(), pos[keep].tolist()
             if token_list is not None:
                 toks = [token_list[t] for t in ids_f]
-                text = "".join(toks).replace("▁", " ").strip()
+                text = "".join(toks).replace("\u2581", " ").strip()
             else:
-                toks = [str(t) for t in ids_f]
+                toks = ids[keep].astype(str).tolist()
                 text = " ".join(toks)
-            out.append((text, toks, ids_f, [p for _, p in keep], dict(yseq=y, score=sc, xpos=xp)))
+            out.append((text, toks, ids_f, pos_f, dict(yseq=y, score=sc, xpos=xp)))
         return out
