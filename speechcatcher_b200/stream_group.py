@@ -253,9 +253,8 @@ class StreamGroup:
                     "traffic": None, "search_iterations": int(cnt[4]), "active_rows_total": int(cnt[1])})
         return out
 
-    def beams_all(self):
-        """Beams of every stream with four bulk D2H copies into pinned buffers:
-        list over streams of (yseq per hyp, scores, xpos per hyp, process_idx)."""
+    def _read_all(self):
+        """Bulk D2H of control words, yseq, xpos and scores of every stream into pinned buffers (numpy views)."""
         S, B = self.n_streams, self.beam_size
         if not hasattr(self, "_bulk"):
             lcap = C.c_int32()
@@ -270,17 +269,28 @@ class StreamGroup:
             _lib.check(self.lib.sc_engine_read_all(self.handle, C.c_void_p(ctl.data_ptr()), C.c_void_p(ys.data_ptr()),
                                                    C.c_void_p(xp.data_ptr()), C.c_void_p(sc.data_ptr()),
                                                    C.c_void_p(self.stream.cuda_stream)), "read_all")
-        ctl_n, ys_n, xp_n, sc_n = ctl.numpy(), ys.numpy(), xp.numpy(), sc.numpy()
+        return ctl.numpy(), ys.numpy(), xp.numpy(), sc.numpy()
+
+    def beams_all(self):
+        """Beams of every stream with four bulk D2H copies into pinned buffers:
+        list over streams of (yseq per hyp, scores, xpos per hyp, process_idx)."""
+        ctl_n, ys_n, xp_n, sc_n = self._read_all()
         out = []
-        for s in range(S):
+        for s in range(self.n_streams):
             cur, n, ln, pidx = (int(v) for v in ctl_n[s, :4])
             out.append(([ys_n[cur, s, h, :ln].tolist() for h in range(n)], sc_n[cur, s, :n].tolist(),
                         [xp_n[cur, s, h, :ln].tolist() for h in range(n)], pidx))
         return out
 
     def results_all(self, is_final: bool, finalize_all: bool, token_list=None):
-        """`results` for every stream from one bulk read-back."""
-        return [self._assemble(b, is_final, finalize_all, token_list) for b in self.beams_all()]
+        """`results` for every stream from one bulk read-back (hypotheses stay numpy rows until the final lists)."""
+        ctl_n, ys_n, xp_n, sc_n = self._read_all()
+        out = []
+        for s in range(self.n_streams):
+            cur, n, ln, pidx = (int(v) for v in ctl_n[s, :4])
+            out.append(self._assemble((ys_n[cur, s, :n, :ln], sc_n[cur, s, :n].tolist(), xp_n[cur, s, :n, :ln], pidx),
+                                      is_final, finalize_all, token_list))
+        return out
 
     def last_plan(self, stream: int) -> ScStreamPlan:
         p = ScStreamPlan()
@@ -300,29 +310,43 @@ class StreamGroup:
         """Output assembly of Speech2TextStreaming.__call__ (speech2text_streaming.py:466-539)."""
         return self._assemble(self.beam(stream), is_final, finalize_all, token_list)
 
-    @staticmethod
-    def _assemble(beam, is_final: bool, finalize_all: bool, token_list=None):
+    _TOK_TABLES = {}
+
+    @classmethod
+    def _tok_table(cls, token_list):
+        """Token strings as a numpy object array so a hypothesis is turned into strings with one fancy index."""
+        key = id(token_list) if token_list is not None else None
+        hit = cls._TOK_TABLES.get(key)
+        if hit is None or hit[0] is not token_list:
+            names = token_list if token_list is not None else [str(i) for i in range(65536)]
+            arr = np.empty(len(names), dtype=object)
+            arr[:] = list(names)
+            hit = cls._TOK_TABLES[key] = (token_list, arr)
+        return hit[1]
+
+    @classmethod
+    def _assemble(cls, beam, is_final: bool, finalize_all: bool, token_list=None):
         """Output assembly of Speech2TextStreaming.__call__ (speech2text_streaming.py:466-539), vectorised with numpy
         (a 60 s hypothesis holds ~600 tokens; per-token Python loops would dominate the end-to-end time)."""
         yseqs, scores, xposs, _ = beam
         out = []
-        drop = np.array([0, 1, EOS_FILTER_ID])
+        table = cls._tok_table(token_list)
         for y, sc, xp in zip(yseqs, scores, xposs):
+            y, xp = np.array(y, dtype=np.int32), np.array(xp, dtype=np.int32)     # owned copies (hyp.yseq / hyp.xpos)
             if (not is_final or not finalize_all) and y[-1] != EOS_FILTER_ID:
                 continue
             if is_final:
-                ids, pos = np.asarray(y[1:], dtype=np.int64), np.asarray(xp[1:], dtype=np.int64)
+                ids, pos = y[1:], xp[1:]
                 if ids.size and ids[-1] == EOS_FILTER_ID:
                     ids, pos = ids[:-1], pos[:-1]
+                keep = (ids > 1) & (ids != EOS_FILTER_ID)     # drops blank 0, sos/eos 1 and the hard-coded 1023
+                ids, pos = ids[keep], pos[keep]
             else:
-                ids = pos = np.zeros(0, np.int64)  # output_index is always 0 in the reference (SURVEY.md Q8)
-            keep = ~np.isin(ids, drop)
-            ids_f, pos_f = ids[keep].tolist(), pos[keep].tolist()
+                ids = pos = np.zeros(0, np.int32)  # output_index is always 0 in the reference (SURVEY.md Q8)
+            toks = table[ids].tolist()
             if token_list is not None:
-                toks = [token_list[t] for t in ids_f]
                 text = "".join(toks).replace("\u2581", " ").strip()
             else:
-                toks = ids[keep].astype(str).tolist()
                 text = " ".join(toks)
-            out.append((text, toks, ids_f, pos_f, dict(yseq=y, score=sc, xpos=xp)))
+            out.append((text, toks, ids.tolist(), pos.tolist(), dict(yseq=y, score=sc, xpos=xp)))
         return out
