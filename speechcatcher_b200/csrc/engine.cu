@@ -22,6 +22,9 @@ int launch_dec_attention_mma(const SearchBuffers& sb, int mode, int layer, const
                              __nv_bfloat16* out16, cudaStream_t st);
 int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                              int n_head, int d_model, cudaStream_t st);
+int launch_ffn_fused_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W1, const float* b1,
+                          const __nv_bfloat16* W2, const float* b2, float* C, int ldc, int accumulate, int M, int F,
+                          cudaStream_t st, long long* dbg = nullptr);
 int launch_gemm_bf16_lnA(const float* X, int ldx, const float* lna_w, const float* lna_b, const __nv_bfloat16* W,
                          const float* bias, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int relu,
                          const int* n_rows_dev, cudaStream_t st);
@@ -105,6 +108,10 @@ struct Engine {
   bool fuse_ln = false;
   // bf16 mode: compute every LayerNorm inside the GEMM that consumes it (LayerNorm-prologue GEMM, K = 256)
   bool ln_prologue = false;
+  // bf16 mode: encoder FFN1 -> ReLU -> FFN2 as one kernel with the hidden activation kept on the SM
+  // (kernels_ffn_fused.cu); used when a launch has at least `fused_ffn_min_rows` rows
+  bool fused_ffn = false;
+  int fused_ffn_min_rows = 1024;
   // deferred decoding: a push stops iterating once fewer than `lazy_threshold` streams are active and leaves
   // the stragglers' blocks queued on the device; they continue during later pushes (0 = strict, drain every push)
   int lazy_threshold = 0;
@@ -312,11 +319,19 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
       PE(T_ENC_O, linear(e, o, st));
     }
     if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
-    TRY(ln_linear(e, T_ENC_LN, T_ENC_FFN1, false, e.X, D, w.ln2w, w.ln2b, rows, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
-    {
-      Lin f2{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr};
-      if (fl && nx) f2 = with_ln(f2, nx->ln1w, nx->ln1b, e.Nrm16);
-      PE(T_ENC_FFN2, linear(e, f2, st));
+    if (tc && e.fused_ffn && !fl && !e.ln_prologue && rows >= e.fused_ffn_min_rows) {
+      // LayerNorm -> one fused FFN kernel (hidden activation stays in TMEM / shared memory); timed under the FFN2 tag
+      e.launches += 2;
+      PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
+      if (e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
+      PE(T_ENC_FFN2, launch_ffn_fused_bf16(e.Nrm16, D, w.f1w16, w.f1b, w.f2w16, w.f2b, e.X, D, 1, rows, F, st));
+    } else {
+      TRY(ln_linear(e, T_ENC_LN, T_ENC_FFN1, false, e.X, D, w.ln2w, w.ln2b, rows, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
+      {
+        Lin f2{e.FF, F, tc ? e.FF16 : nullptr, w.f2w, w.f2w16, w.f2b, e.X, D, e.X, D, nullptr, rows, D, F, 0, nullptr};
+        if (fl && nx) f2 = with_ln(f2, nx->ln1w, nx->ln1b, e.Nrm16);
+        PE(T_ENC_FFN2, linear(e, f2, st));
+      }
     }
     PE(T_ENC_HANDOVER, launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, (fl && nx) ? nx->ln1w : nullptr,
                                            (fl && nx) ? nx->ln1b : nullptr, e.Nrm16, st));
@@ -440,6 +455,8 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     const char* lp = getenv("SCB_LN_PROLOGUE");
     // measured slower than a separate LayerNorm kernel (every N-tile CTA re-normalises its 128 rows): opt-in only
     e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && lp && strcmp(lp, "1") == 0;
+    const char* ff = getenv("SCB_FUSED_FFN");   // "0" keeps the two-GEMM encoder FFN (A/B tests)
+    e->fused_ffn = cfg->precision == 1 && cfg->d_model == 256 && cfg->ffn % 128 == 0 && !(ff && strcmp(ff, "0") == 0);
     const char* pdl = getenv("SCB_PDL");     // programmatic dependent launch of the decode-step kernel chain (default on)
     g_use_pdl = !(pdl && strcmp(pdl, "0") == 0);
   }
@@ -887,6 +904,11 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (strcmp(name, "overlap") == 0) { e->overlap = value != 0; return SC_OK; }
   if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
   if (strcmp(name, "ln_prologue") == 0) { e->ln_prologue = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
+  if (strcmp(name, "fused_ffn") == 0) {
+    e->fused_ffn = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256 && e->cfg.ffn % 128 == 0;
+    return SC_OK;
+  }
+  if (strcmp(name, "fused_ffn_min_rows") == 0) { e->fused_ffn_min_rows = value; return SC_OK; }
   if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = value != 0 && e->cfg.precision == 1; return SC_OK; }
   if (strcmp(name, "mma_attention") == 0) {
     e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16;
@@ -974,6 +996,18 @@ int sc_linear_bf16_ln(const void* x, const void* w, const float* bias, const flo
                       const float* ln_b, void* ln_out_bf16, int32_t m, int32_t k, void* stream) {
   return launch_gemm_bf16_ln((const __nv_bfloat16*)x, k, (const __nv_bfloat16*)w, bias, residual, 256, y, 256, nullptr, 0, nullptr,
                              m, 256, k, 0, nullptr, ln_w, ln_b, (__nv_bfloat16*)ln_out_bf16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+
+int sc_ffn_bf16(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, float* y, int32_t accumulate,
+                int32_t m, int32_t f, void* stream) {
+  return launch_ffn_fused_bf16((const __nv_bfloat16*)x, 256, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2, b2, y, 256,
+                               accumulate, m, f, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+
+int sc_ffn_bf16_timeline(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, float* y,
+                         int32_t accumulate, int32_t m, int32_t f, int64_t* stamps, void* stream) {
+  return launch_ffn_fused_bf16((const __nv_bfloat16*)x, 256, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2, b2, y, 256,
+                               accumulate, m, f, (cudaStream_t)stream, (long long*)stamps) ? SC_ERR_CUDA : SC_OK;
 }
 
 int sc_linear_bf16_lnA(const float* x_f32, const float* ln_w, const float* ln_b, const void* w, const float* bias, float* y,

@@ -17,79 +17,9 @@
 #include <mutex>
 #include <tuple>
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace scb {
-
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int TC_THREADS = 192;
-constexpr int UMMA_K = 16;
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i receives row (lane base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
-//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major),
-//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between row groups), [46,48) version = 1,
-//   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 struct TcParams {
   const float* bias; const float* R; int ldr; float* C; int ldc; __nv_bfloat16* Cb; int ldcb;
@@ -148,10 +78,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
   } else
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    // The whole warp runs the loop and waits on the barriers (uniform control flow); one elected lane issues.
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one_sync()) {
         if (LNA) {
           mbar_expect_tx(&full_bar[s], B_BYTES);
         } else {
@@ -160,18 +91,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
         }
         tma_load_2d(&map_b, &full_bar[s], sB + s * B_BYTES, kb * TC_BK, n0);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      if (LNA) mbar_wait(a_ready, 0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    // Same shape: warp-uniform loop, elected lane issues.  Under `if (lane == 0)` ptxas cannot prove the descriptors
+    // uniform and wraps every UTCHMMA in a lane-serialising R2UR loop (~100 cycles per MMA, measured).
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (LNA) mbar_wait(a_ready, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint64_t da = make_smem_desc(smem_u32(sA + s * A_BYTES));
         const uint64_t db = make_smem_desc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
@@ -180,10 +113,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
           umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
         }
         umma_commit(&empty_bar[s]);           // frees the smem stage once the MMAs have read it
+        if (kb == nkb - 1) umma_commit(tmem_full);   // accumulator complete
       }
-      umma_commit(tmem_full);                 // accumulator complete
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
@@ -239,8 +172,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready)) : "memory");
     }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int m = m0 + q * 32 + lane;
     const bool row_ok = m < M;
     float* crow = nullptr;
@@ -252,39 +183,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tc_kernel(const __gri
       if (p.R) rrow = p.R + (size_t)m * p.ldr;
     }
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (row_ok) {
-        const int n = n0 + c0;
-        float o[32];
+    // 16 columns per step.  With one epilogue warp per scheduler every load latency is exposed, so the loads are
+    // hoisted: the residual of the first step is requested BEFORE waiting for the accumulator (it overlaps the
+    // main loop), each later step's residual one step ahead, and the bias vector ahead of the TMEM read.
+    // (R may alias C: a step only ever stores columns whose residual it has already consumed.)
+    float4 rn[4];
+    if (rrow) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (p.bias) x += __ldg(p.bias + n + j);
-          if (p.relu) x = fmaxf(x, 0.f);
-          o[j] = x;
+      for (int i = 0; i < 4; ++i) rn[i] = *reinterpret_cast<const float4*>(rrow + n0 + 4 * i);
+    }
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      const int n = n0 + c0;
+      float4 bb[4], rr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bb[i] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t v[16];
+      tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rr[i] = rn[i];
+      if (rrow && c0 + 16 < BN) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rn[i] = *reinterpret_cast<const float4*>(rrow + n + 16 + 4 * i);
+      }
+      tmem_ld_wait();
+      if (row_ok) {
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb[i].x; o[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb[i].y;
+          o[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb[i].z; o[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb[i].w;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
         }
         if (rrow) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 r4 = *reinterpret_cast<const float4*>(rrow + n + j);
-            o[j] += r4.x; o[j + 1] += r4.y; o[j + 2] += r4.z; o[j + 3] += r4.w;
-          }
+          for (int i = 0; i < 4; ++i) { o[4 * i] += rr[i].x; o[4 * i + 1] += rr[i].y; o[4 * i + 2] += rr[i].z; o[4 * i + 3] += rr[i].w; }
         }
         if (p.ln_w) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { s1 += o[j]; s2 = fmaf(o[j], o[j], s2); }
+          for (int j = 0; j < 16; ++j) { s1 += o[j]; s2 = fmaf(o[j], o[j], s2); }
         }
         if (crow) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
+          for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(crow + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         }
         if (cbrow) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < 16; j += 8) {
             __nv_bfloat162 h0 = __floats2bfloat162_rn(o[j], o[j + 1]);
             __nv_bfloat162 h1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
             __nv_bfloat162 h2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]);
@@ -337,17 +288,22 @@ static PFN_encodeTiled g_encode = nullptr;
 static std::mutex g_map_mu;
 static std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
 
-static int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-  std::lock_guard<std::mutex> lk(g_map_mu);
-  if (!g_encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-      set_last_error("cuTensorMapEncodeTiled entry point not found");
-      return -1;
-    }
-    g_encode = (PFN_encodeTiled)fn;
+// caller holds g_map_mu
+static int ensure_encode_locked() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point not found");
+    return -1;
   }
+  g_encode = (PFN_encodeTiled)fn;
+  return 0;
+}
+
+int tc_get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (ensure_encode_locked()) return -1;
   auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return 0; }
@@ -362,6 +318,30 @@ static int get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CU
   if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return -1; }
   if (g_maps.size() > 4096) g_maps.clear();
   g_maps[key] = m;
+  *out = m;
+  return 0;
+}
+
+// fp32 row-major [rows][cols] (ld in elements), box = 32 columns (128 bytes) x box_rows, 128-byte swizzle: the staging
+// layout of the fused-FFN output tile (TMA store / reduce-add).
+int tc_get_map_f32(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  static std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> maps;
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (ensure_encode_locked()) return -1;
+  auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+  auto it = maps.find(key);
+  if (it != maps.end()) { *out = it->second; return 0; }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(f32) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return -1; }
+  if (maps.size() > 4096) maps.clear();
+  maps[key] = m;
   *out = m;
   return 0;
 }
@@ -400,8 +380,8 @@ int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
   const bool small = !ln && ((N % 128 != 0) || ((long)cdiv(M, TC_BM) * (N / 128) < kNumSMs));
   const int BN = ln ? 256 : (small ? 64 : 128);
   CUtensorMap ma, mb;
-  if (get_map(A, M, K, lda, TC_BM, &ma)) return -1;
-  if (get_map(W, N, K, K, BN, &mb)) return -1;
+  if (tc_get_map(A, M, K, lda, TC_BM, &ma)) return -1;
+  if (tc_get_map(W, N, K, K, BN, &mb)) return -1;
   TcParams p{bias, R, ldr, C, ldc, Cb, ldcb, c_row_off, M, N, K, relu, n_rows_dev, ln_w, ln_b, ln_out, nullptr, 0, nullptr, nullptr};
   // K <= 256 has only four K-blocks: two stages let several CTAs share an SM so that one CTA's epilogue
   // overlaps another's main loop; deeper K keeps the four-stage ring
@@ -425,7 +405,7 @@ int launch_gemm_bf16_lnA(const float* X, int ldx, const float* lna_w, const floa
   const bool small = (N % 128 != 0) || ((long)cdiv(M, TC_BM) * (N / 128) < kNumSMs);
   const int BN = small ? 64 : 128;
   CUtensorMap mb;
-  if (get_map(W, N, K, K, BN, &mb)) return -1;
+  if (tc_get_map(W, N, K, K, BN, &mb)) return -1;
   TcParams p{bias, nullptr, 0, C, ldc, Cb, ldcb, nullptr, M, N, K, relu, n_rows_dev, nullptr, nullptr, nullptr, X, ldx, lna_w, lna_b};
   return small ? launch_bn<64, 4, true>(mb, mb, p, st) : launch_bn<128, 4, true>(mb, mb, p, st);
 }

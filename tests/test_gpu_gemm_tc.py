@@ -101,3 +101,41 @@ def test_linear_bf16_layernorm_prologue(M, N, relu, bf16_out):
     assert (y - want).abs().mean().item() <= 1e-3
     if bf16_out:
         assert (y16.float() - want).abs().max().item() <= 5e-2
+
+
+@pytest.mark.parametrize("M,F", [(128, 128), (77, 256), (300, 2048), (2688, 2048), (10752, 2048)])
+def test_ffn_fused_matches_two_gemm_path(M, F):
+    """Fused FFN1 -> ReLU -> FFN2 kernel (hidden kept on the SM) against (a) the two tcgen05 GEMMs it replaces, with
+    the same bf16 rounding of the hidden activation: same accumulation order, so equal to fp32 rounding noise; and
+    (b) a plain PyTorch fp32 reference of the op (tolerance: bf16 rounding of the hidden activation)."""
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    D = 256
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + F)
+    a = torch.randn(M, D, generator=g, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn(F, D, generator=g, device="cuda") / D ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(F, generator=g, device="cuda") * 0.1
+    w2 = (torch.randn(D, F, generator=g, device="cuda") / F ** 0.5).to(torch.bfloat16)
+    b2 = torch.randn(D, generator=g, device="cuda") * 0.1
+    r = torch.randn(M, D, generator=g, device="cuda")
+    # two-GEMM path
+    h16 = torch.zeros(M, F, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.sc_linear_bf16(a.data_ptr(), w1.data_ptr(), b1.data_ptr(), None, None, h16.data_ptr(), M, F, D, 1, None), "ffn1")
+    y2 = r.clone()
+    _lib.check(lib.sc_linear_bf16(h16.data_ptr(), w2.data_ptr(), b2.data_ptr(), y2.data_ptr(), y2.data_ptr(), None, M, D, F, 0, None), "ffn2")
+    # fused, in place on the residual like the engine (accumulate), and as a plain store
+    y = r.clone()
+    _lib.check(lib.sc_ffn_bf16(a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), y.data_ptr(),
+                               1, M, F, None), "ffn_fused")
+    y0 = torch.full((M, D), float("nan"), device="cuda")
+    _lib.check(lib.sc_ffn_bf16(a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), y0.data_ptr(),
+                               0, M, F, None), "ffn_fused")
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all() and torch.isfinite(y0).all()
+    d = (y - y2).abs().max().item()
+    assert d <= 1e-5 * max(1.0, y2.abs().max().item()), f"fused vs two-GEMM: {d}"
+    h = (a.float() @ w1.float().t() + b1).relu()
+    want = h.to(torch.bfloat16).float() @ w2.float().t() + b2 + r
+    err = (y - want).abs().max().item()
+    assert err <= 5e-3 * max(1.0, want.abs().max().item()), f"fused vs fp32 reference: {err}"
+    assert (y0 + r - y).abs().max().item() <= 1e-5 * max(1.0, y.abs().max().item())
