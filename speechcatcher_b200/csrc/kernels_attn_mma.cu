@@ -14,11 +14,10 @@
 
 namespace scb {
 
-constexpr int MMA_TILE = 64;       // keys per tile: small tiles keep ~10 CTAs per SM resident, which hides the
-                                   // dependent global-load latency of these short (2-12 tile) kernels
-constexpr int MMA_KPW = MMA_TILE / 4;   // keys per warp
-constexpr int MMA_NT = MMA_KPW / 8;     // score n-tiles per warp
-constexpr int MMA_KK = MMA_KPW / 16;    // k-steps of the P*V product per warp
+constexpr int A_KPW = 32;          // keys per warp per step (each warp runs its own cp.async pipeline)
+constexpr int A_STEP = 4 * A_KPW;  // keys per CTA step
+constexpr int A_NT = A_KPW / 8;    // score n-tiles per warp
+constexpr int A_KK = A_KPW / 16;   // k-steps of the P*V product per warp
 constexpr int MMA_MAXB = 16;       // rows of the m16 tile
 constexpr int MMA_KEYS_SMEM = 768;  // self-attention key list entries staged in shared memory (longer lists spill to global)
 
@@ -100,6 +99,23 @@ int launch_build_self_keys(const SearchBuffers& sb, cudaStream_t st) {
   return 0;
 }
 
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ float ex2_approx(float x) {      // 2^x, ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ncu (mid-utterance, T ~ 400): the first version of this kernel was ISSUE-bound, not memory-bound -- 1900 warp
+// instructions per 64-key tile for 32 HMMAs (CTA-wide double buffering with two __syncthreads per tile, per-element
+// branches around expf, per-element mask loads, 64-bit address arithmetic per cp.async).  This version gives every
+// warp a private two-stage cp.async pipeline over its own 32 keys per step (no CTA barrier in the main loop), works
+// on raw scores with one ex2 per element (scale * log2(e) folded into an FMA), masks only where a mask can exist
+// (self: the divergent tail, found with one warp vote; cross: the last step), and fetches B fragments with x4
+// ldmatrix.
 template <int DK, int MODE>
 __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __nv_bfloat16* kv_layer,
                                                            const float* __restrict__ q, int ldq, int q_off,
@@ -115,15 +131,16 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
   constexpr int CPR = DK / 8;                // 16-byte chunks per K (or V) row
   constexpr int KSTEPS = DK / 16;
   constexpr int NDT = DK / 8;                // n-tiles of the output
+  constexpr int RPP = 32 / CPR;              // rows one pass of the warp's 32 lanes covers
+  constexpr int PASSES = A_KPW / RPP;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);               // [16][RS]
-  __nv_bfloat16* Kt = Qs + 16 * RS;                                             // [2][TILE][RS]
-  __nv_bfloat16* Vt = Kt + 2 * MMA_TILE * RS;                                   // [2][TILE][RS]
-  signed char* own = reinterpret_cast<signed char*>(Vt + 2 * MMA_TILE * RS);    // [2][TILE]
-  int* keys_s = reinterpret_cast<int*>(own + 2 * MMA_TILE);                      // self only: [MMA_KEYS_SMEM]
-  // merge scratch aliases the K tiles after the main loop
-  float* mrg_m = reinterpret_cast<float*>(Kt);                                   // [4][16]
+  __nv_bfloat16* KV = Qs + 16 * RS;                                             // [4 warps][2 stages][K|V][A_KPW][RS]
+  signed char* own = reinterpret_cast<signed char*>(KV + 4 * 2 * 2 * A_KPW * RS);   // [4][2][A_KPW]
+  int* keys_s = reinterpret_cast<int*>(own + 4 * 2 * A_KPW);                     // self only: [MMA_KEYS_SMEM]
+  // merge scratch aliases the K|V stages after the main loop
+  float* mrg_m = reinterpret_cast<float*>(KV);                                   // [4][16]
   float* mrg_l = mrg_m + 64;                                                     // [4][16]
   float* mrg_o = mrg_l + 64;                                                     // [4][16][DK]
 
@@ -133,7 +150,7 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
   if (MODE == 1) base = kv_layer + (size_t)s * sb.Tcap * row_stride + head * DK;
   else base = kv_layer + (size_t)s * sb.Lcap * B * row_stride + head * DK;
 
-  // ---- Q tile (rows >= nb are zero), self: append K|V and build the ancestor tables
+  // ---- Q tile (rows >= nb are zero: they produce finite values that are never written), self: append K|V
   for (int i = tid; i < 16 * DK; i += 128) {
     const int r = i / DK, d = i % DK;
     const float v = r < nb ? q[(size_t)(row0 + r) * ldq + q_off + head * DK + d] : 0.f;
@@ -150,133 +167,151 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
     }
     n_keys = sb.self_nkeys[s];
     keys = sb.self_keys + (size_t)s * sb.key_cap;
-    // the key list is read once, coalesced, instead of one dependent global load in front of every tile
+    // the key list is read once, coalesced, instead of one dependent global load in front of every step
     for (int i = tid; i < n_keys && i < MMA_KEYS_SMEM; i += 128) keys_s[i] = keys[i];
-    __syncthreads();                    // key list staged; appended rows visible to the tile loads below
   } else {
     n_keys = c.Tb;
     if (tid == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 2));
   }
-  const int n_tiles = (n_keys + MMA_TILE - 1) / MMA_TILE;
+  __syncthreads();                      // Qs, key list staged; appended rows visible to the loads below
+  const int n_steps = (n_keys + A_STEP - 1) / A_STEP;
 
-  auto issue_tile = [&](int t, int buf) {
-    const int u0 = t * MMA_TILE;
-    __nv_bfloat16* kd = Kt + (size_t)buf * MMA_TILE * RS;
-    __nv_bfloat16* vd = Vt + (size_t)buf * MMA_TILE * RS;
-    for (int idx = tid; idx < MMA_TILE * CPR; idx += 128) {
-      const int r = idx / CPR, ch = idx % CPR, u = u0 + r;
+  __nv_bfloat16* kw = KV + (size_t)warp * (2 * 2 * A_KPW * RS);      // this warp's stages: [2][K|V][A_KPW][RS]
+  signed char* ownw = own + warp * 2 * A_KPW;
+  const int lr = lane / CPR, ch8 = (lane % CPR) * 8;
+
+  auto issue = [&](int t, int buf) {
+    const int u0 = t * A_STEP + A_KPW * warp;
+    __nv_bfloat16* kd = kw + (size_t)buf * (2 * A_KPW * RS);
+    __nv_bfloat16* vd = kd + A_KPW * RS;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = lr + RPP * ps, u = u0 + r;
       if (u < n_keys) {
         const __nv_bfloat16* src;
-        int owner = -1;
-        if (MODE == 1) src = base + (size_t)u * row_stride;
+        if (MODE == 1) src = base + (size_t)u * row_stride + ch8;
         else {
           const int kd_ = u < MMA_KEYS_SMEM ? keys_s[u] : keys[u];
-          src = base + ((size_t)(kd_ & 0xffff) * B + ((kd_ >> 16) & 0xff)) * row_stride;
-          owner = (kd_ >> 24) - 1;
+          src = base + ((size_t)(kd_ & 0xffff) * B + ((kd_ >> 16) & 0xff)) * row_stride + ch8;
+          if (ch8 == 0) ownw[buf * A_KPW + r] = (signed char)((kd_ >> 24) - 1);
         }
-        cp_async16(kd + r * RS + ch * 8, src + ch * 8);
-        cp_async16(vd + r * RS + ch * 8, src + D + ch * 8);
-        if (ch == 0) own[buf * MMA_TILE + r] = (signed char)owner;
+        cp_async16(kd + r * RS + ch8, src);
+        cp_async16(vd + r * RS + ch8, src + D);
       } else {
-        *reinterpret_cast<uint4*>(kd + r * RS + ch * 8) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(vd + r * RS + ch * 8) = make_uint4(0, 0, 0, 0);
-        if (ch == 0) own[buf * MMA_TILE + r] = (signed char)-2;      // invisible to everyone
+        *reinterpret_cast<uint4*>(kd + r * RS + ch8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(vd + r * RS + ch8) = make_uint4(0, 0, 0, 0);
+        if (MODE == 0 && ch8 == 0) ownw[buf * A_KPW + r] = (signed char)-2;      // invisible to everyone
       }
     }
     cp_async_commit();
   };
 
-  if (n_tiles > 0) issue_tile(0, 0);
-  __syncthreads();                      // Qs complete
+  if (n_steps > 0) issue(0, 0);
   uint32_t qa[KSTEPS][4];
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks)
     ldsm_x4(qa[ks], Qs + ((lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 16 * ks + 8 * (lane >> 4));
 
-  const float inv_sqrt = 1.0f / sqrtf((float)DK);
+  const float cs = 1.4426950408889634f / sqrtf((float)DK);      // softmax scale * log2(e): p = 2^(cs * (s - m))
   const int r0 = lane >> 2, r1 = r0 + 8, qd = lane & 3;
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};   // running max of the RAW scores
   float o[NDT][4];
 #pragma unroll
   for (int i = 0; i < NDT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
-  for (int t = 0; t < n_tiles; ++t) {
+  for (int t = 0; t < n_steps; ++t) {
     const int buf = t & 1;
-    if (t + 1 < n_tiles) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const __nv_bfloat16* kb = Kt + (size_t)buf * MMA_TILE * RS + (size_t)(MMA_KPW * warp) * RS;
-    const __nv_bfloat16* vb = Vt + (size_t)buf * MMA_TILE * RS + (size_t)(MMA_KPW * warp) * RS;
-    const signed char* ob = own + buf * MMA_TILE + MMA_KPW * warp;
-    // ---- S = Q K^T for this warp's MMA_KPW keys
-    float sacc[MMA_NT][4];
+    if (t + 1 < n_steps) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncwarp();                       // the other lanes' copies / zero fills of this stage are visible
+    const int u0 = t * A_STEP + A_KPW * warp;
+    if (u0 < n_keys) {
+      const __nv_bfloat16* kb = kw + (size_t)buf * (2 * A_KPW * RS);
+      const __nv_bfloat16* vb = kb + A_KPW * RS;
+      // ---- S = Q K^T for this warp's A_KPW keys (raw scores)
+      float sacc[A_NT][4];
 #pragma unroll
-    for (int nt = 0; nt < MMA_NT; ++nt) {
-      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+      for (int nt = 0; nt < A_NT; ++nt) {
+        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) {
-        uint32_t bfr[2];
-        ldsm_x2(bfr, kb + (8 * nt + (lane & 7)) * RS + 16 * ks + 8 * ((lane >> 3) & 1));
-        mma_bf16(sacc[nt], qa[ks], bfr);
+        for (int k2 = 0; k2 < KSTEPS / 2; ++k2) {
+          uint32_t bfr[4];              // B fragments of two k-steps with one ldmatrix
+          ldsm_x4(bfr, kb + (8 * nt + (lane & 7)) * RS + 32 * k2 + 8 * (lane >> 3));
+          mma_bf16(sacc[nt], qa[2 * k2], bfr);
+          mma_bf16(sacc[nt], qa[2 * k2 + 1], bfr + 2);
+        }
+      }
+      // ---- mask: only where one can exist
+      if (MODE == 0) {
+        const signed char* ob = ownw + buf * A_KPW;
+        if (!__all_sync(0xffffffffu, ob[lane] == -1)) {       // step touches the divergent tail (or padding)
+#pragma unroll
+          for (int nt = 0; nt < A_NT; ++nt) {
+            const int o0 = ob[8 * nt + 2 * qd], o1 = ob[8 * nt + 2 * qd + 1];
+            if (!(o0 == -1 || o0 == r0)) sacc[nt][0] = -INFINITY;
+            if (!(o1 == -1 || o1 == r0)) sacc[nt][1] = -INFINITY;
+            if (!(o0 == -1 || o0 == r1)) sacc[nt][2] = -INFINITY;
+            if (!(o1 == -1 || o1 == r1)) sacc[nt][3] = -INFINITY;
+          }
+        }
+      } else if (u0 + A_KPW > n_keys) {                        // cross: zero-filled rows past the last frame
+#pragma unroll
+        for (int nt = 0; nt < A_NT; ++nt) {
+          const int k0 = u0 + 8 * nt + 2 * qd;
+          if (k0 >= n_keys) { sacc[nt][0] = -INFINITY; sacc[nt][2] = -INFINITY; }
+          if (k0 + 1 >= n_keys) { sacc[nt][1] = -INFINITY; sacc[nt][3] = -INFINITY; }
+        }
+      }
+      // ---- online softmax (rows r0, r1 of this thread)
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < A_NT; ++nt) {
+        mx[0] = fmaxf(mx[0], fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+      float scale[2], nm[2], psum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+        const float m_new = fmaxf(m_run[h], mx[h]);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // row has seen no visible key yet
+        scale[h] = ex2_approx((m_run[h] - m_use) * cs);             // m_run = -inf -> 0 (o, l are still 0)
+        m_run[h] = m_new;
+        nm[h] = -m_use * cs;
+      }
+      uint32_t pa[A_KK][4];
+#pragma unroll
+      for (int nt = 0; nt < A_NT; ++nt) {
+        const float p0 = ex2_approx(fmaf(sacc[nt][0], cs, nm[0])), p1 = ex2_approx(fmaf(sacc[nt][1], cs, nm[0]));
+        const float p2 = ex2_approx(fmaf(sacc[nt][2], cs, nm[1])), p3 = ex2_approx(fmaf(sacc[nt][3], cs, nm[1]));
+        psum[0] += p0 + p1; psum[1] += p2 + p3;
+        // C fragment of S -> A fragment of P: n-tile 2kk -> a0/a1, n-tile 2kk+1 -> a2/a3
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        psum[h] += __shfl_xor_sync(0xffffffffu, psum[h], 1);
+        psum[h] += __shfl_xor_sync(0xffffffffu, psum[h], 2);
+        l_run[h] = l_run[h] * scale[h] + psum[h];
+      }
+#pragma unroll
+      for (int nd = 0; nd < NDT; ++nd) { o[nd][0] *= scale[0]; o[nd][1] *= scale[0]; o[nd][2] *= scale[1]; o[nd][3] *= scale[1]; }
+      // ---- O += P V
+#pragma unroll
+      for (int kk = 0; kk < A_KK; ++kk) {
+#pragma unroll
+        for (int n2 = 0; n2 < NDT / 2; ++n2) {
+          uint32_t bfr[4];              // V fragments of two output n-tiles with one transposing ldmatrix
+          ldsm_x4_trans(bfr, vb + (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 16 * n2 + 8 * (lane >> 4));
+          mma_bf16(o[2 * n2], pa[kk], bfr);
+          mma_bf16(o[2 * n2 + 1], pa[kk], bfr + 2);
+        }
       }
     }
-    // ---- mask + online softmax (rows r0, r1 of this thread)
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int nt = 0; nt < MMA_NT; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = 8 * nt + 2 * qd + (e & 1);
-        const int row = (e & 2) ? r1 : r0;
-        const int ow = ob[key];
-        const bool vis = row < nb && (ow == -1 || ow == row);
-        const float v = vis ? sacc[nt][e] * inv_sqrt : -INFINITY;
-        sacc[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
-      }
-    }
-    float scale[2], psum[2] = {0.f, 0.f};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-      const float m_new = fmaxf(m_run[h], mx[h]);
-      scale[h] = (m_new == -INFINITY) ? 1.f : expf(m_run[h] - m_new);
-      m_run[h] = m_new;
-    }
-    uint32_t pa[MMA_KK][4];
-#pragma unroll
-    for (int nt = 0; nt < MMA_NT; ++nt) {
-      float p[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float mref = m_run[e >> 1];
-        p[e] = (mref == -INFINITY) ? 0.f : expf(sacc[nt][e] - mref);
-        psum[e >> 1] += p[e];
-      }
-      // C fragment of S -> A fragment of P: n-tile 2kk -> a0/a1, n-tile 2kk+1 -> a2/a3
-      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
-      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      psum[h] += __shfl_xor_sync(0xffffffffu, psum[h], 1);
-      psum[h] += __shfl_xor_sync(0xffffffffu, psum[h], 2);
-      l_run[h] = l_run[h] * scale[h] + psum[h];
-    }
-#pragma unroll
-    for (int nd = 0; nd < NDT; ++nd) { o[nd][0] *= scale[0]; o[nd][1] *= scale[0]; o[nd][2] *= scale[1]; o[nd][3] *= scale[1]; }
-    // ---- O += P V
-#pragma unroll
-    for (int kk = 0; kk < MMA_KK; ++kk) {
-#pragma unroll
-      for (int nd = 0; nd < NDT; ++nd) {
-        uint32_t bfr[2];
-        ldsm_x2_trans(bfr, vb + (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 8 * nd);
-        mma_bf16(o[nd], pa[kk], bfr);
-      }
-    }
-    __syncthreads();                    // tile fully consumed before its buffer is refilled
+    __syncwarp();                       // stage fully consumed before this warp refills it
   }
+  __syncthreads();                      // every warp is done with its stages: the merge scratch aliases them
   // ---- merge the four warps' partial (m, l, O)
   if (qd == 0) {
     mrg_m[warp * 16 + r0] = m_run[0]; mrg_m[warp * 16 + r1] = m_run[1];
@@ -298,7 +333,7 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float mw = mrg_m[w * 16 + r];
-      const float f = (mw == -INFINITY) ? 0.f : expf(mw - M);
+      const float f = (mw == -INFINITY) ? 0.f : ex2_approx((mw - M) * cs);
       L += mrg_l[w * 16 + r] * f;
       acc += mrg_o[((size_t)w * 16 + r) * DK + d] * f;
     }
@@ -440,10 +475,11 @@ template <int DK, int MODE>
 static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const float* q, int ldq, int q_off, float* out,
                         __nv_bfloat16* out16, cudaStream_t st) {
   constexpr int RS = DK + 8;
-  size_t smem = sizeof(__nv_bfloat16) * ((size_t)16 * RS + 4 * (size_t)MMA_TILE * RS) + 2 * MMA_TILE + 16;
+  const size_t stages = sizeof(__nv_bfloat16) * 4 * 2 * 2 * (size_t)A_KPW * RS;     // [4 warps][2 stages][K|V][A_KPW][RS]
+  size_t smem = sizeof(__nv_bfloat16) * (size_t)16 * RS + stages + 4 * 2 * A_KPW + 16;
   if (MODE == 0) smem += sizeof(int) * MMA_KEYS_SMEM;
   const size_t merge = sizeof(float) * (128 + 4 * 16 * DK);
-  if (sizeof(__nv_bfloat16) * 2 * (size_t)MMA_TILE * RS < merge) { set_last_error("attn_mma: merge scratch does not fit"); return -1; }
+  if (stages < merge) { set_last_error("attn_mma: merge scratch does not fit"); return -1; }
   static size_t attr = 0;
   if (attr < smem) {
     if (cudaFuncSetAttribute(dec_attn_mma_kernel<DK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

@@ -31,9 +31,10 @@ def run(kind, arch, beam, n_streams, seconds):
 
 
 def main():
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
     for arch, beam in (("xl_d4", 10), ("m_d2", 5)):
-        a_logs, a_beams, a_enc = run("simt", arch, beam, 4, 5.0)
-        b_logs, b_beams, b_enc = run("mma", arch, beam, 4, 5.0)
+        a_logs, a_beams, a_enc = run("simt", arch, beam, 4, seconds)
+        b_logs, b_beams, b_enc = run("mma", arch, beam, 4, seconds)
         print(f"{arch}: encoder output max |simt - mma| = {float((a_enc - b_enc).abs().max()):.5f} (scale {float(a_enc.abs().max()):.2f})")
         first_div = None
         for i, (x, y) in enumerate(zip(a_beams, b_beams)):
