@@ -159,9 +159,10 @@ int sc_linear_bf16_lnA(const float* x_f32, const float* ln_w, const float* ln_b,
  * (model/layers/feed_forward.py:41-50) as one tcgen05 kernel; x [m][256] bf16, w1 [f][256] bf16, w2 [256][f] bf16,
  * f a multiple of 128.  accumulate != 0: y already holds the residual and the result is added to it in place
  * (contextual_block_encoder_layer.py:243-251), else y is overwritten.  The hidden activation is rounded to bf16 after
- * bias + ReLU, as in the two-GEMM path. */
+ * bias + ReLU, as in the two-GEMM path.  splits > 1 (needs accumulate): the hidden dimension is divided over that
+ * many CTAs per 128-row tile whose partial results are added at the L2 (small-m launches of the decode step). */
 int sc_ffn_bf16(const void* x_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
-                float* y_f32, int32_t accumulate, int32_t m, int32_t f, void* stream);
+                float* y_f32, int32_t accumulate, int32_t m, int32_t f, int32_t splits, void* stream);
 
 /* Same kernel with a device-side timeline: `stamps` (device, >= 1024 int64) receives clock64() stamps of the first
  * CTA's MMA-issue warp and of one epilogue thread per hidden chunk (performance diagnosis, tests/ffn_timeline.py). */

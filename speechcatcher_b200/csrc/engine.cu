@@ -24,7 +24,7 @@ int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat
                              int n_head, int d_model, cudaStream_t st);
 int launch_ffn_fused_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W1, const float* b1,
                           const __nv_bfloat16* W2, const float* b2, float* C, int ldc, int accumulate, int M, int F,
-                          cudaStream_t st, long long* dbg = nullptr);
+                          int splits, const int* n_rows_dev, cudaStream_t st, long long* dbg = nullptr);
 int launch_gemm_bf16_lnA(const float* X, int ldx, const float* lna_w, const float* lna_b, const __nv_bfloat16* W,
                          const float* bias, float* C, int ldc, __nv_bfloat16* Cb, int ldcb, int M, int N, int relu,
                          const int* n_rows_dev, cudaStream_t st);
@@ -106,12 +106,17 @@ struct Engine {
   // Correct (tests/test_gpu_gemm_tc.py) but currently slower than separate LayerNorm kernels: the one-row-per-thread
   // epilogue over 256 columns serialises too much and BN = 256 leaves few CTAs; off by default.
   bool fuse_ln = false;
+  bool fuse_ln_dec = false;         // same for the decoder step (self-O -> norm2, cross-O -> norm3, FFN2 -> next norm1)
   // bf16 mode: compute every LayerNorm inside the GEMM that consumes it (LayerNorm-prologue GEMM, K = 256)
   bool ln_prologue = false;
   // bf16 mode: encoder FFN1 -> ReLU -> FFN2 as one kernel with the hidden activation kept on the SM
   // (kernels_ffn_fused.cu); used when a launch has at least `fused_ffn_min_rows` rows
   bool fused_ffn = false;
   int fused_ffn_min_rows = 1024;
+  // hidden-dimension splits of the fused FFN (partial tiles are added at the L2): 0 = automatic (enough CTAs to
+  // spread a small-M launch over the GPU; results then depend on the add order at fp32 rounding level), 1 = never split
+  int ffn_splits = 0;
+  bool fused_ffn_dec = false;       // decode step: LayerNorm -> fused FFN (split) instead of LayerNorm -> FFN1 -> FFN2
   // deferred decoding: a push stops iterating once fewer than `lazy_threshold` streams are active and leaves
   // the stragglers' blocks queued on the device; they continue during later pushes (0 = strict, drain every push)
   int lazy_threshold = 0;
@@ -280,19 +285,29 @@ static inline void prof_mark(Engine& e, int tag, cudaStream_t st, bool begin) {
 static int ln_linear(Engine& e, int ln_tag, int gemm_tag, bool dec, const float* X, int ldx, const float* ln_w,
                      const float* ln_b, int rows_max, const Lin& l, cudaStream_t st) {
   const bool tc = e.cfg.precision == 1;
-  if (tc && e.ln_prologue && !e.fuse_ln) {
+  const bool fuse = dec ? e.fuse_ln_dec : e.fuse_ln;
+  if (tc && e.ln_prologue && !fuse) {
     e.launches++;
     PROFX(gemm_tag, dec, launch_gemm_bf16_lnA(X, ldx, ln_w, ln_b, l.W16, l.bias, l.C, l.ldc, l.C16, l.ldc, l.M, l.N, l.relu,
                                              l.n_rows_dev, st));
     return 0;
   }
-  if (!(tc && e.fuse_ln)) {
+  if (!(tc && fuse)) {
     e.launches++;
     if (tc) PROFX(ln_tag, dec, launch_layernorm_bf16(X, ldx, ln_w, ln_b, const_cast<__nv_bfloat16*>(l.A16), l.lda, rows_max, l.K, l.n_rows_dev, st));
     else PROFX(ln_tag, dec, launch_layernorm(X, ldx, ln_w, ln_b, const_cast<float*>(l.A), l.lda, rows_max, l.K, l.n_rows_dev, st));
   }
   PROFX(gemm_tag, dec, linear(e, l, st));
   return 0;
+}
+
+// splits of the fused FFN's hidden dimension so that a launch has roughly 64+ CTAs (one CTA per SM, 148 SMs)
+static int ffn_auto_splits(const Engine& e, int rows, int F) {
+  if (e.ffn_splits >= 1) return (F / 128) % e.ffn_splits == 0 ? e.ffn_splits : 1;
+  const int tiles = (rows + 127) / 128, chunks = F / 128;
+  int s = 1;
+  while (tiles * s < 64 && s * 2 <= 8 && chunks % (s * 2) == 0) s *= 2;
+  return s;
 }
 
 // ---------------------------------------------------------------- encoder layers over all blocks of the push
@@ -324,7 +339,8 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
       e.launches += 2;
       PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
       if (e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
-      PE(T_ENC_FFN2, launch_ffn_fused_bf16(e.Nrm16, D, w.f1w16, w.f1b, w.f2w16, w.f2b, e.X, D, 1, rows, F, st));
+      PE(T_ENC_FFN2, launch_ffn_fused_bf16(e.Nrm16, D, w.f1w16, w.f1b, w.f2w16, w.f2b, e.X, D, 1, rows, F,
+                                           ffn_auto_splits(e, rows, F), nullptr, st));
     } else {
       TRY(ln_linear(e, T_ENC_LN, T_ENC_FFN1, false, e.X, D, w.ln2w, w.ln2b, rows, Lin{e.Nrm, D, e.Nrm16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.FF, F, tc ? e.FF16 : nullptr, rows, F, D, 1, nullptr}, st));
       {
@@ -349,7 +365,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   e.prof_sample = (e.step_seq++ % e.prof_stride) == 0;
   const bool ptot = prof_on(e, T_DEC_STEP_TOTAL, true);
   if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, true);
-  const bool fl = tc && e.fuse_ln;
+  const bool fl = tc && e.fuse_ln_dec;
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, fl ? e.dec[0].ln1w : nullptr, fl ? e.dec[0].ln1b : nullptr, e.dn16, st));
   if (e.mma_attn) PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
   for (int l = 0; l < c.dec_layers; ++l) {
@@ -371,11 +387,18 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
       if (fl) o = with_ln(o, w.ln3w, w.ln3b, e.dn16);
       PD(T_DEC_CO, linear(e, o, st));
     }
-    TRY(ln_linear(e, T_DEC_LN, T_DEC_FFN1, true, e.dx, D, w.ln3w, w.ln3b, R, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
-    {
-      Lin f2{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr};
-      if (fl) f2 = (l + 1 < c.dec_layers) ? with_ln(f2, e.dec[l + 1].ln1w, e.dec[l + 1].ln1b, e.dn16) : with_ln(f2, e.daw, e.dab, e.dn16);
-      PD(T_DEC_FFN2, linear(e, f2, st));
+    if (tc && e.fused_ffn_dec && !fl && !e.ln_prologue) {
+      e.launches += 2;
+      PD(T_DEC_LN, launch_layernorm_bf16(e.dx, D, w.ln3w, w.ln3b, e.dn16, D, R, D, nr, st));
+      PD(T_DEC_FFN2, launch_ffn_fused_bf16(e.dn16, D, w.f1w16, w.f1b, w.f2w16, w.f2b, e.dx, D, 1, R, F,
+                                           ffn_auto_splits(e, R, F), nr, st));
+    } else {
+      TRY(ln_linear(e, T_DEC_LN, T_DEC_FFN1, true, e.dx, D, w.ln3w, w.ln3b, R, Lin{e.dn, D, e.dn16, w.f1w, w.f1w16, w.f1b, nullptr, 0, tc ? nullptr : e.dffn, F, tc ? e.dffn16 : nullptr, R, F, D, 1, nr}, st));
+      {
+        Lin f2{e.dffn, F, tc ? e.dffn16 : nullptr, w.f2w, w.f2w16, w.f2b, e.dx, D, e.dx, D, nullptr, R, D, F, 0, nr};
+        if (fl) f2 = (l + 1 < c.dec_layers) ? with_ln(f2, e.dec[l + 1].ln1w, e.dec[l + 1].ln1b, e.dn16) : with_ln(f2, e.daw, e.dab, e.dn16);
+        PD(T_DEC_FFN2, linear(e, f2, st));
+      }
     }
     e.launches += fl ? 2 : 5;
   }
@@ -455,8 +478,17 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     const char* lp = getenv("SCB_LN_PROLOGUE");
     // measured slower than a separate LayerNorm kernel (every N-tile CTA re-normalises its 128 rows): opt-in only
     e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && lp && strcmp(lp, "1") == 0;
+    const char* fln = getenv("SCB_FUSE_LN");   // "enc" / "dec" / "1": LayerNorm in the epilogue of the producing GEMM
+    if (fln && cfg->precision == 1) {
+      e->fuse_ln = strcmp(fln, "1") == 0 || strcmp(fln, "enc") == 0;
+      e->fuse_ln_dec = strcmp(fln, "1") == 0 || strcmp(fln, "dec") == 0;
+    }
     const char* ff = getenv("SCB_FUSED_FFN");   // "0" keeps the two-GEMM encoder FFN (A/B tests)
     e->fused_ffn = cfg->precision == 1 && cfg->d_model == 256 && cfg->ffn % 128 == 0 && !(ff && strcmp(ff, "0") == 0);
+    const char* ffd = getenv("SCB_FUSED_FFN_DEC");   // "0" keeps LayerNorm -> FFN1 -> FFN2 in the decode step
+    e->fused_ffn_dec = e->fused_ffn && !(ffd && strcmp(ffd, "0") == 0);
+    const char* fsp = getenv("SCB_FFN_SPLITS");
+    if (fsp) e->ffn_splits = atoi(fsp);
     const char* pdl = getenv("SCB_PDL");     // programmatic dependent launch of the decode-step kernel chain (default on)
     g_use_pdl = !(pdl && strcmp(pdl, "0") == 0);
   }
@@ -909,7 +941,10 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
     return SC_OK;
   }
   if (strcmp(name, "fused_ffn_min_rows") == 0) { e->fused_ffn_min_rows = value; return SC_OK; }
-  if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = value != 0 && e->cfg.precision == 1; return SC_OK; }
+  if (strcmp(name, "fused_ffn_decoder") == 0) { e->fused_ffn_dec = value != 0 && e->fused_ffn; return SC_OK; }
+  if (strcmp(name, "ffn_splits") == 0) { e->ffn_splits = value < 0 ? 0 : value; return SC_OK; }
+  if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = e->fuse_ln_dec = value != 0 && e->cfg.precision == 1; return SC_OK; }
+  if (strcmp(name, "fuse_layernorm_decoder") == 0) { e->fuse_ln_dec = value != 0 && e->cfg.precision == 1; return SC_OK; }
   if (strcmp(name, "mma_attention") == 0) {
     e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16;
     e->mma_enc = value != 0 && e->cfg.precision == 1;
@@ -999,15 +1034,15 @@ int sc_linear_bf16_ln(const void* x, const void* w, const float* bias, const flo
 }
 
 int sc_ffn_bf16(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, float* y, int32_t accumulate,
-                int32_t m, int32_t f, void* stream) {
+                int32_t m, int32_t f, int32_t splits, void* stream) {
   return launch_ffn_fused_bf16((const __nv_bfloat16*)x, 256, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2, b2, y, 256,
-                               accumulate, m, f, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+                               accumulate, m, f, splits, nullptr, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }
 
 int sc_ffn_bf16_timeline(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, float* y,
                          int32_t accumulate, int32_t m, int32_t f, int64_t* stamps, void* stream) {
   return launch_ffn_fused_bf16((const __nv_bfloat16*)x, 256, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2, b2, y, 256,
-                               accumulate, m, f, (cudaStream_t)stream, (long long*)stamps) ? SC_ERR_CUDA : SC_OK;
+                               accumulate, m, f, 1, nullptr, (cudaStream_t)stream, (long long*)stamps) ? SC_ERR_CUDA : SC_OK;
 }
 
 int sc_linear_bf16_lnA(const float* x_f32, const float* ln_w, const float* ln_b, const void* w, const float* bias, float* y,

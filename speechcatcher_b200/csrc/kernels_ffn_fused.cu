@@ -46,6 +46,7 @@ constexpr int FF_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epi
 struct FfnParams {
   const float* b1; const float* b2;
   int M, F, accumulate;   // accumulate: C += tile (in-place residual) instead of C = tile
+  const int* n_rows_dev;  // optional device-side row bound (decode step: rows of the active hypotheses)
   long long* dbg;   // optional timeline of CTA 0 (clock64 stamps), see sc_ffn_bf16_timeline
 };
 
@@ -70,7 +71,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_bf16_kernel(const __g
   uint32_t* tmem_slot = (uint32_t*)(acc2_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_chunks = p.F / FF_CH;
+  // gridDim.y > 1: the hidden dimension is split across CTAs; each adds its partial tile to C at the L2 (TMA
+  // reduce-add), so a small-M launch (decode step) still spreads over many SMs.  Split 0 carries b2.
+  const int n_chunks = p.F / FF_CH / (int)gridDim.y;
+  const int jb = blockIdx.y * n_chunks;          // first hidden chunk of this CTA
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -94,7 +98,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_bf16_kernel(const __g
   const uint32_t tm_acc2 = tmem_base + 256;
 
   pdl_sync();
-  const bool cta_active = m0 < p.M;
+  int M = p.M;
+  if (p.n_rows_dev) M = min(M, *p.n_rows_dev);
+  const bool cta_active = m0 < M;
   const bool stamp = p.dbg && blockIdx.x == 0;
 
   if (!cta_active) {
@@ -122,9 +128,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_bf16_kernel(const __g
       ++c;
     };
     // W1 chunk j: stage t holds K-blocks 2t, 2t+1 of rows [j*128, j*128+128)
-    auto put_w1 = [&](int j) { for (int t = 0; t < 2; ++t) put(&map_w1, (2 * t) * TC_BK, j * FF_CH, (2 * t + 1) * TC_BK, j * FF_CH); };
+    auto put_w1 = [&](int j) { for (int t = 0; t < 2; ++t) put(&map_w1, (2 * t) * TC_BK, (jb + j) * FF_CH, (2 * t + 1) * TC_BK, (jb + j) * FF_CH); };
     // W2 chunk j: stage kb holds all 256 output rows of K-block kb (columns j*128 + kb*64 ..)
-    auto put_w2 = [&](int j) { for (int kb = 0; kb < 2; ++kb) put(&map_w2, j * FF_CH + kb * TC_BK, 0, j * FF_CH + kb * TC_BK, 128); };
+    auto put_w2 = [&](int j) { for (int kb = 0; kb < 2; ++kb) put(&map_w2, (jb + j) * FF_CH + kb * TC_BK, 0, (jb + j) * FF_CH + kb * TC_BK, 128); };
     put_w1(0);
     if (n_chunks > 1) put_w1(1);
     for (int j = 0; j < n_chunks; ++j) {
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_bf16_kernel(const __g
       tc_fence_after();
       if (estamp) p.dbg[128 + j * 4 + 2] = clock64();   // H buffer free
       // this warp converts hidden columns [half*64, half*64+64) of the chunk = K-block `half` of H[b]
-      const float4* b1v = reinterpret_cast<const float4*>(p.b1 + j * FF_CH + half * 64);
+      const float4* b1v = reinterpret_cast<const float4*>(p.b1 + (jb + j) * FF_CH + half * 64);
       unsigned char* tile = sH + (b * 2 + half) * FF_BOX + R * 128;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -256,7 +262,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_bf16_kernel(const __g
     for (int g = half * 4; g < half * 4 + 4; ++g) {
       float4 bb[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.b2 + g * 32) + i);
+      for (int i = 0; i < 8; ++i)
+        bb[i] = blockIdx.y == 0 ? __ldg(reinterpret_cast<const float4*>(p.b2 + g * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       uint32_t v[32];
       tmem_ld32(tm_acc2 + lane_base + (uint32_t)(g * 32), v);
       unsigned char* row = sA + g * FF_BOX + R * 128;
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_bf16_kernel(const __g
     if (elect_one_sync()) {
       for (int g = half * 4; g < half * 4 + 4; ++g) {
         const void* src = sA + g * FF_BOX + q * 32 * 128;
-        if (p.accumulate) tma_reduce_add_2d(&map_c, src, g * 32, m0 + q * 32);
+        if (p.accumulate || gridDim.y > 1) tma_reduce_add_2d(&map_c, src, g * 32, m0 + q * 32);
         else tma_store_2d(&map_c, src, g * 32, m0 + q * 32);
       }
       tma_store_commit();
@@ -291,12 +298,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_bf16_kernel(const __g
 
 // C[M][256] (+)= W2 * ReLU(W1 * A + b1) + b2.  A [M][256] bf16 (lda), W1 [F][256] bf16, W2 [256][F] bf16; F % 128 == 0.
 // accumulate != 0: C already holds the residual and the tile is added to it (TMA reduce-add), else C is overwritten.
+// splits > 1 (needs accumulate): the hidden dimension is divided over `splits` CTAs per row tile; the partial tiles
+// meet in C through fp32 adds at the L2, so the result depends on their arrival order at rounding level.
 int launch_ffn_fused_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W1, const float* b1,
                           const __nv_bfloat16* W2, const float* b2, float* C, int ldc, int accumulate, int M, int F,
-                          cudaStream_t st, long long* dbg) {
+                          int splits, const int* n_rows_dev, cudaStream_t st, long long* dbg) {
   if (M <= 0) return 0;
-  if (F % FF_CH != 0 || F < FF_CH || lda % 8 != 0 || ldc % 4 != 0 || !C) {
-    set_last_error("ffn_fused: unsupported shape M=%d F=%d lda=%d ldc=%d", M, F, lda, ldc);
+  if (splits < 1) splits = 1;
+  if (F % (FF_CH * splits) != 0 || F < FF_CH || lda % 8 != 0 || ldc % 4 != 0 || !C || (splits > 1 && !accumulate)) {
+    set_last_error("ffn_fused: unsupported shape M=%d F=%d lda=%d ldc=%d splits=%d accumulate=%d", M, F, lda, ldc, splits, accumulate);
     return -1;
   }
   CUtensorMap ma, mw1, mw2, mc;
@@ -313,8 +323,8 @@ int launch_ffn_fused_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     }
     attr_set = true;
   }
-  FfnParams p{b1, b2, M, F, accumulate, dbg};
-  launch_k(ffn_fused_bf16_kernel, dim3(cdiv(M, TC_BM)), dim3(FF_THREADS), smem, st, ma, mw1, mw2, mc, p);
+  FfnParams p{b1, b2, M, F, accumulate, n_rows_dev, dbg};
+  launch_k(ffn_fused_bf16_kernel, dim3(cdiv(M, TC_BM), splits), dim3(FF_THREADS), smem, st, ma, mw1, mw2, mc, p);
   SCB_LAUNCH_CHECK();
   return 0;
 }

@@ -85,7 +85,8 @@ def main():
                      "gbs": round(per / us / 1e3, 1), "max_err": err}
         print(name, out[name], flush=True)
     # fused FFN (FFN1 -> ReLU -> FFN2 in one kernel) against the sum of the two GEMMs above
-    for name, M in (("enc_ffn_fused", 10752), ("enc_ffn_fused_s", 2688), ("dec_ffn_fused", 2560)):
+    for name, M, splits in (("enc_ffn_fused", 10752, 1), ("enc_ffn_fused_s", 2688, 1), ("enc_ffn_fused_s_x4", 2688, 4),
+                            ("dec_ffn_fused", 2560, 1), ("dec_ffn_fused_x4", 2560, 4), ("dec_ffn_fused_s_x8", 640, 8)):
         F, D = 2048, 256
         g = torch.Generator(device=dev).manual_seed(2)
         xs = [torch.randn(M, D, device=dev, generator=g).to(torch.bfloat16) for _ in range(2)]
@@ -99,7 +100,7 @@ def main():
             j = i % 2
             _lib.check(lib.sc_ffn_bf16(C.c_void_p(xs[j].data_ptr()), C.c_void_p(w1.data_ptr()), C.c_void_p(b1.data_ptr()),
                                        C.c_void_p(w2.data_ptr()), C.c_void_p(b2.data_ptr()), C.c_void_p(ys[j].data_ptr()),
-                                       1, M, F, C.c_void_p(st.cuda_stream)), "sc_ffn_bf16")
+                                       1, M, F, splits, C.c_void_p(st.cuda_stream)), "sc_ffn_bf16")
 
         for i in range(10):
             launch(i)
