@@ -134,6 +134,34 @@ int sc_planner_destroy(void* planner);
 int sc_planner_reset(void* planner, int32_t stream_id);
 int sc_planner_push(void* planner, int32_t stream_id, int32_t n_samples, int32_t is_final, ScStreamPlan* plan);
 
+/* ---- offline segmentation of long files (replaces speechcatcher/simple_endpointing.py) ---- */
+/* Parameters of the cut-point search = the reference's BeamSearch constructor (simple_endpointing.py:23-34);
+ * segment_speech() fills them as beam 10, ideal 100 * average_segment_length, look-ahead 18000, min 2000, step 10,
+ * len_reward_weight 12, energy_weight 1 (:124-130).  Lengths are in 10 ms frames. */
+typedef struct ScSegmentParams {
+  int32_t beam_size;
+  int32_t ideal_segment_len;
+  int32_t max_lookahead;
+  int32_t min_len;
+  int32_t step;
+  int32_t reserved;
+  double len_reward_weight;
+  double energy_weight;
+} ScSegmentParams;
+/* Frames python_speech_features.logfbank(winlen=0.025, winstep=0.01) yields for n_samples at 16 kHz (host only). */
+int sc_segment_num_frames(int64_t n_samples, int64_t* n_frames);
+/* The 28 FFT-bin edges of the 26 mel triangles (python_speech_features get_filterbanks; host only, for tests). */
+int sc_segment_filterbank_bins(double* bins28);
+/* simple_endpointing.py:73-75 on the device, fp64: energy_dev[t] = sum_j log(fbank_j(frame t)) / 10 and
+ * smoothed_dev = -gaussian_filter1d(energy, sigma) (scipy defaults: reflect, radius int(4 sigma + .5)).
+ * pcm_dev: n_samples int16 samples (the raw file, 16 kHz mono); both outputs hold n_frames doubles. */
+int sc_segment_energy(const int16_t* pcm_dev, int64_t n_samples, double* energy_dev, double* smoothed_dev,
+                      int64_t n_frames, double sigma, void* stream);
+/* BeamSearch.search (simple_endpointing.py:43-69) on the host over the smoothed curve (host memory): writes the
+ * best cut list [0, c1, c2, ...] (segments are consecutive pairs); sequential, data dependent, microseconds. */
+int sc_segment_search(const double* smoothed_host, int64_t n_frames, const ScSegmentParams* p, int64_t* cuts,
+                      int32_t max_cuts, int32_t* n_cuts);
+
 /* ---- single operators over raw device pointers (used by the parity tests) ---- */
 /* LayerNorm eps=1e-12 (model/layers/normalization.py:23) */
 int sc_layernorm_f32(const float* x, const float* w, const float* b, float* y, int32_t rows, int32_t d,

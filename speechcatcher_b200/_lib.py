@@ -28,6 +28,11 @@ class ScStreamPlan(C.Structure):
         "called", "n_feat", "n_sub", "n_blocks", "n_enc_out", "enc_len", "n_decode_blocks", "last_T")]
 
 
+class ScSegmentParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("beam_size", "ideal_segment_len", "max_lookahead", "min_len", "step",
+                                         "reserved")] + [("len_reward_weight", C.c_double), ("energy_weight", C.c_double)]
+
+
 # every symbol include/speechcatcher_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _sz = C.c_void_p, C.c_int32, C.c_size_t
 _pi32, _pf, _pd = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
@@ -54,6 +59,10 @@ SYMBOLS = {
     "sc_planner_destroy": (C.c_int, [_vp]),
     "sc_planner_reset": (C.c_int, [_vp, _i32]),
     "sc_planner_push": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(ScStreamPlan)]),
+    "sc_segment_num_frames": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),
+    "sc_segment_filterbank_bins": (C.c_int, [_pd]),
+    "sc_segment_energy": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_double, _vp]),
+    "sc_segment_search": (C.c_int, [_pd, C.c_int64, C.POINTER(ScSegmentParams), C.POINTER(C.c_int64), _i32, _pi32]),
     "sc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "sc_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "sc_linear_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
