@@ -76,10 +76,8 @@ class Speech2TextStreaming:
             if not self._owns_group or self._calls_since_reset > 0:
                 raise ValueError(f"chunk of {len(speech)} samples exceeds the engine capacity max_chunk="
                                  f"{self.group.max_chunk}; construct with a larger max_chunk")
-            self.group.close()
             need = (len(speech) + 159999) // 160000 * 160000
-            secs = max(self._group_args["max_seconds"], need / 16000.0 + 2.0)
-            self.group = StreamGroup(max_chunk=need, **{**self._group_args, "max_seconds": secs})
+            self.ensure_capacity(max_chunk=need, max_seconds=need / 16000.0 + 2.0)
         self._calls_since_reset += 1
         self.group.push([self.stream_id], [speech], [is_final])
         plan = self.group.last_plan(self.stream_id)
@@ -87,6 +85,23 @@ class Speech2TextStreaming:
             return []                           # speech2text_streaming.py:431-433
         self.beam_state = self.group.beam(self.stream_id)
         return self.group.results(self.stream_id, is_final, finalize_all, self.token_list)
+
+    def ensure_capacity(self, n_streams: int = 1, max_seconds: float = 0.0, max_chunk: int = 0):
+        """Re-create the owned engine if it is too small (streams, seconds per stream, samples per call).  Only a
+        facade that owns its engine may do this, and only while the stream holds no state (right after reset): the
+        file-level `recognize` uses it to run the segments of one file as concurrent streams."""
+        g = self.group
+        if g.n_streams >= n_streams and g.max_seconds >= max_seconds and g.max_chunk >= max_chunk:
+            return
+        if not self._owns_group:
+            raise ValueError("this facade is a view onto a shared StreamGroup and cannot resize it")
+        if self._calls_since_reset > 0:
+            raise ValueError("the engine can only be resized right after reset()")
+        args = {**self._group_args, "n_streams": max(n_streams, g.n_streams),
+                "max_seconds": max(max_seconds, g.max_seconds)}
+        g.close()
+        self.group = StreamGroup(max_chunk=max(max_chunk, g.max_chunk), **args)
+        self._group_args = args
 
     def recognize(self, speech):
         self.reset()

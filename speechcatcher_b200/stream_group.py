@@ -77,6 +77,7 @@ class StreamGroup:
         conf = yaml.safe_load(open(cfg_path)) if cfg_path.exists() else {}
         enc, dec = conf.get("encoder_conf", {}), conf.get("decoder_conf", {})
         self.max_chunk = int(max_chunk)
+        self.max_seconds = float(max_seconds)
         max_frames = int(max_seconds * 25) + 64
         self.cfg = ScConfig(
             d_model=enc.get("output_size", 256), enc_heads=enc.get("attention_heads", 4),

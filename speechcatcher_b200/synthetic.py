@@ -58,11 +58,13 @@ def _linear(rng, out_f, in_f, fan_in=None):
     return w, b
 
 
-def make_state_dict(arch: Arch, seed: int = 0, sharpen: float = 1.0) -> Dict[str, np.ndarray]:
+def make_state_dict(arch: Arch, seed: int = 0, sharpen: float = 1.0, eos_bias: float = 0.0) -> Dict[str, np.ndarray]:
     """Random-init weights keyed like the reference's state_dict.
 
     `sharpen` multiplies `decoder.output_layer.weight` and `ctc.ctc_lo.weight`
-    (SURVEY.md 8(d) "sharpened" weight set: wider decision margins).
+    (SURVEY.md 8(d) "sharpened" weight set: wider decision margins).  `eos_bias` is added to the decoder's
+    output bias of <sos/eos> (the last token): with plain random weights a hypothesis practically never ends, so
+    segment ends inside a file (is_final without finalize_all) would return nothing; ~6-8 makes them end regularly.
     """
     rng = np.random.default_rng(seed)
     D, F, V = arch.d_model, arch.ffn, arch.vocab
@@ -116,6 +118,8 @@ def make_state_dict(arch: Arch, seed: int = 0, sharpen: float = 1.0) -> Dict[str
     if sharpen != 1.0:
         sd["decoder.output_layer.weight"] = sd["decoder.output_layer.weight"] * np.float32(sharpen)
         sd["ctc.ctc_lo.weight"] = sd["ctc.ctc_lo.weight"] * np.float32(sharpen)
+    if eos_bias != 0.0:
+        sd["decoder.output_layer.bias"][V - 1] += np.float32(eos_bias)
     return sd
 
 
@@ -133,7 +137,7 @@ def make_feats_stats(n_mels: int = 80, seed: int = 0):
     }
 
 
-def make_model_dir(path, arch="xl", seed: int = 0, sharpen: float = 1.0) -> Path:
+def make_model_dir(path, arch="xl", seed: int = 0, sharpen: float = 1.0, eos_bias: float = 0.0) -> Path:
     """Write `valid.acc.best.pth`, `config.yaml`, `feats_stats.npz` under `path`."""
     import torch
     import yaml
@@ -141,7 +145,7 @@ def make_model_dir(path, arch="xl", seed: int = 0, sharpen: float = 1.0) -> Path
     a = ARCHS[arch] if isinstance(arch, str) else arch
     path = Path(path)
     path.mkdir(parents=True, exist_ok=True)
-    sd = {k: torch.from_numpy(v.copy()) for k, v in make_state_dict(a, seed, sharpen).items()}
+    sd = {k: torch.from_numpy(v.copy()) for k, v in make_state_dict(a, seed, sharpen, eos_bias).items()}
     torch.save({"model": sd}, path / "valid.acc.best.pth")
     cfg = {
         "encoder_conf": {"output_size": a.d_model, "attention_heads": a.enc_heads,
