@@ -93,3 +93,33 @@ class ScriptedGroup:
     def results(self, s, is_final, finalize_all, token_list=None):
         assert is_final
         return self.streams[s].final_results(finalize_all)
+
+
+class ScriptedLive:
+    """Scripted recogniser for the LIVE session glue: partial texts whose length grows while the
+    chunks carry signal and stalls on silent chunks, so the "length unchanged for N iterations" rule has something to
+    look at.  Same protocol as ScriptedSpeech2Text; results are ESPnet-shaped 5-tuples."""
+
+    def __init__(self, empty_until: int = 2):
+        self.empty_until = empty_until
+        self.reset()
+        self.log = []
+
+    def reset(self):
+        self.voiced = 0
+        self.calls = 0
+
+    def __call__(self, speech, is_final=False, finalize_all=False, always_assemble_hyps=True):
+        x = np.asarray(speech, np.float32)
+        self.log.append((int(x.size), round(float(np.abs(x).sum()), 3), bool(is_final)))
+        self.calls += 1
+        if float(np.abs(x).max(initial=0.0)) > 0.01:
+            self.voiced += 1
+        if self.calls <= self.empty_until:
+            return []
+        toks = [PIECES[(3 * k + self.voiced) % len(PIECES)] for k in range(self.voiced)]
+        text = "".join(toks).replace("▁", " ").strip()
+        res = [(text, toks, list(range(2, 2 + len(toks))), [3 * k for k in range(len(toks))], {})]
+        if is_final:
+            self.voiced = 0        # the next utterance starts short again (the recogniser itself is not reset)
+        return res
