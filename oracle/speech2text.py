@@ -33,6 +33,21 @@ def load_model_dir(model_dir):
     return W, cfg, mean, std
 
 
+def load_token_list(model_dir):
+    """speech2text_streaming.py:97-124: ESPnet vocabulary from the SentencePiece model next to the checkpoint,
+    ["<blank>", SP[0], SP[3..n-1], "<sos/eos>"]; None without a bpe.model (same three search locations)."""
+    d = Path(model_dir)
+    for p in (d / "bpe.model", d.parent.parent / "data/de_token_list/bpe_unigram1024/bpe.model",
+              d / "../data/de_token_list/bpe_unigram1024/bpe.model"):
+        if p.exists():
+            import sentencepiece as spm
+            sp = spm.SentencePieceProcessor()
+            sp.Load(str(p))
+            n = sp.GetPieceSize()
+            return ["<blank>", sp.IdToPiece(0)] + [sp.IdToPiece(i) for i in range(3, n)] + ["<sos/eos>"]
+    return None
+
+
 class OracleSpeech2Text:
     def __init__(self, model_dir, beam_size: int = 5, ctc_weight: float = 0.3, use_bbd: bool = False,
                  trace: Optional[Callable[[dict], None]] = None):
@@ -48,6 +63,7 @@ class OracleSpeech2Text:
                                        use_bbd, trace)
         self.beam_size = beam_size
         self.last_feats: Optional[torch.Tensor] = None
+        self.token_list = load_token_list(model_dir)
         self.reset()
 
     def reset(self):
@@ -79,6 +95,11 @@ class OracleSpeech2Text:
             else:
                 ids = h.yseq[1:1]              # output_index is always 0 here
             ids = [t for t in ids if t not in (0, 1, 1023)]
-            toks = [str(t) for t in ids]
-            results.append((" ".join(toks), toks, list(ids)))
+            if self.token_list is not None:                      # :520-523
+                toks = [self.token_list[t] for t in ids]
+                text = "".join(toks).replace("\u2581", " ").strip()
+            else:                                                # :531-535
+                toks = [str(t) for t in ids]
+                text = " ".join(toks)
+            results.append((text, toks, list(ids)))
         return results

@@ -18,6 +18,7 @@ from typing import List, Optional, Tuple, Union
 import numpy as np
 import torch
 
+from .model_files import load_tokenizer
 from .stream_group import StreamGroup
 
 
@@ -41,16 +42,7 @@ class Speech2TextStreaming:
         self.device, self.dtype = str(group.device), dtype
         self.mean, self.std = group.mean, group.std
         self.win_length, self.hop_length = 400, 160
-        self.token_list = None
-        self.tokenizer = None
-        bpe = self.model_dir / "bpe.model"
-        if bpe.exists():                       # speech2text_streaming.py:100-124
-            import sentencepiece as spm
-            self.tokenizer = spm.SentencePieceProcessor()
-            self.tokenizer.Load(str(bpe))
-            n = self.tokenizer.GetPieceSize()
-            self.token_list = (["<blank>", self.tokenizer.IdToPiece(0)] +
-                               [self.tokenizer.IdToPiece(i) for i in range(3, n)] + ["<sos/eos>"])
+        self.tokenizer, self.token_list = load_tokenizer(self.model_dir)      # speech2text_streaming.py:97-124
         self.beam_state = None
         self.processed_frames = 0
         self.frontend_states = None

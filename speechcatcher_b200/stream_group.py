@@ -17,32 +17,18 @@ import yaml
 
 from . import _lib
 from ._lib import ScConfig, ScPushStats, ScStreamPlan
+from .model_files import find_checkpoint, find_stats, read_stats, state_dict_of
 from .weights import bf16_names, pack_weights
 
 EOS_FILTER_ID = 1023   # hard-coded in the reference's output filter (speech2text_streaming.py:474)
 
 
 def _find_checkpoint(model_dir: Path) -> Path:
-    """Same search order as the reference (speech2text_streaming.py:163-189)."""
-    names = ["valid.acc.best.pth", "valid.acc.ave_6best.pth", "valid.acc.ave.pth", "model.pth", "checkpoint.pth"]
-    paths = [model_dir / n for n in names]
-    for exp in sorted(model_dir.glob("exp/*/")):
-        paths += [exp / n for n in names]
-    for p in paths:
-        if p.exists():
-            return p
-    raise FileNotFoundError(f"No checkpoint found in {model_dir}")
+    return find_checkpoint(model_dir)
 
 
 def load_stats(path: Path):
-    """speechcatcher/model/checkpoint_loader.py:210-237 (fp64 mean / std)."""
-    st = np.load(path)
-    if "mean" in st:
-        return np.asarray(st["mean"], np.float64), np.asarray(st["std"], np.float64)
-    count = st["count"]
-    mean = st["sum"] / count
-    std = np.sqrt(np.maximum(st["sum_square"] / count - mean ** 2, 1e-10))
-    return np.asarray(mean, np.float64), np.asarray(std, np.float64)
+    return read_stats(path)
 
 
 def _frontend_tables():
@@ -71,7 +57,7 @@ class StreamGroup:
             raise ValueError("dtype must be 'float32' (parity mode) or 'bfloat16' (tensor-core mode)")
         self.precision = 0 if dtype == "float32" else 1
         ckpt = torch.load(_find_checkpoint(self.model_dir), map_location="cpu")
-        sd = ckpt.get("model", ckpt)
+        sd = state_dict_of(ckpt)
         vocab = sd["decoder.embed.0.weight"].shape[0]
         cfg_path = self.model_dir / "config.yaml"
         conf = yaml.safe_load(open(cfg_path)) if cfg_path.exists() else {}
@@ -105,10 +91,7 @@ class StreamGroup:
                 _lib.check(self.lib.sc_engine_set_weight(self.handle, k.encode(), C.c_void_p(v.data_ptr()),
                                                          v.numel()), f"set_weight({k})")
             window, mel = _frontend_tables()
-            self.mean = self.std = None
-            stats = self.model_dir / "feats_stats.npz"
-            if stats.exists():
-                self.mean, self.std = load_stats(stats)
+            self.mean, self.std = find_stats(self.model_dir)
             mean_p = self.mean.ctypes.data_as(C.c_void_p) if self.mean is not None else None
             std_p = self.std.ctypes.data_as(C.c_void_p) if self.std is not None else None
             _lib.check(self.lib.sc_engine_set_frontend(self.handle, C.c_void_p(window.data_ptr()),
