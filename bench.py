@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="always run the all-kernel timing pass")
     ap.add_argument("--shards", type=int, default=int(os.environ.get("SCB_BENCH_SHARDS", "4")),
                     help="split the GPU's streams into this many concurrently driven groups (own CUDA stream + host thread)")
+    ap.add_argument("--graph", type=int, default=int(os.environ.get("SCB_BENCH_GRAPH", "0")),
+                    help="CUDA-graph replay (experimental, off by default): 1 = search iteration, 2 = encoder stack, 3 = both")
     ap.add_argument("--lazy", type=int, default=int(os.environ.get("SCB_BENCH_LAZY", "-1")),
                     help="deferred-decode threshold (streams); 0 = strict per-push decoding; -1 = streams - streams/32")
     args = ap.parse_args()
@@ -233,10 +235,16 @@ def main():
         if G == 1:
             g = StreamGroup(md, n_streams=S, device=dev, **kw)
             g.set_option("lazy_threshold", lazy)
-            return None, [g]
-        sg_ = ShardedStreamGroup(md, S, G, device=dev, **kw)
-        sg_.set_option("lazy_threshold", lazy)
-        return sg_, sg_.shards
+            sg_, shards = None, [g]
+        else:
+            sg_ = ShardedStreamGroup(md, S, G, device=dev, **kw)
+            sg_.set_option("lazy_threshold", lazy)
+            shards = sg_.shards
+        if args.graph:
+            for g in shards:
+                g.set_option("graph_decode", args.graph & 1)
+                g.set_option("graph_encoder", (args.graph >> 1) & 1)
+        return sg_, shards
 
     sg, groups = make_groups(args.dtype)
     grp = groups[0]                                   # kernel timing / roofline are taken on shard 0
@@ -433,7 +441,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.dtype == "float32" else "bf16", "data": "synthetic",
                 "config": {"workload": workload, "l2": f"inputs larger than L2 ({S * n_chunks * CHUNK * 4 / 1e6:.0f} MB of waveforms per GPU)",
-                           "shards_per_gpu": G,
+                           "shards_per_gpu": G, "cuda_graphs": args.graph,
                            "decode_scheduling": ("strict: every push drains its decode blocks" if lazy == 0 else
                                                  f"deferred: a push stops iterating below {lazy} active streams; final calls drain"),
                            "decode_steps_per_pass": timed_stats["steps"] // max(1, args.steps),

@@ -113,7 +113,11 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
  * "overlap" = 0/1 (default 1): in deferred mode run a push's frontend/encoder on a second CUDA stream while the
  * caller's stream keeps iterating the search for blocks queued by earlier pushes.
  * "mma_attention" = 0/1: CUDA-core or tensor-core attention in the bf16 mode.  "pdl" = 0/1: programmatic dependent
- * launch of the decode-step kernel chain (process-wide).  "fuse_layernorm" = 0/1: experimental LN-in-epilogue GEMMs. */
+ * launch of the decode-step kernel chain (process-wide).  "fuse_layernorm" = 0/1: experimental LN-in-epilogue GEMMs.
+ * "graph_decode" / "graph_encoder" = 0/1 (default 0, experimental): replay one search iteration / the encoder stack of
+ * a push as an instantiated CUDA graph instead of ~165 / ~7-per-layer individual launches (their arguments are
+ * iteration-invariant); needs a non-default CUDA stream, falls back to plain launches when capture is refused and
+ * while a kernel is being profiled. */
 int sc_engine_set_option(void* handle, const char* name, int32_t value);
 
 /* Live kernel timing with CUDA-event pairs on the launching stream (bench.py roofline and step breakdown).

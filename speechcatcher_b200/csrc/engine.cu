@@ -137,6 +137,19 @@ struct Engine {
   int prof_used = 0;
   double prof_flops = 0.0;          // host-known algorithmic FLOPs of the tagged launches (encoder GEMMs)
 
+  // CUDA graphs (opt-in, "graph_decode" / "graph_encoder"): a search iteration is ~165 kernel launches whose
+  // arguments never change (every length lives in device memory), the encoder stack of a push ~7 launches per layer
+  // whose arguments depend only on the number of blocks.  Capturing them once and replaying the instantiated graph
+  // takes the per-launch driver cost off the host threads (4 shard threads x ~140k launches per pass otherwise).
+  // Replay is skipped while a kernel is being profiled; a failed capture (e.g. on the legacy default stream) falls
+  // back to plain launches for the lifetime of the engine.
+  bool graph_decode = false, graph_encoder = false, graph_failed = false;
+  int graph_warm = 0;                       // plain iterations before the first capture (lazy launch-state set-up)
+  cudaGraphExec_t step_graph = nullptr;
+  int step_graph_launches = 0;
+  struct EncGraph { cudaGraphExec_t exec; int launches; int uses; };
+  std::unordered_map<int, EncGraph> enc_graphs;    // n_blk -> captured encoder stack
+
   explicit Engine(const ScConfig& c) : cfg(c), cap(make_caps(c)), planner(c.n_streams), pending_bound(c.n_streams, 0), last_plan(c.n_streams) {}
 };
 
@@ -414,6 +427,74 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------- CUDA-graph replay of the two launch-heavy parts
+static void drop_graphs(Engine& e) {
+  if (e.step_graph) { cudaGraphExecDestroy(e.step_graph); e.step_graph = nullptr; }
+  for (auto& kv : e.enc_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e.enc_graphs.clear();
+  e.graph_failed = false; e.graph_warm = 0;
+}
+
+// Captures fn(st) into an executable graph.  Returns 0 and *exec == nullptr when capture is not possible here (the
+// caller then launches plainly); a non-zero return is a real launch error.
+template <typename Fn>
+static int capture_graph(Engine& e, cudaStream_t st, Fn fn, cudaGraphExec_t* exec, int* n_launches) {
+  *exec = nullptr;
+  const int before = e.launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError(); e.graph_failed = true; return 0;
+  }
+  const int rc = fn(st);
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &g);
+  *n_launches = e.launches - before;
+  e.launches = before;                                    // captured, not launched
+  if (rc != 0 || ce != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    e.graph_failed = true;
+    return 0;
+  }
+  cudaGraphExec_t x = nullptr;
+  if (cudaGraphInstantiate(&x, g, 0) != cudaSuccess || !x) { cudaGetLastError(); e.graph_failed = true; x = nullptr; }
+  cudaGraphDestroy(g);
+  *exec = x;
+  return 0;
+}
+
+static int decode_step(Engine& e, cudaStream_t st) {
+  if (!e.graph_decode || e.graph_failed || e.prof_tag != 0) return run_decode_step(e, st);
+  if (!e.step_graph) {
+    if (e.graph_warm < 2) { e.graph_warm++; return run_decode_step(e, st); }
+    TRY(capture_graph(e, st, [&](cudaStream_t s) { return run_decode_step(e, s); }, &e.step_graph, &e.step_graph_launches));
+    if (!e.step_graph) return run_decode_step(e, st);
+  }
+  SCB_CUDA_CHECK(cudaGraphLaunch(e.step_graph, st));
+  e.launches += e.step_graph_launches;
+  e.step_seq++;
+  return 0;
+}
+
+static int encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
+  if (!e.graph_encoder || e.graph_failed || e.prof_tag != 0) return run_encoder_layers(e, n_blk, st);
+  auto it = e.enc_graphs.find(n_blk);
+  if (it == e.enc_graphs.end()) {
+    // a block count is captured the second time it is seen (steady-state pushes repeat a handful of counts)
+    e.enc_graphs[n_blk] = Engine::EncGraph{nullptr, 0, 1};
+    return run_encoder_layers(e, n_blk, st);
+  }
+  Engine::EncGraph& g = it->second;
+  if (!g.exec) {
+    if (e.enc_graphs.size() > 64) return run_encoder_layers(e, n_blk, st);      // bounded cache
+    TRY(capture_graph(e, st, [&](cudaStream_t s) { return run_encoder_layers(e, n_blk, s); }, &g.exec, &g.launches));
+    if (!g.exec) return run_encoder_layers(e, n_blk, st);
+  }
+  SCB_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+  e.launches += g.launches;
+  g.uses++;
+  return 0;
+}
+
 }  // namespace scb
 
 using namespace scb;
@@ -499,6 +580,7 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
 int sc_engine_destroy(void* handle) {
   Engine* e = (Engine*)handle;
   if (!e) return SC_OK;
+  drop_graphs(*e);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->h_flag) cudaFreeHost(e->h_flag);
   cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
@@ -772,7 +854,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   if (n_blk > 0) {
 #define e eref
     PE(T_BLOCK_ASM, launch_block_assemble(e.subbuf, k.sub_cap, e.pe, e.d_blk, n_blk, e.addin, e.prev_addin, e.X, D, st));
-    TRY(run_encoder_layers(e, n_blk, st));
+    TRY(encoder_layers(e, n_blk, st));
     PE(T_STITCH, launch_stitch_norm(e.X, e.d_blk, n_blk, e.eaw, e.eab, e.encbuf, k.Tcap, D, tc ? e.encnew16 : nullptr, st));
 #undef e
     e->launches += 4;
@@ -826,7 +908,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     SCB_CUDA_CHECK(cudaEventRecord(e->ev[0], sd));
     // one step is always in flight ahead of the host's view of n_active (kernels of an empty step exit at once)
     for (int i = 0;; ++i) {
-      TRY(run_decode_step(*e, sd));
+      TRY(decode_step(*e, sd));
       steps++;
       SCB_CUDA_CHECK(cudaMemcpyAsync(&e->h_flag[2 * ((i + 1) & 1)], e->sb.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, sd));
       SCB_CUDA_CHECK(cudaEventRecord(e->ev[(i + 1) & 1], sd));
@@ -934,6 +1016,9 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
   if (strcmp(name, "lazy_threshold") == 0) { e->lazy_threshold = value < 0 ? 0 : value; return SC_OK; }
   if (strcmp(name, "overlap") == 0) { e->overlap = value != 0; return SC_OK; }
+  drop_graphs(*e);     // everything below changes which kernels a step launches: captured graphs are stale
+  if (strcmp(name, "graph_decode") == 0) { e->graph_decode = value != 0; return SC_OK; }
+  if (strcmp(name, "graph_encoder") == 0) { e->graph_encoder = value != 0; return SC_OK; }
   if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
   if (strcmp(name, "ln_prologue") == 0) { e->ln_prologue = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
   if (strcmp(name, "fused_ffn") == 0) {
