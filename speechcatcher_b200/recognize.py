@@ -116,13 +116,18 @@ def _engine_of(speech2text, want_streams: int, need_seconds: float, chunk_length
 
 def recognize(speech2text, raw_speech_data, rate, chunk_length=8192, num_processes=1, progress=True, quiet=False,
               status=None, decoder_impl="native", segments: Optional[Sequence[Tuple[int, int]]] = None,
-              segmenter: Optional[Callable] = None, on_step: Optional[Callable[[int, int], None]] = None):
+              segmenter: Optional[Callable] = None, on_step: Optional[Callable[[int, int], None]] = None,
+              shard: Optional[Tuple[int, int]] = None):
     """Transcribe the int16 samples of one file; returns `(complete_text, auxiliary_info)` like speechcatcher.py:414.
 
     speech2text: a `speechcatcher_b200.Speech2TextStreaming` (or a `StreamGroup`).  `segments` overrides the offline
     segmentation (list of (start, end) frame pairs as `segment_speech` returns them); `segmenter(data, rate)` replaces
     `speechcatcher_b200.simple_endpointing.segment_speech`.  `on_step(done_calls, total_calls)` reports progress;
     `status.publish_status(str)` is called like the reference's status thread (every 10 calls).
+
+    `shard=(rank, world)`: one process per GPU; every rank plans the same segments, decodes segments
+    k with k % world == rank on its own engine -- no data-path collective -- and the per-segment results are exchanged
+    once at the end (`sharding.gather_results`, NCCL or gloo), so every rank returns the complete transcript.
     """
     if decoder_impl != "native":
         raise ValueError("the B200 path implements the native decoder only (decoder_impl='native')")
@@ -143,11 +148,12 @@ def recognize(speech2text, raw_speech_data, rate, chunk_length=8192, num_process
     group, streams, token_list = _engine_of(speech2text, max(1, min(int(num_processes), K)),
                                             longest / rate + 2.0, chunk_length)
 
-    total_calls = sum(len(c) for c in calls)
     done_calls = 0
     # per-segment result: [text, tokens, positions, hyp] (batch_recognize_inner_loop's return value)
     seg_out: List[list] = [["", [], [], {}] for _ in range(K)]
-    waiting = list(range(K))
+    mine = list(range(K)) if shard is None else [k for k in range(K) if k % shard[1] == shard[0]]
+    total_calls = sum(len(calls[k]) for k in mine)
+    waiting = list(mine)
     active = {}                                                        # stream id -> [segment, next call index]
     for s in streams:
         group.reset([s])
@@ -179,6 +185,10 @@ def recognize(speech2text, raw_speech_data, rate, chunk_length=8192, num_process
                 on_step(done_calls, total_calls)
             if status is not None and done_calls % 10 == 0:
                 status.publish_status(f"Decoding progress: {done_calls / max(total_calls, 1) * 100.0:.2f}%")
+    if shard is not None and shard[1] > 1:
+        from .sharding import gather_results
+        for k, v in gather_results({k: seg_out[k] for k in mine}).items():
+            seg_out[k] = v
     return merge_paragraphs(seg_out, plan.seconds)
 
 

@@ -56,3 +56,38 @@ def test_shard_range_partitions():
                 lo, hi = shard_range(n, w, r)
                 cover += list(range(lo, hi))
             assert cover == list(range(n))
+
+
+def _recognize_worker(rank, world, port, case_name, q):
+    """Long-file recognition sharded by segment (config 4 on N GPUs): scripted recogniser, gloo gather."""
+    import json
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helpers import GOLDEN
+    from oracle.gen_golden_recognize import case_audio
+    from oracle.scripted_backend import ScriptedGroup
+    from speechcatcher_b200.recognize import recognize
+    case = next(c for c in json.loads((GOLDEN / "recognize.json").read_text())["recognize"] if c["name"] == case_name)
+    group = ScriptedGroup(3)
+    text, aux = recognize(group, case_audio(case["seed"], case["n"]), 16000, chunk_length=case["chunk"],
+                          segments=[tuple(x) for x in case["segments"]], shard=(rank, world))
+    n_calls = sum(len(p) for p in group.pushes)
+    q.put((rank, text == case["text"], aux == case["aux"], n_calls, len(case["calls"])))
+    dist.destroy_process_group()
+
+
+def test_long_file_sharded_by_segment_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_recognize_worker, args=(r, 2, port, "many_segments_chunk4000", q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok_text and ok_aux for _, ok_text, ok_aux, _, _ in got)        # every rank holds the full transcript
+    assert sum(n for _, _, _, n, _ in got) == got[0][4]                        # the calls were split, not duplicated
+    assert all(0 < n < got[0][4] for _, _, _, n, _ in got)
