@@ -38,6 +38,11 @@ CASES = {
     "m_d2_b5_short": ("m_d2", 5, 5000, "noise", "A", False, 1.0, 2),
     "xl_b10_4s": ("xl", 10, 4 * 16000, "noise", "A", False, 1.0, 0),
     "m_b5_8s": ("m", 5, 8 * 16000, "tones", "A", False, 1.0, 0),
+    # EOS-biased weights (synthetic.make_state_dict eos_bias): hypotheses end regularly, so the <eos> branches of the
+    # search (ended hypotheses, results of non-final / intermediate-final calls) carry data
+    "xl_d4_b10_eos": ("xl_d4", 10, 6 * 16000 + 999, "noise", "A", False, 1.0, 2, 7.0),
+    # live-server pattern (speechcatcher_server.py:252-270): utterances finalised mid-stream, NO reset in between
+    "m_d2_b5_eos_live": ("m_d2", 5, 16 * CHUNK, "noise", "L", False, 1.0, 0, 7.0),
 }
 
 
@@ -48,7 +53,7 @@ def chunk_plan(n_samples: int, pattern: str):
     n_chunks = (n_samples + CHUNK - 1) // CHUNK
     for i in range(n_chunks):
         s, e = i * CHUNK, min((i + 1) * CHUNK, n_samples)
-        calls.append((s, e, pattern == "A" and i == n_chunks - 1))
+        calls.append((s, e, (pattern in ("A", "L") and i == n_chunks - 1) or (pattern == "L" and i in (5, 6, 11))))
     if pattern == "B":
         calls.append((n_samples, n_samples, True))
     return calls
@@ -168,11 +173,13 @@ def main(only=None):
     torch.manual_seed(0)
     outdir = REPO / "tests" / "golden"
     outdir.mkdir(parents=True, exist_ok=True)
-    for name, (arch, beam, n, kind, pattern, bbd, sharpen, n_trace) in CASES.items():
+    for name, case in CASES.items():
+        arch, beam, n, kind, pattern, bbd, sharpen, n_trace = case[:8]
+        eos_bias = case[8] if len(case) > 8 else 0.0
         if only and name not in only:
             continue
         with tempfile.TemporaryDirectory() as td:
-            md = make_model_dir(td, arch, seed=0, sharpen=sharpen)
+            md = make_model_dir(td, arch, seed=0, sharpen=sharpen, eos_bias=eos_bias)
             audio = synth_audio(0, n, kind)
             calls = chunk_plan(n, pattern)
             ref, rtrace, tr = run_reference(md, beam, audio, calls, bbd, n_trace)
@@ -183,7 +190,7 @@ def main(only=None):
                 d = float(np.abs(a[k] - b[k]).max())
                 dev["trace_" + k] = max(dev.get("trace_" + k, 0.0), d)
         meta = dict(arch=arch, beam=beam, n_samples=n, kind=kind, pattern=pattern, use_bbd=bbd,
-                    sharpen=sharpen, seed=0, stream=0, calls=calls, chunk=CHUNK,
+                    sharpen=sharpen, eos_bias=eos_bias, seed=0, stream=0, calls=calls, chunk=CHUNK,
                     ref_seconds=tr, oracle_seconds=to, oracle_vs_ref_dev=dev,
                     torch=torch.__version__)
         np.savez_compressed(outdir / f"{name}.npz", **pack(ref, rtrace, meta))

@@ -12,7 +12,7 @@ def main():
     from speechcatcher_b200.synthetic import synth_audio
     for case in GOLDEN_CASES:
         meta, calls, _ = load_golden(case)
-        md = model_dir(meta["arch"], meta["seed"], meta["sharpen"])
+        md = model_dir(meta["arch"], meta["seed"], meta["sharpen"], meta.get("eos_bias", 0.0))
         audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
         mc = max(8192, max(e - s for s, e, _ in meta["calls"]))
         gpu = Speech2TextStreaming(md, beam_size=meta["beam"], device="cuda:0", dtype="bfloat16", use_bbd=meta["use_bbd"], max_chunk=mc)

@@ -19,7 +19,7 @@ def test_bf16_encoder_close_to_reference(case):
     from speechcatcher_b200 import Speech2TextStreaming
     from speechcatcher_b200.synthetic import synth_audio
     meta, calls, _ = load_golden(case)
-    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"])
+    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"], meta.get("eos_bias", 0.0))
     audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
     gpu = Speech2TextStreaming(md, beam_size=meta["beam"], device="cuda:0", dtype="bfloat16", use_bbd=meta["use_bbd"])
     seen = 0
@@ -44,7 +44,7 @@ def test_decoder_rows_are_normalised_log_probs(dtype):
     from speechcatcher_b200 import Speech2TextStreaming
     from speechcatcher_b200.synthetic import synth_audio
     meta, calls, _ = load_golden("xl_d4_b10_cli")
-    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"])
+    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"], meta.get("eos_bias", 0.0))
     audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
     gpu = Speech2TextStreaming(md, beam_size=4, device="cuda:0", dtype=dtype)
     for (s, e, fin) in meta["calls"][:6]:

@@ -52,7 +52,7 @@ def _run_case(case, check_internals=True):
     from speechcatcher_b200 import Speech2TextStreaming
     from speechcatcher_b200.synthetic import synth_audio
     meta, calls, _ = load_golden(case)
-    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"])
+    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"], meta.get("eos_bias", 0.0))
     audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
     max_chunk = max(8192, max(e - s for s, e, _ in meta["calls"]))
     gpu = Speech2TextStreaming(md, beam_size=meta["beam"], ctc_weight=0.3, device="cuda:0", use_bbd=meta["use_bbd"],
@@ -93,7 +93,7 @@ def test_frontend_features_vs_golden():
     from speechcatcher_b200 import Speech2TextStreaming
     from speechcatcher_b200.synthetic import synth_audio
     meta, calls, _ = load_golden("xl_d4_b10_cli")
-    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"])
+    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"], meta.get("eos_bias", 0.0))
     audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
     gpu = Speech2TextStreaming(md, beam_size=meta["beam"], device="cuda:0")
     carry = 0

@@ -97,3 +97,26 @@ def test_planner_reset_and_8192_schedule():
         assert [s[2] for s in seen][:5] == [0, 0, 0, 0, 1]
         lib.sc_planner_reset(p, 1)
     lib.sc_planner_destroy(p)
+
+
+def test_planner_replays_every_golden_call_list():
+    """The reference-generated goldens (incl. the live pattern with mid-stream finals) through the host planner:
+    feature frames and encoder frames per call must be the reference's."""
+    from helpers import GOLDEN_CASES, load_golden
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    for case in GOLDEN_CASES:
+        meta, calls, _ = load_golden(case)
+        p = C.c_void_p()
+        assert lib.sc_planner_create(1, C.byref(p)) == 0
+        try:
+            for ci, ((s, e, fin), g) in enumerate(zip(meta["calls"], calls)):
+                pl = _lib.ScStreamPlan()
+                assert lib.sc_planner_push(p, 0, e - s, int(fin), C.byref(pl)) == 0, lib.sc_last_error()
+                assert bool(pl.called) == (g["feats"] is not None), (case, ci)
+                if g["feats"] is None:
+                    continue
+                assert pl.n_feat == g["feats"].shape[0], (case, ci)
+                assert pl.n_enc_out == (0 if g["enc"] is None else g["enc"].shape[0]), (case, ci)
+        finally:
+            lib.sc_planner_destroy(p)

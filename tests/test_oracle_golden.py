@@ -15,7 +15,7 @@ def test_oracle_replays_reference(case):
     from speechcatcher_b200.synthetic import synth_audio
 
     meta, calls, trace = load_golden(case)
-    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"])
+    md = model_dir(meta["arch"], meta["seed"], meta["sharpen"], meta.get("eos_bias", 0.0))
     audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
     got_trace = []
     o = OracleSpeech2Text(md, beam_size=meta["beam"], ctc_weight=0.3, use_bbd=meta["use_bbd"],
