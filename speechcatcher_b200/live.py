@@ -21,7 +21,7 @@ from __future__ import annotations
 import json
 from queue import Queue
 from threading import Lock
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -78,7 +78,7 @@ class LiveSession:
     """One client's live session (SpeechRecognitionSession without the ffmpeg pipe)."""
 
     def __init__(self, speech2text, audio_format="s16le", finalize_update_iters=7, max_partial_iters=1024,
-                 vosk_output_format=False, real_timestamps=False, reset_on_finalize=False):
+                 vosk_output_format=False, real_timestamps=False, reset_on_finalize=False, partials="reference"):
         if audio_format not in ("s16le", "pcm", "int16"):
             raise NotImplementedError("live sessions take 16 kHz mono s16le PCM; transcoding other container formats "
                                       "(the reference's per-session ffmpeg pipe) is outside the B200 path")
@@ -89,6 +89,13 @@ class LiveSession:
         # fails loudly.  reset_on_finalize=True starts every utterance from a clean stream (a deliberate deviation
         # for long-running connections); False is the reference's behaviour.
         self.reset_on_finalize = reset_on_finalize
+        # partials="reference": non-final calls return what the reference returns -- ended hypotheses with NO committed
+        # tokens, so partial texts are empty and the rule degenerates to "every N result-bearing calls".
+        # partials="best": the partial is the text of the best running hypothesis (a read of the current beam, no
+        # state change), which gives the "length unchanged for N iterations" rule real lengths to look at.
+        if partials not in ("reference", "best"):
+            raise ValueError("partials must be 'reference' or 'best'")
+        self.partials = partials
         self.vosk_sample_rate = self.decoder_sample_rate = 16000
         self.rule = LiveEndpointer(finalize_update_iters, max_partial_iters)
 
@@ -150,6 +157,9 @@ class LiveSession:
         if early is not None:
             return early
         results = self.speech2text(speech=data, is_final=fin)
+        if self.partials == "best" and not fin:
+            best = self.speech2text.get_best_hypothesis()
+            results = [best] if best is not None else []
         return self._finish(results, fin, forced)
 
 
@@ -179,7 +189,10 @@ def process_many(sessions: Sequence[LiveSession], audio_chunks: Sequence) -> Lis
             f._calls_since_reset += 1
             if group.last_plan(f.stream_id).called:
                 f.beam_state = group.beam(f.stream_id)
-                results = group.results(f.stream_id, fin, False, f.token_list)
+                if s.partials == "best" and not fin:
+                    results = group.results(f.stream_id, True, True, f.token_list)[:1]
+                else:
+                    results = group.results(f.stream_id, fin, False, f.token_list)
             else:
                 results = []
             out[i] = s._finish(results, fin, forced)

@@ -91,3 +91,39 @@ def test_process_many_equals_per_session_calls():
         assert got == want, t
     assert group.n_pushes <= 40                        # one batched push per step, not one per session
     assert [r.log for r in group.rec] == [r.log for r in solo_rec]
+
+
+def test_best_hypothesis_partials_drive_the_rule():
+    """partials="best": the rule sees the running hypothesis grow and stall (silence), instead of empty partials."""
+    class Rec:
+        def __init__(self):
+            self.n, self.log = 0, []
+
+        def reset(self):
+            self.n = 0
+
+        def __call__(self, speech, is_final=False, finalize_all=False):
+            self.log.append(bool(is_final))
+            if float(np.abs(np.asarray(speech, np.float32)).max()) > 0.01:
+                self.n += 1
+            out = [("x" * self.n, ["x"] * self.n, [5] * self.n, list(range(self.n)), {})] if is_final else []
+            if is_final:
+                self.n = 0
+            return out
+
+        def get_best_hypothesis(self):
+            return ("x" * self.n, ["x"] * self.n, [5] * self.n, list(range(self.n)), {}) if self.n else None
+
+    loud = (np.ones(4096) * 3000).astype(np.int16)
+    quiet = np.zeros(4096, np.int16) + 1
+    rec = Rec()
+    sess = LiveSession(rec, finalize_update_iters=3, partials="best")
+    outs = [sess.process_audio_chunk(c) for c in [loud] * 5 + [quiet] * 4 + [loud] * 2]
+    assert outs[:5] == ["x", "xx", "xxx", "xxxx", "xxxxx"]
+    assert rec.log.index(True) == 7                    # lengths 1..5, then 5, 5: the last three are equal -> finalise
+    assert outs[7] == "xxxxx.\n" and outs[8] == "" and outs[9] == "x"
+    ref_mode = Rec()
+    sess2 = LiveSession(ref_mode, finalize_update_iters=3)           # reference partials: nothing to observe
+    assert [sess2.process_audio_chunk(c) for c in [loud] * 5] == [""] * 5 and True not in ref_mode.log
+    with pytest.raises(ValueError):
+        LiveSession(rec, partials="all")
