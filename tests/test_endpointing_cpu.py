@@ -62,7 +62,8 @@ def test_frame_count_and_filterbank_bins_match_oracle():
     from speechcatcher_b200.simple_endpointing import num_frames
     for n in (1, 399, 400, 401, 559, 560, 561, 16000, 960001, 57600000):
         assert num_frames(n) == psf_n_frames(n), n
-        assert num_frames(n) == psf_logfbank(np.zeros(min(n, 2000), np.int16)).shape[0] or n > 2000
+        if n <= 16000:
+            assert num_frames(n) == psf_logfbank(np.ones(n, np.int16)).shape[0], n
     bins = (C.c_double * 28)()
     _lib.check(_lib.load().sc_segment_filterbank_bins(bins))
     assert list(bins) == psf_filterbank_bins().tolist()
