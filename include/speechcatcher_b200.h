@@ -114,6 +114,8 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
  * caller's stream keeps iterating the search for blocks queued by earlier pushes.
  * "mma_attention" = 0/1: CUDA-core or tensor-core attention in the bf16 mode.  "pdl" = 0/1: programmatic dependent
  * launch of the decode-step kernel chain (process-wide).  "fuse_layernorm" = 0/1: experimental LN-in-epilogue GEMMs.
+ * "ln_prologue" / "ln_prologue_decoder" = 0/1 (default 0): compute LayerNorm inside the consuming GEMM (everywhere /
+ * decode step only; the latter has not run on a device yet).
  * "graph_decode" / "graph_encoder" = 0/1 (default 0, experimental): replay one search iteration / the encoder stack of
  * a push as an instantiated CUDA graph instead of ~165 / ~7-per-layer individual launches (their arguments are
  * iteration-invariant); needs a non-default CUDA stream, falls back to plain launches when capture is refused and

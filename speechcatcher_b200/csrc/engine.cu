@@ -109,6 +109,7 @@ struct Engine {
   bool fuse_ln_dec = false;         // same for the decoder step (self-O -> norm2, cross-O -> norm3, FFN2 -> next norm1)
   // bf16 mode: compute every LayerNorm inside the GEMM that consumes it (LayerNorm-prologue GEMM, K = 256)
   bool ln_prologue = false;
+  bool ln_prologue_dec = false;     // same, decode step only (QKV, cross-Q and output GEMMs; small M, untested on device)
   // bf16 mode: encoder FFN1 -> ReLU -> FFN2 as one kernel with the hidden activation kept on the SM
   // (kernels_ffn_fused.cu); used when a launch has at least `fused_ffn_min_rows` rows
   bool fused_ffn = false;
@@ -299,7 +300,8 @@ static int ln_linear(Engine& e, int ln_tag, int gemm_tag, bool dec, const float*
                      const float* ln_b, int rows_max, const Lin& l, cudaStream_t st) {
   const bool tc = e.cfg.precision == 1;
   const bool fuse = dec ? e.fuse_ln_dec : e.fuse_ln;
-  if (tc && e.ln_prologue && !fuse) {
+  const bool lnp = e.ln_prologue || (dec && e.ln_prologue_dec);
+  if (tc && lnp && !fuse) {
     e.launches++;
     PROFX(gemm_tag, dec, launch_gemm_bf16_lnA(X, ldx, ln_w, ln_b, l.W16, l.bias, l.C, l.ldc, l.C16, l.ldc, l.M, l.N, l.relu,
                                              l.n_rows_dev, st));
@@ -570,6 +572,10 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     e->fused_ffn_dec = e->fused_ffn && !(ffd && strcmp(ffd, "0") == 0);
     const char* fsp = getenv("SCB_FFN_SPLITS");
     if (fsp) e->ffn_splits = atoi(fsp);
+    const char* gr = getenv("SCB_GRAPH");    // bit 0: replay the search iteration as a CUDA graph, bit 1: the encoder stack
+    if (gr) { e->graph_decode = (atoi(gr) & 1) != 0; e->graph_encoder = (atoi(gr) & 2) != 0; }
+    const char* lpd = getenv("SCB_LN_PROLOGUE_DEC");
+    e->ln_prologue_dec = cfg->precision == 1 && cfg->d_model == 256 && lpd && strcmp(lpd, "1") == 0;
     const char* pdl = getenv("SCB_PDL");     // programmatic dependent launch of the decode-step kernel chain (default on)
     g_use_pdl = !(pdl && strcmp(pdl, "0") == 0);
   }
@@ -1021,6 +1027,7 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (strcmp(name, "graph_encoder") == 0) { e->graph_encoder = value != 0; return SC_OK; }
   if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
   if (strcmp(name, "ln_prologue") == 0) { e->ln_prologue = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
+  if (strcmp(name, "ln_prologue_decoder") == 0) { e->ln_prologue_dec = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
   if (strcmp(name, "fused_ffn") == 0) {
     e->fused_ffn = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256 && e->cfg.ffn % 128 == 0;
     return SC_OK;
