@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of the next round (about 4-5 minutes of box time):
+#   /usr/local/graft/bin/gpurun --timeout 420 -- 'bash scripts/round2_first_call.sh'
+# 1. the whole GPU suite on the current state, 2. parity + capture check of the opt-in CUDA-graph replay (never run on a
+# device in round 1), 3. the throughput effect of graphs / decoder LayerNorm-prologue, each against the plain baseline.
+# Everything lands in gpurun_out/r2_first/.
+mkdir -p gpurun_out/r2_first
+O=gpurun_out/r2_first
+timeout 150 python -m pytest tests -q -m gpu -x > $O/tests_gpu.txt 2>&1; echo "tests_rc=$?" > $O/rc.txt
+timeout 60 python tests/graph_replay_ab.py > $O/graph_ab.txt 2>&1; echo "graph_ab_rc=$?" >> $O/rc.txt
+SCB_GRAPH=3 timeout 60 python -m pytest tests/test_gpu_multistream.py -q -m gpu -k "sharded or batch_invariance" > $O/graph_sharded_tests.txt 2>&1; echo "graph_sharded_rc=$?" >> $O/rc.txt
+for g in 0 1 2 3; do
+  echo "graph=$g: $(SCB_BENCH_GRAPH=$g timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
+done
+echo "ln_prologue_decoder=1: $(SCB_LN_PROLOGUE_DEC=1 timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
+echo "graph=3 shards=8: $(SCB_BENCH_GRAPH=3 SCB_BENCH_SHARDS=8 timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
+echo "graph=3 shards=2: $(SCB_BENCH_GRAPH=3 SCB_BENCH_SHARDS=2 timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
+cat $O/rc.txt $O/bench_graph.txt
