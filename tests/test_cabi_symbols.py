@@ -33,3 +33,35 @@ def test_missing_cuda_fails_loudly():
     from speechcatcher_b200 import StreamGroup
     with pytest.raises(RuntimeError):
         StreamGroup(model_dir("m_d2"), n_streams=1)
+
+
+def test_workspace_of_every_baseline_config_fits_one_b200():
+    """Host-only arithmetic (no GPU call): the caller-owned workspace of each BASELINE.json configuration, per GPU,
+    against 180 GB of HBM3e."""
+    import ctypes as C
+    from speechcatcher_b200 import _lib
+    from speechcatcher_b200._lib import ScConfig
+    lib = _lib.load()
+
+    def gib(**kw):
+        base = dict(d_model=256, enc_heads=8, enc_layers=30, dec_heads=8, dec_layers=14, vocab=1024, ffn=2048,
+                    n_streams=256, beam=10, max_chunk=8192, max_frames=int(61 * 25) + 64, use_bbd=0, precision=1,
+                    ctc_weight=0.3)
+        base.update(kw)
+        n = C.c_size_t()
+        _lib.check(lib.sc_engine_workspace_bytes(C.byref(ScConfig(**base)), C.byref(n)))
+        return n.value / 2 ** 30
+
+    xl_bf16, xl_f32 = gib(), gib(precision=0)
+    assert 20 < xl_bf16 < 40 and xl_bf16 < xl_f32 < 70              # config 2: bf16 KV caches halve the big buffers
+    assert abs(4 * gib(n_streams=64) - xl_bf16) < 1.0               # 4 shards of 64 streams = one group of 256
+    assert gib(enc_layers=18, dec_layers=8) < xl_bf16               # config 3 (L, 256 streams per GPU)
+    assert gib(enc_layers=18, dec_layers=8, n_streams=60, max_frames=185 * 25 + 64) < 20   # config 4: 60 segments <= 180 s
+    assert gib(beam=20) < 80                                         # config 5
+    for bad in (dict(beam=21), dict(d_model=512), dict(n_streams=0)):
+        n = C.c_size_t()
+        base = dict(d_model=256, enc_heads=8, enc_layers=30, dec_heads=8, dec_layers=14, vocab=1024, ffn=2048,
+                    n_streams=256, beam=10, max_chunk=8192, max_frames=1589, use_bbd=0, precision=1, ctc_weight=0.3)
+        base.update(bad)
+        assert lib.sc_engine_workspace_bytes(C.byref(ScConfig(**base)), C.byref(n)) != 0
+        assert lib.sc_last_error()
