@@ -22,6 +22,25 @@ from .model_files import load_tokenizer
 from .stream_group import StreamGroup
 
 
+class _SearchView:
+    """What callers read off `speech2text.beam_search` in the reference (beam_search.py:266-327, 845-924)."""
+
+    def __init__(self, facade):
+        self._f = facade
+        self.beam_size, self.use_bbd = facade.beam_size, facade.use_bbd
+        self.weights = {"decoder": 1.0 - facade.ctc_weight, "ctc": facade.ctc_weight}
+        self.scorers = {"decoder": "libscb200 decoder step (KV-cached)", "ctc": "libscb200 CTC prefix scorer"}
+        self.block_size, self.hop_size, self.look_ahead, self.max_length = 40, 16, 16, 500
+        self.sos = self.eos = facade.group.cfg.vocab - 1
+
+    @property
+    def process_idx(self):
+        return self._f.beam_state[3] if self._f.beam_state is not None else 0
+
+    def reset(self):
+        self._f.reset()
+
+
 class Speech2TextStreaming:
     def __init__(self, model_dir: Union[str, Path] = None, beam_size: int = 5, ctc_weight: float = 0.3,
                  device: str = "cuda", dtype: str = "float32", use_bbd: bool = False,
@@ -43,6 +62,11 @@ class Speech2TextStreaming:
         self.mean, self.std = group.mean, group.std
         self.win_length, self.hop_length = 400, 160
         self.tokenizer, self.token_list = load_tokenizer(self.model_dir)      # speech2text_streaming.py:97-124
+        # attributes the reference's callers / tests read (speech2text_streaming.py:62, 143-150): there is no
+        # torch.nn.Module and no Python search object here, so `model` is the engine that holds the weights and
+        # `beam_search` a read-only view of the search configuration
+        self.model = group
+        self.beam_search = _SearchView(self)
         self.beam_state = None
         self.processed_frames = 0
         self.frontend_states = None
@@ -92,7 +116,7 @@ class Speech2TextStreaming:
         args = {**self._group_args, "n_streams": max(n_streams, g.n_streams),
                 "max_seconds": max(max_seconds, g.max_seconds)}
         g.close()
-        self.group = StreamGroup(max_chunk=max(max_chunk, g.max_chunk), **args)
+        self.group = self.model = StreamGroup(max_chunk=max(max_chunk, g.max_chunk), **args)
         self._group_args = args
 
     def recognize(self, speech):

@@ -15,11 +15,12 @@ def test_facade_surface_and_tuple_shape():
     md = model_dir("m_d2")
     s2t = create_streaming_interface(md, beam_size=5, device="cuda")
     assert isinstance(s2t, Speech2TextStreaming)
-    for attr in ("beam_size", "beam_state", "frontend_states", "processed_frames", "mean", "std", "token_list",
+    for attr in ("model", "beam_search", "beam_size", "beam_state", "frontend_states", "processed_frames", "mean", "std", "token_list",
                  "win_length", "hop_length", "reset", "recognize", "recognize_stream", "n_best_hypotheses",
                  "get_best_hypothesis"):
         assert hasattr(s2t, attr), attr
     assert s2t.n_best_hypotheses == 5 and s2t.win_length == 400 and s2t.hop_length == 160
+    assert s2t.model is not None and s2t.beam_search.use_bbd is False and s2t.beam_search.weights["ctc"] == 0.3
     audio = synth_audio(7, 3 * 16000 + 99)
     chunks = [audio[i:i + 8192] for i in range(0, len(audio), 8192)]
     # recognize_stream: last chunk is_final, finalize_all False -> only hypotheses ending in <eos> (id 1023) are returned
