@@ -92,6 +92,14 @@ int sc_engine_reset(void* handle, const int32_t* streams, int32_t n, void* strea
 int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const int32_t* streams,
                    const int32_t* n_samples, const int32_t* is_final, int32_t n, void* stream,
                    ScPushStats* stats);
+/* Same for pre-computed feature frames (the 2-D / 3-D input of Speech2TextStreaming.__call__,
+ * speech2text_streaming.py:438-450): feats_dev[i*ld_feats ...] holds n_frames[i] rows of 80 floats for stream
+ * streams[i], already normalised by the caller ((x - mean) / std for 2-D input, untouched for 3-D input, like the
+ * reference); the frontend is skipped and process_block runs for every listed stream.  At most
+ * (max_chunk + 400) / 160 + 6 frames per stream and push. */
+int sc_engine_push_features(void* handle, const float* feats_dev, int32_t ld_feats, const int32_t* streams,
+                            const int32_t* n_frames, const int32_t* is_final, int32_t n, void* stream,
+                            ScPushStats* stats);
 /* Current beam of one stream (beam_state.hypotheses): copies to host buffers and synchronises.
  * yseq/xpos: [beam][max_len] int32, score: [beam] fp64. */
 int sc_engine_read_beam(void* handle, int32_t stream_id, int32_t max_len, int32_t* n_hyp, int32_t* len,
@@ -139,6 +147,7 @@ int sc_planner_create(int32_t n_streams, void** planner);
 int sc_planner_destroy(void* planner);
 int sc_planner_reset(void* planner, int32_t stream_id);
 int sc_planner_push(void* planner, int32_t stream_id, int32_t n_samples, int32_t is_final, ScStreamPlan* plan);
+int sc_planner_push_features(void* planner, int32_t stream_id, int32_t n_frames, int32_t is_final, ScStreamPlan* plan);
 
 /* ---- offline segmentation of long files (replaces speechcatcher/simple_endpointing.py) ---- */
 /* Parameters of the cut-point search = the reference's BeamSearch constructor (simple_endpointing.py:23-34);

@@ -77,7 +77,16 @@ class OracleSpeech2Text:
         if isinstance(speech, np.ndarray):
             speech = torch.from_numpy(speech)
         speech = speech.to(torch.float32)
-        feats = self.frontend(speech, is_final)
+        if speech.dim() == 1:
+            feats = self.frontend(speech, is_final)
+        elif speech.dim() == 2:                      # :438-446 pre-computed features: numpy normalisation, no frontend
+            f = speech.numpy()
+            if self.frontend.mean is not None:
+                f = (f - self.frontend.mean) / self.frontend.std
+            feats = torch.from_numpy(np.asarray(f)).to(torch.float32)
+        else:                                        # :447-450 already batched (1, T, 80): used as is
+            assert speech.size(0) == 1
+            feats = speech[0]
         self.last_feats = feats
         if feats is None:
             return []

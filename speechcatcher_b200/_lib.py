@@ -47,6 +47,7 @@ SYMBOLS = {
     "sc_engine_finalize": (C.c_int, [_vp]),
     "sc_engine_reset": (C.c_int, [_vp, _vp, _i32, _vp]),
     "sc_engine_push": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, C.POINTER(ScPushStats)]),
+    "sc_engine_push_features": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, C.POINTER(ScPushStats)]),
     "sc_engine_read_beam": (C.c_int, [_vp, _i32, _i32, _pi32, _pi32, _pi32, _vp, _vp, _vp, _vp]),
     "sc_engine_read_all": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sc_engine_token_capacity": (C.c_int, [_vp, _pi32]),
@@ -59,6 +60,7 @@ SYMBOLS = {
     "sc_planner_destroy": (C.c_int, [_vp]),
     "sc_planner_reset": (C.c_int, [_vp, _i32]),
     "sc_planner_push": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(ScStreamPlan)]),
+    "sc_planner_push_features": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(ScStreamPlan)]),
     "sc_segment_num_frames": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),
     "sc_segment_filterbank_bins": (C.c_int, [_pd]),
     "sc_segment_energy": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_double, _vp]),

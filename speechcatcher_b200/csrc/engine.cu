@@ -692,8 +692,11 @@ int sc_engine_reset(void* handle, const int32_t* streams, int32_t n, void* strea
   return SC_OK;
 }
 
-int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const int32_t* streams,
-                   const int32_t* n_samples, const int32_t* is_final, int32_t n, void* stream, ScPushStats* stats) {
+// One push of n streams.  feats_dev == nullptr: waveform chunks (n_samples = samples per stream).  feats_dev != nullptr:
+// pre-computed, already normalised feature frames [i][n_samples[i]][80] with row pitch ld_wave floats per stream
+// (speech2text_streaming.py:438-450): the frontend is skipped and the frames are copied behind each stream's carried ones.
+static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const float* feats_dev, const int32_t* streams,
+                     const int32_t* n_samples, const int32_t* is_final, int32_t n, void* stream, ScPushStats* stats) {
   Engine* e = (Engine*)handle;
   if (!e || !e->finalized) { set_last_error("engine not finalized"); return SC_ERR_STATE; }
   const ScConfig& c = e->cfg; const Caps& k = e->cap;
@@ -715,13 +718,23 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
   for (int i = 0; i < n; ++i) {
     const int s = streams[i];
     if (s < 0 || s >= S) { set_last_error("bad stream id %d", s); return SC_ERR_ARG; }
-    if (n_samples[i] < 0 || n_samples[i] > c.max_chunk) {
-      set_last_error("stream %d: chunk of %d samples exceeds max_chunk %d", s, n_samples[i], c.max_chunk);
-      return SC_ERR_CAPACITY;
+    if (feats_dev) {
+      if (n_samples[i] < 0 || n_samples[i] > k.feat_cap - 12) {
+        set_last_error("stream %d: %d feature frames exceed the per-push capacity %d (raise max_chunk)", s, n_samples[i],
+                       k.feat_cap - 12);
+        return SC_ERR_CAPACITY;
+      }
+      if ((int64_t)n_samples[i] * 80 > ld_wave) { set_last_error("feature row pitch too small"); return SC_ERR_ARG; }
+    } else {
+      if (n_samples[i] < 0 || n_samples[i] > c.max_chunk) {
+        set_last_error("stream %d: chunk of %d samples exceeds max_chunk %d", s, n_samples[i], c.max_chunk);
+        return SC_ERR_CAPACITY;
+      }
+      if (n_samples[i] > ld_wave) { set_last_error("ld_wave too small"); return SC_ERR_ARG; }
     }
-    if (n_samples[i] > ld_wave) { set_last_error("ld_wave too small"); return SC_ERR_ARG; }
     const StreamHost before = e->planner.state(s);
-    plans[i] = e->planner.push(s, n_samples[i], is_final[i] != 0);
+    plans[i] = feats_dev ? e->planner.push_features(s, n_samples[i], is_final[i] != 0)
+                         : e->planner.push(s, n_samples[i], is_final[i] != 0);
     StreamPush& p = plans[i];
     if (p.error) {
       set_last_error("stream %d: input shape the reference cannot process (code %d)", s, p.error);
@@ -819,11 +832,24 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
 #define e eref
   const bool petot = prof_on(e, T_ENC_TOTAL, false);
   if (petot) prof_mark(e, T_ENC_TOTAL, st, true);
-  PE(T_FRONTEND, launch_frontend(wave_dev, ld_wave, e.wbuf, 512, e.d_fd, n_fd, frame_base, e.has_stats ? e.d_mean : nullptr,
-                      e.has_stats ? e.d_std : nullptr, e.featbuf, k.feat_cap, st));
+  if (!feats_dev) {
+    PE(T_FRONTEND, launch_frontend(wave_dev, ld_wave, e.wbuf, 512, e.d_fd, n_fd, frame_base, e.has_stats ? e.d_mean : nullptr,
+                        e.has_stats ? e.d_std : nullptr, e.featbuf, k.feat_cap, st));
+  }
 #undef e
-  TRY(launch_wavebuf_update(wave_dev, ld_wave, e->wbuf, 512, e->d_fd, n_fd_all, st));
-  e->launches += 2;
+  if (!feats_dev) {
+    TRY(launch_wavebuf_update(wave_dev, ld_wave, e->wbuf, 512, e->d_fd, n_fd_all, st));
+    e->launches += 2;
+  } else {
+    for (int i = 0; i < n; ++i) {                       // feature frames go behind the stream's carried frames
+      const StreamPush& p = plans[i];
+      if (p.n_feat <= 0) continue;
+      n_feat_total += p.n_feat;
+      SCB_CUDA_CHECK(cudaMemcpyAsync(e->featbuf + ((size_t)streams[i] * k.feat_cap + p.fd.feat_off) * 80,
+                                     feats_dev + (size_t)i * ld_wave, sizeof(float) * 80 * (size_t)p.n_feat,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
+  }
   if (use_enc_stream) {                             // later work on the caller's stream (e.g. the next H2D into wave_dev)
     SCB_CUDA_CHECK(cudaEventRecord(e->ev_wave, st));   // is ordered after the waveforms have been consumed
     SCB_CUDA_CHECK(cudaStreamWaitEvent(sd, e->ev_wave, 0));
@@ -956,6 +982,17 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
     stats->n_decode_steps = steps; stats->n_kernel_launches = e->launches;
   }
   return SC_OK;
+}
+
+int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const int32_t* streams,
+                   const int32_t* n_samples, const int32_t* is_final, int32_t n, void* stream, ScPushStats* stats) {
+  return push_impl(handle, wave_dev, ld_wave, nullptr, streams, n_samples, is_final, n, stream, stats);
+}
+
+int sc_engine_push_features(void* handle, const float* feats_dev, int32_t ld_feats, const int32_t* streams,
+                            const int32_t* n_frames, const int32_t* is_final, int32_t n, void* stream, ScPushStats* stats) {
+  if (!feats_dev) { set_last_error("push_features: null feature pointer"); return SC_ERR_ARG; }
+  return push_impl(handle, nullptr, ld_feats, feats_dev, streams, n_frames, is_final, n, stream, stats);
 }
 
 int sc_engine_read_beam(void* handle, int32_t s, int32_t max_len, int32_t* n_hyp, int32_t* len, int32_t* process_idx,
@@ -1093,9 +1130,16 @@ int sc_planner_create(int32_t n_streams, void** planner) {
 }
 int sc_planner_destroy(void* planner) { delete (Planner*)planner; return SC_OK; }
 int sc_planner_reset(void* planner, int32_t s) { ((Planner*)planner)->reset(s); return SC_OK; }
+static int planner_push_any(void* planner, int32_t s, int32_t count, int32_t is_final, int features, ScStreamPlan* plan);
 int sc_planner_push(void* planner, int32_t s, int32_t n_samples, int32_t is_final, ScStreamPlan* plan) {
+  return planner_push_any(planner, s, n_samples, is_final, 0, plan);
+}
+int sc_planner_push_features(void* planner, int32_t s, int32_t n_frames, int32_t is_final, ScStreamPlan* plan) {
+  return planner_push_any(planner, s, n_frames, is_final, 1, plan);
+}
+static int planner_push_any(void* planner, int32_t s, int32_t count, int32_t is_final, int features, ScStreamPlan* plan) {
   Planner* p = (Planner*)planner;
-  StreamPush r = p->push(s, n_samples, is_final != 0);
+  StreamPush r = features ? p->push_features(s, count, is_final != 0) : p->push(s, count, is_final != 0);
   if (r.error) { set_last_error("planner: unsupported shape (code %d)", r.error); return SC_ERR_STATE; }
   plan->called = r.called; plan->n_feat = r.n_feat; plan->n_sub = r.run_sub ? r.sd.t2 : 0; plan->n_blocks = (int)r.blocks.size();
   plan->n_enc_out = r.n_enc_out; plan->enc_len = p->state(s).enc_len; plan->n_decode_blocks = (int)r.dq_T.size();

@@ -87,8 +87,29 @@ class Planner {
     p.fd.emit0 = e0; p.fd.emit1 = e1;
     p.called = true;
     p.n_feat = e1 - e0;
-    const int carry = h.enc_state ? h.feat_carry : 0;
-    p.fd.feat_off = carry;
+    p.fd.feat_off = h.enc_state ? h.feat_carry : 0;
+    encoder_and_trigger(h, p, s, is_final);
+    return p;
+  }
+
+  // Pre-computed features instead of a waveform (speech2text_streaming.py:438-450: the frontend is skipped and
+  // process_block is always called): `n_feat` new feature frames go to featbuf[s] at row `feat_off`.
+  StreamPush push_features(int s, int n_feat, bool is_final) {
+    StreamHost& h = hs_[s];
+    StreamPush p;
+    p.has_fd = false;
+    p.called = true;
+    p.n_feat = n_feat;
+    p.fd.stream = s;
+    p.fd.feat_off = h.enc_state ? h.feat_carry : 0;
+    encoder_and_trigger(h, p, s, is_final);
+    return p;
+  }
+
+ private:
+  // everything after the frontend: encoder buffering / blocks and the decode-block trigger
+  void encoder_and_trigger(StreamHost& h, StreamPush& p, int s, bool is_final) {
+    const int carry = p.fd.feat_off;
     // ---------------- encoder (contextual_block_transformer_encoder.py:278-419)
     if (p.n_feat >= 3) {                              // beam_search.py:551: skip the encoder otherwise
       const int T = carry + p.n_feat;
@@ -105,7 +126,7 @@ class Planner {
           h.feat_carry = n_res; h.enc_state = true;
         }
       } else {
-        if (T < 7) { p.error = 1; return p; }        // conv2d would raise in the reference
+        if (T < 7) { p.error = 1; return; }        // conv2d would raise in the reference
         t_in = T; t2 = conv_out_len(T);
         h.feat_carry = 0;
       }
@@ -120,7 +141,7 @@ class Planner {
           if (!short_path) {
             bn = (totf - (kBlock - kHopB - kLook) - kLook + kHopB - 1) / kHopB;      // ceil((tot-24)/16)
             if (totf - 24 <= 0) bn = 0;
-            if (bn <= 0) { p.error = 2; return p; }   // the reference indexes an empty block tensor here
+            if (bn <= 0) { p.error = 2; return; }   // the reference indexes an empty block tensor here
           }
           h.sub_n = 0;
         } else {
@@ -175,10 +196,8 @@ class Planner {
       h.processed_block++;
     }
     if (is_final && h.enc_len > 0) { p.dq_T.push_back(h.enc_len); p.dq_final.push_back(1); }
-    return p;
   }
 
- private:
   std::vector<StreamHost> hs_;
 };
 

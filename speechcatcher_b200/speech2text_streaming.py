@@ -84,8 +84,10 @@ class Speech2TextStreaming:
         if isinstance(speech, torch.Tensor):
             speech = speech.detach().cpu().numpy()
         speech = np.asarray(speech, np.float32)
+        if speech.ndim in (2, 3):
+            return self._call_features(speech, is_final, finalize_all)
         if speech.ndim != 1:
-            raise NotImplementedError("the B200 path takes raw 1-D waveforms (pre-computed features are not supported)")
+            raise ValueError(f"speech must be a 1-D waveform, 2-D features or 3-D batched features, got {speech.ndim}-D")
         if len(speech) > self.group.max_chunk:
             # the engine's buffers are sized for a maximum chunk; a facade that owns its engine re-creates it with a
             # larger capacity, which is only possible while the stream holds no state (right after reset)
@@ -99,6 +101,25 @@ class Speech2TextStreaming:
         plan = self.group.last_plan(self.stream_id)
         if not plan.called:
             return []                           # speech2text_streaming.py:431-433
+        self.beam_state = self.group.beam(self.stream_id)
+        return self.group.results(self.stream_id, is_final, finalize_all, self.token_list)
+
+    def _call_features(self, feats: np.ndarray, is_final: bool, finalize_all: bool):
+        """Pre-computed features (speech2text_streaming.py:438-450): 2-D input is normalised with the global statistics
+        in numpy like the reference, 3-D (1, T, 80) input is used as it is; the frontend is skipped."""
+        if feats.ndim == 3:
+            if feats.shape[0] != 1:
+                raise ValueError("batched feature input must have batch size 1 (one stream per facade)")
+            feats = feats[0]
+        elif self.mean is not None and self.std is not None:
+            feats = ((feats - self.mean) / self.std).astype(np.float32)
+        if len(feats) > self.group.max_feature_frames():
+            if not self._owns_group or self._calls_since_reset > 0:
+                raise ValueError(f"{len(feats)} feature frames exceed the engine capacity "
+                                 f"{self.group.max_feature_frames()} per call; construct with a larger max_chunk")
+            self.ensure_capacity(max_chunk=len(feats) * 160)
+        self._calls_since_reset += 1
+        self.group.push_features([self.stream_id], [feats], [is_final])
         self.beam_state = self.group.beam(self.stream_id)
         return self.group.results(self.stream_id, is_final, finalize_all, self.token_list)
 

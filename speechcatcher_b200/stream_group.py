@@ -142,6 +142,40 @@ class StreamGroup:
             self._wave_dev.copy_(host, non_blocking=True)
         return self.push_device(ids, self._wave_dev, lens, fin)
 
+    def max_feature_frames(self) -> int:
+        """Feature frames one stream may push per call (sc_engine_push_features)."""
+        return (self.max_chunk + 400) // 160 + 6
+
+    def push_features(self, streams: Sequence[int], feats: Sequence[np.ndarray], is_final: Sequence[bool]) -> ScPushStats:
+        """Pre-computed, already normalised feature frames ([n_i, 80] float32 per listed stream) instead of waveforms:
+        the 2-D / 3-D input mode of the reference's __call__ (speech2text_streaming.py:438-450)."""
+        n = len(streams)
+        ids = np.ascontiguousarray(streams, np.int32)
+        counts = np.asarray([len(f) for f in feats], np.int32)
+        fin = np.asarray([1 if f else 0 for f in is_final], np.int32)
+        if n and counts.max() > self.max_feature_frames():
+            raise ValueError(f"{int(counts.max())} feature frames exceed the per-push capacity "
+                             f"{self.max_feature_frames()} of this engine; construct with a larger max_chunk")
+        ld = max(1, int(counts.max()) if n else 1) * 80
+        host = torch.zeros(max(n, 1), ld, dtype=torch.float32)
+        for i, f in enumerate(feats):
+            f = np.ascontiguousarray(f, np.float32)
+            if f.ndim != 2 or f.shape[1] != 80:
+                raise ValueError(f"features must be [frames, 80], got {f.shape}")
+            if len(f):
+                host[i, : f.size] = torch.from_numpy(f.reshape(-1))
+        st = ScPushStats()
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self._feat_dev = host.to(self.device)          # kept alive until the next call (the copy is asynchronous)
+            rc = self.lib.sc_engine_push_features(self.handle, C.c_void_p(self._feat_dev.data_ptr()), ld,
+                                                  ids.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                                  fin.ctypes.data_as(C.c_void_p), n,
+                                                  C.c_void_p(self.stream.cuda_stream), C.byref(st))
+        _lib.check(rc, "push_features")
+        self.last_stats = st
+        self.total_launches += st.n_kernel_launches
+        return st
+
     def push_batch(self, ids: np.ndarray, wave_host: torch.Tensor, lens: np.ndarray, fin: np.ndarray) -> ScPushStats:
         """Host waveforms as one [n_streams, L] float32 tensor (row s = stream s); one pinned H2D copy."""
         L = wave_host.shape[1]

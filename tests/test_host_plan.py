@@ -120,3 +120,48 @@ def test_planner_replays_every_golden_call_list():
                 assert pl.n_enc_out == (0 if g["enc"] is None else g["enc"].shape[0]), (case, ci)
         finally:
             lib.sc_planner_destroy(p)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_planner_feature_mode_matches_oracle_shapes(seed):
+    """Pre-computed feature input (speech2text_streaming.py:438-450): no frontend, process_block on every call."""
+    from oracle.encoder import EncoderOracle
+    from oracle.speech2text import load_model_dir
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    W, _, _, _ = load_model_dir(model_dir("m_d2"))
+    rng = np.random.default_rng(100 + seed)
+    n_calls = int(rng.integers(3, 12))
+    frames = [int(rng.choice([100, 100, 64, 37, 9, 2, 1, 0, 48])) for _ in range(n_calls)]
+    finals = [bool(rng.random() < 0.15) for _ in range(n_calls)]
+    finals[-1] = True
+    enc = EncoderOracle(W, 2, 4)
+    enc_len, processed_block, want = 0, 0, []
+    try:
+        for n, fin in zip(frames, finals):
+            n_enc = 0
+            if n >= 3:
+                n_enc = enc(torch.zeros(1, n, 80), fin).size(1)
+            enc_len += n_enc
+            nd, last_T = 0, 0
+            while enc_len > 0 and 24 + 16 * processed_block < enc_len:
+                last_T = 24 + 16 * processed_block
+                nd += 1
+                processed_block += 1
+            if fin and enc_len > 0:
+                nd += 1
+                last_T = enc_len
+            want.append(dict(called=1, n_feat=n, n_enc_out=n_enc, enc_len=enc_len, n_decode=nd, last_T=last_T))
+    except Exception:
+        pytest.skip("the reference algorithm itself cannot process this chunk pattern")
+    p = C.c_void_p()
+    assert lib.sc_planner_create(1, C.byref(p)) == 0
+    try:
+        for i, (n, fin) in enumerate(zip(frames, finals)):
+            pl = _lib.ScStreamPlan()
+            assert lib.sc_planner_push_features(p, 0, n, int(fin), C.byref(pl)) == 0, lib.sc_last_error()
+            got = dict(called=pl.called, n_feat=pl.n_feat, n_enc_out=pl.n_enc_out, enc_len=pl.enc_len,
+                       n_decode=pl.n_decode_blocks, last_T=pl.last_T)
+            assert got == want[i], f"call {i} frames={frames} finals={finals}: {got} != {want[i]}"
+    finally:
+        lib.sc_planner_destroy(p)
