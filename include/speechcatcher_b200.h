@@ -96,7 +96,7 @@ int sc_engine_push(void* handle, const float* wave_dev, int32_t ld_wave, const i
  * speech2text_streaming.py:438-450): feats_dev[i*ld_feats ...] holds n_frames[i] rows of 80 floats for stream
  * streams[i], already normalised by the caller ((x - mean) / std for 2-D input, untouched for 3-D input, like the
  * reference); the frontend is skipped and process_block runs for every listed stream.  At most
- * (max_chunk + 400) / 160 + 6 frames per stream and push. */
+ * (max_chunk + 400) / 160 + 2 frames per stream and push (what the largest waveform chunk would produce). */
 int sc_engine_push_features(void* handle, const float* feats_dev, int32_t ld_feats, const int32_t* streams,
                             const int32_t* n_frames, const int32_t* is_final, int32_t n, void* stream,
                             ScPushStats* stats);

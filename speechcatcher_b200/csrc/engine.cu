@@ -719,9 +719,11 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
     const int s = streams[i];
     if (s < 0 || s >= S) { set_last_error("bad stream id %d", s); return SC_ERR_ARG; }
     if (feats_dev) {
-      if (n_samples[i] < 0 || n_samples[i] > k.feat_cap - 12) {
+      // every capacity downstream (conv rows, sub-sampled frames, blocks) is sized for 12 carried + fmax new frames,
+      // fmax = STFT frames of the largest waveform slab = feat_cap - 16 (make_caps)
+      if (n_samples[i] < 0 || n_samples[i] > k.feat_cap - 16) {
         set_last_error("stream %d: %d feature frames exceed the per-push capacity %d (raise max_chunk)", s, n_samples[i],
-                       k.feat_cap - 12);
+                       k.feat_cap - 16);
         return SC_ERR_CAPACITY;
       }
       if ((int64_t)n_samples[i] * 80 > ld_wave) { set_last_error("feature row pitch too small"); return SC_ERR_ARG; }

@@ -144,7 +144,7 @@ class StreamGroup:
 
     def max_feature_frames(self) -> int:
         """Feature frames one stream may push per call (sc_engine_push_features)."""
-        return (self.max_chunk + 400) // 160 + 6
+        return (self.max_chunk + 400) // 160 + 2      # = the STFT frames of the largest waveform slab (make_caps)
 
     def push_features(self, streams: Sequence[int], feats: Sequence[np.ndarray], is_final: Sequence[bool]) -> ScPushStats:
         """Pre-computed, already normalised feature frames ([n_i, 80] float32 per listed stream) instead of waveforms:

@@ -3,7 +3,8 @@ produced by the reference, plus the reference's own feature-driven tests (tests/
 restated on the B200 class.
 
 The feature-input push (`sc_engine_push_features`) was written after round 1's GPU minutes were spent: these tests are
-marked xfail(strict=False) until they have run on a device once, so a defect here cannot mask the rest of the suite."""
+marked xfail(strict=False) until they have run on a device once, and the file name sorts last among the GPU tests, so
+a defect here (even one that poisons the CUDA context) cannot mask the rest of the suite."""
 import json
 
 import numpy as np
