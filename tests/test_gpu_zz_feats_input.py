@@ -13,7 +13,7 @@ import pytest
 from helpers import GOLDEN, model_dir
 from oracle.gen_golden_feats import feature_chunks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="feature-input path not yet run on a device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180), pytest.mark.xfail(strict=False, reason="feature-input path not yet run on a device")]
 G = json.loads((GOLDEN / "feats_input.json").read_text())
 
 

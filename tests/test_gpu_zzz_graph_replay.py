@@ -10,7 +10,7 @@ import torch
 
 from helpers import model_dir
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="graph replay not yet run on a device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180), pytest.mark.xfail(strict=False, reason="graph replay not yet run on a device")]
 
 
 def _run(md, graph, dtype, lengths):
