@@ -368,3 +368,30 @@ class StreamGroup:
                 text = " ".join(toks)
             out.append((text, toks, ids.tolist(), pos.tolist(), dict(yseq=y, score=sc, xpos=xp)))
         return out
+
+    @classmethod
+    def _assemble_rowwise(cls, beam, is_final: bool, finalize_all: bool, token_list=None):
+        """One hypothesis at a time, following speech2text_streaming.py:466-539 line by line (the checker of the
+        numpy `_assemble` in tests/test_assemble_cpu.py)."""
+        yseqs, scores, xposs, _ = beam
+        out = []
+        for y, sc, xp in zip(yseqs, scores, xposs):
+            y, xp = [int(t) for t in y], [int(t) for t in xp]
+            if (not is_final or not finalize_all) and y[-1] != EOS_FILTER_ID:
+                continue
+            if is_final:
+                ids, pos = y[1:], xp[1:]
+                if ids and ids[-1] == EOS_FILTER_ID:
+                    ids, pos = ids[:-1], pos[:-1]
+            else:
+                ids, pos = [], []
+            keep = [i for i, t in enumerate(ids) if t not in (0, 1, EOS_FILTER_ID)]
+            ids, pos = [ids[i] for i in keep], [pos[i] for i in keep]
+            if token_list is not None:
+                toks = [token_list[t] for t in ids]
+                text = "".join(toks).replace("\u2581", " ").strip()
+            else:
+                toks = [str(t) for t in ids]
+                text = " ".join(toks)
+            out.append((text, toks, ids, pos, dict(yseq=np.array(y, np.int32), score=sc, xpos=np.array(xp, np.int32))))
+        return out
