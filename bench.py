@@ -376,6 +376,22 @@ def main():
                "h2d_bytes_per_step": int(S * n_samples * 4), "d2h_bytes_per_step": int(d2h),
                "p50_chunk_ms": float(statistics.median(lat_ms)), "p95_chunk_ms": float(np.percentile(lat_ms, 95))}
 
+        if world > 1:
+            # the one exchange of a sharded run: finished transcripts of every rank's streams as
+            # fixed-width records over NCCL / NVLink (outside the timed region; a few MB per rank)
+            from speechcatcher_b200.sharding import gather_beams
+            parts = [[], [], [], []]
+            for g_ in groups:
+                ctl_n, ys_n, xp_n, sc_n = g_._read_all()
+                cur, idx = ctl_n[:, 0], np.arange(ctl_n.shape[0])
+                for lst, arr in zip(parts, (ctl_n[:, 1:3], ys_n[cur, idx], xp_n[cur, idx], sc_n[cur, idx])):
+                    lst.append(np.ascontiguousarray(arr))
+            tg = time.perf_counter()
+            g_ctl, g_ys, g_xp, g_sc = gather_beams(*[np.concatenate(x) for x in parts], device=dev)
+            assert g_ctl.shape[0] == world * S and (g_ctl[:, 0] == args.beam).all()
+            e2e["transcript_gather"] = {"streams": int(g_ctl.shape[0]), "ms": 1000.0 * (time.perf_counter() - tg),
+                                        "bytes": int(g_ctl.nbytes + g_ys.nbytes + g_xp.nbytes + g_sc.nbytes)}
+
     # per-kernel rooflines without cross-shard interference: one dedicated group holding all S streams, one full pass
     # per kernel with CUDA-event pairs around every launch of that kernel (same workload, same deferred scheduling)
     extra_roof = None

@@ -35,3 +35,26 @@ def gather_results(local: Dict[int, Any], group=None) -> Dict[int, Any]:
             raise RuntimeError(f"streams owned by two ranks: {sorted(dup)[:5]}")
         out.update(p)
     return out
+
+
+def gather_beams(ctl, yseq, xpos, score, device=None, group=None):
+    """The one exchange of a sharded run as fixed-width records: every rank contributes the
+    beams of its S streams -- ctl [S, 2] int32 (n_hyp, len), yseq / xpos [S, B, L] int32, score [S, B] float64 -- and
+    receives the same four arrays for all world * S streams, rank r's block at [r * S, (r + 1) * S).  Tensors travel
+    as they are (NCCL all-gather over NVLink on CUDA tensors, gloo on CPU tensors); nothing is pickled."""
+    import torch
+    import torch.distributed as dist
+    parts = [torch.as_tensor(ctl, dtype=torch.int32), torch.as_tensor(yseq, dtype=torch.int32),
+             torch.as_tensor(xpos, dtype=torch.int32), torch.as_tensor(score, dtype=torch.float64)]
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return tuple(p.cpu().numpy() for p in parts)
+    world = dist.get_world_size(group)
+    out = []
+    for p in parts:
+        p = p.contiguous()
+        if device is not None:
+            p = p.to(device)
+        full = torch.empty((world * p.shape[0],) + tuple(p.shape[1:]), dtype=p.dtype, device=p.device)
+        dist.all_gather_into_tensor(full, p, group=group)
+        out.append(full.cpu().numpy())
+    return tuple(out)

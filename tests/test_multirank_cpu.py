@@ -91,3 +91,40 @@ def test_long_file_sharded_by_segment_world2():
     assert all(ok_text and ok_aux for _, ok_text, ok_aux, _, _ in got)        # every rank holds the full transcript
     assert sum(n for _, _, _, n, _ in got) == got[0][4]                        # the calls were split, not duplicated
     assert all(0 < n < got[0][4] for _, _, _, n, _ in got)
+
+
+def _beams_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from speechcatcher_b200.sharding import gather_beams
+    S, B, L = 5, 3, 16
+    rng = np.random.default_rng(rank)
+    ctl = np.stack([np.full(S, B), rng.integers(1, L, S)], axis=1).astype(np.int32)
+    ys = rng.integers(0, 1024, (S, B, L)).astype(np.int32)
+    xp = rng.integers(0, 1500, (S, B, L)).astype(np.int32)
+    sc = rng.standard_normal((S, B))
+    g_ctl, g_ys, g_xp, g_sc = gather_beams(ctl, ys, xp, sc)
+    ok = g_ctl.shape == (world * S, 2) and g_ys.shape == (world * S, B, L) and g_sc.dtype == np.float64
+    ok = ok and np.array_equal(g_ys[rank * S:(rank + 1) * S], ys) and np.array_equal(g_sc[rank * S:(rank + 1) * S], sc)
+    other = 1 - rank
+    ro = np.random.default_rng(other)
+    ro.integers(1, L, S)
+    ok = ok and np.array_equal(g_ys[other * S:(other + 1) * S], ro.integers(0, 1024, (S, B, L)).astype(np.int32))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_fixed_width_beam_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_beams_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in got)
