@@ -100,6 +100,7 @@ class StreamGroup:
         self.stream = torch.cuda.current_stream(self.device)
         self._wave_dev = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32, device=self.device)
         self._wave_host = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32).pin_memory()
+        self._h2d_done = None
         self.last_stats = ScPushStats()
         self.total_launches = 0
 
@@ -135,11 +136,17 @@ class StreamGroup:
         if n and lens.max() > self.max_chunk:
             raise ValueError(f"chunk of {int(lens.max())} samples exceeds max_chunk={self.max_chunk}")
         host = self._wave_host
+        # the pinned staging buffer is reused: in deferred / overlapped mode a push can return before its H2D copy has
+        # drained, so wait for the previous copy before overwriting the buffer (almost always already complete)
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
         for i, (s, c) in enumerate(zip(ids, chunks)):
             if len(c):
                 host[s, : len(c)] = torch.as_tensor(np.asarray(c, np.float32))
         with torch.cuda.device(self.device):
             self._wave_dev.copy_(host, non_blocking=True)
+            self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.device))
         return self.push_device(ids, self._wave_dev, lens, fin)
 
     def max_feature_frames(self) -> int:
