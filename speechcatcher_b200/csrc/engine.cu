@@ -516,6 +516,12 @@ static int check_cfg(const ScConfig* c) {
   }
   if (c->beam < 1 || c->beam > 20) { set_last_error("beam %d out of range [1, 20]", c->beam); return SC_ERR_ARG; }
   if (c->n_streams < 1 || c->max_chunk < 1 || c->max_frames < 32) { set_last_error("bad capacities"); return SC_ERR_ARG; }
+  // the positional table holds 5000 positions like the reference's (positional_encoding.py:31,72): an un-reset
+  // stream ends there (200 s); the encoder indexes up to max_frames + one block of look-ahead frames
+  if (c->max_frames + 64 > 5000) {
+    set_last_error("max_frames %d exceeds the 5000-position table of the model (at most 4936 frames = 197 s per stream)", c->max_frames);
+    return SC_ERR_ARG;
+  }
   int dk_e = c->d_model / c->enc_heads, dk_d = c->d_model / c->dec_heads;
   if ((dk_e != 32 && dk_e != 64) || (dk_d != 32 && dk_d != 64)) { set_last_error("head dim must be 32 or 64"); return SC_ERR_ARG; }
   return SC_OK;

@@ -65,6 +65,9 @@ class StreamGroup:
         self.max_chunk = int(max_chunk)
         self.max_seconds = float(max_seconds)
         max_frames = int(max_seconds * 25) + 64
+        if max_frames + 64 > 5000:
+            raise ValueError(f"max_seconds={max_seconds:g} exceeds what one un-reset stream can hold: the model's positional "
+                             "table has 5000 positions (reference positional_encoding.py:31), i.e. at most 194 s")
         self.cfg = ScConfig(
             d_model=enc.get("output_size", 256), enc_heads=enc.get("attention_heads", 4),
             enc_layers=enc.get("num_blocks", 12), dec_heads=dec.get("attention_heads", 4),

@@ -58,7 +58,7 @@ def test_workspace_of_every_baseline_config_fits_one_b200():
     assert gib(enc_layers=18, dec_layers=8) < xl_bf16               # config 3 (L, 256 streams per GPU)
     assert gib(enc_layers=18, dec_layers=8, n_streams=60, max_frames=185 * 25 + 64) < 20   # config 4: 60 segments <= 180 s
     assert gib(beam=20) < 80                                         # config 5
-    for bad in (dict(beam=21), dict(d_model=512), dict(n_streams=0)):
+    for bad in (dict(beam=21), dict(d_model=512), dict(n_streams=0), dict(max_frames=5000)):
         n = C.c_size_t()
         base = dict(d_model=256, enc_heads=8, enc_layers=30, dec_heads=8, dec_layers=14, vocab=1024, ffn=2048,
                     n_streams=256, beam=10, max_chunk=8192, max_frames=1589, use_bbd=0, precision=1, ctc_weight=0.3)

@@ -60,7 +60,7 @@ def test_errors_are_loud():
     s2t(np.zeros(4000, np.float32))
     with pytest.raises((RuntimeError, ValueError)):
         s2t(np.zeros(20000, np.float32))              # larger than max_chunk in the middle of an utterance
-    with pytest.raises(NotImplementedError):
-        s2t(np.zeros((10, 80), np.float32))           # pre-computed features are not part of the path
+    with pytest.raises(ValueError):
+        s2t(np.zeros((1, 1, 10, 80), np.float32))     # 1-D waveforms, 2-D features or 3-D batched features only
     with pytest.raises(RuntimeError):
         StreamGroup(md, n_streams=1, beam_size=64)    # beam out of range
