@@ -380,15 +380,15 @@ def main():
             # the one exchange of a sharded run: finished transcripts of every rank's streams as
             # fixed-width records over NCCL / NVLink (outside the timed region; a few MB per rank)
             from speechcatcher_b200.sharding import gather_beams
-            parts = [[], [], [], []]
-            for g_ in groups:
-                ctl_n, ys_n, xp_n, sc_n = g_._read_all()
-                cur, idx = ctl_n[:, 0], np.arange(ctl_n.shape[0])
-                for lst, arr in zip(parts, (ctl_n[:, 1:3], ys_n[cur, idx], xp_n[cur, idx], sc_n[cur, idx])):
-                    lst.append(np.ascontiguousarray(arr))
             tg = time.perf_counter()
             try:
-                g_ctl, g_ys, g_xp, g_sc = gather_beams(*[np.concatenate(x) for x in parts], device=dev)
+                recs = [[], [], [], []]
+                for g_ in groups:
+                    ctl_n, ys_n, xp_n, sc_n = g_._read_all()
+                    cur, idx = ctl_n[:, 0], np.arange(ctl_n.shape[0])
+                    for lst, arr in zip(recs, (ctl_n[:, 1:3], ys_n[cur, idx], xp_n[cur, idx], sc_n[cur, idx])):
+                        lst.append(np.ascontiguousarray(arr))
+                g_ctl, g_ys, g_xp, g_sc = gather_beams(*[np.concatenate(x) for x in recs], device=dev)
                 assert g_ctl.shape[0] == world * S and (g_ctl[:, 0] == args.beam).all()
                 e2e["transcript_gather"] = {"streams": int(g_ctl.shape[0]), "ms": 1000.0 * (time.perf_counter() - tg),
                                             "bytes": int(g_ctl.nbytes + g_ys.nbytes + g_xp.nbytes + g_sc.nbytes)}
