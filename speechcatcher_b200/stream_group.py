@@ -44,7 +44,7 @@ def _frontend_tables():
 class StreamGroup:
     def __init__(self, model_dir, n_streams: int = 1, beam_size: int = 5, ctc_weight: float = 0.3,
                  device: str = "cuda:0", dtype: str = "float32", use_bbd: bool = False,
-                 max_chunk: int = 8192, max_seconds: float = 61.0):
+                 max_chunk: int = 8192, max_seconds: float = 61.0, own_stream: bool = False):
         if not str(device).startswith("cuda"):
             raise RuntimeError("speechcatcher_b200 runs on CUDA devices only (no CPU fallback)")
         if not torch.cuda.is_available():
@@ -100,7 +100,11 @@ class StreamGroup:
             _lib.check(self.lib.sc_engine_set_frontend(self.handle, C.c_void_p(window.data_ptr()),
                                                        C.c_void_p(mel.data_ptr()), mean_p, std_p), "set_frontend")
             _lib.check(self.lib.sc_engine_finalize(self.handle), "finalize")
-        self.stream = torch.cuda.current_stream(self.device)
+        # The engine runs on the stream that is current at construction.  own_stream=True gives it a stream of its own
+        # (ordered after the caller's stream at every push): needed for the CUDA-graph replay when the caller works on
+        # the legacy default stream, which cannot be captured.
+        self.own_stream = bool(own_stream)
+        self.stream = torch.cuda.Stream(device=self.device) if own_stream else torch.cuda.current_stream(self.device)
         self._wave_dev = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32, device=self.device)
         self._wave_host = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32).pin_memory()
         self._h2d_done = None
@@ -204,6 +208,8 @@ class StreamGroup:
         fin = np.ascontiguousarray(fin, np.int32)
         st = ScPushStats()
         with torch.cuda.device(self.device):
+            if self.own_stream:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))     # the caller's copies into wave_dev
             rc = self.lib.sc_engine_push(self.handle, C.c_void_p(wave_dev.data_ptr() + 4 * col_offset), wave_dev.shape[1],
                                          ids.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
                                          fin.ctypes.data_as(C.c_void_p), len(ids),
