@@ -11,6 +11,9 @@ timeout 60 python -m pytest tests/test_gpu_zz_feats_input.py -q -m gpu -rxX > $O
 timeout 60 python -m pytest tests/test_gpu_zzz_graph_replay.py -q -m gpu -rxX > $O/graph_tests.txt 2>&1
 timeout 60 python tests/graph_replay_ab.py > $O/graph_ab.txt 2>&1; echo "graph_ab_rc=$?" >> $O/rc.txt
 SCB_GRAPH=3 timeout 60 python -m pytest tests/test_gpu_multistream.py -q -m gpu -k "sharded or batch_invariance" > $O/graph_sharded_tests.txt 2>&1; echo "graph_sharded_rc=$?" >> $O/rc.txt
+# the whole parity suite with every engine on its own stream and both graphs on (engines on the default stream would
+# silently keep plain launches)
+SCB_GRAPH=3 SCB_OWN_STREAM=1 timeout 200 python -m pytest tests -q -m gpu > $O/tests_gpu_graphs_everywhere.txt 2>&1; echo "graphs_everywhere_rc=$?" >> $O/rc.txt
 for g in 0 1 2 3; do
   echo "graph=$g: $(SCB_BENCH_GRAPH=$g timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
 done

@@ -103,6 +103,8 @@ class StreamGroup:
         # The engine runs on the stream that is current at construction.  own_stream=True gives it a stream of its own
         # (ordered after the caller's stream at every push): needed for the CUDA-graph replay when the caller works on
         # the legacy default stream, which cannot be captured.
+        import os
+        own_stream = own_stream or os.environ.get("SCB_OWN_STREAM") == "1"     # switch for whole-suite validation runs
         self.own_stream = bool(own_stream)
         self.stream = torch.cuda.Stream(device=self.device) if own_stream else torch.cuda.current_stream(self.device)
         self._wave_dev = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32, device=self.device)
