@@ -153,9 +153,12 @@ class StreamGroup:
             if len(c):
                 host[s, : len(c)] = torch.as_tensor(np.asarray(c, np.float32))
         with torch.cuda.device(self.device):
-            self._wave_dev.copy_(host, non_blocking=True)
+            # own_stream: the copy goes on the engine's stream so that it is ordered after the previous push's reads
+            copy_stream = self.stream if self.own_stream else torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(copy_stream):
+                self._wave_dev.copy_(host, non_blocking=True)
             self._h2d_done = torch.cuda.Event()
-            self._h2d_done.record(torch.cuda.current_stream(self.device))
+            self._h2d_done.record(copy_stream)
         return self.push_device(ids, self._wave_dev, lens, fin)
 
     def max_feature_frames(self) -> int:
