@@ -562,7 +562,9 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   e->enc.resize(cfg->enc_layers); e->dec.resize(cfg->dec_layers);
   {
     const char* a = getenv("SCB_ATTN");     // "simt" forces the CUDA-core attention kernels in the bf16 mode (A/B tests)
-    e->mma_attn = cfg->precision == 1 && cfg->beam <= 16 && !(a && strcmp(a, "simt") == 0);
+    // beam 17..32 takes the tiled (WIDE) tensor-core kernel only on request ("mma_wide"): not yet run on a device
+    const int mma_beam = (a && strcmp(a, "mma_wide") == 0) ? 32 : 16;
+    e->mma_attn = cfg->precision == 1 && cfg->beam <= mma_beam && !(a && strcmp(a, "simt") == 0);
     e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
     const char* lp = getenv("SCB_LN_PROLOGUE");
     // measured slower than a separate LayerNorm kernel (every N-tile CTA re-normalises its 128 rows): opt-in only
@@ -1083,7 +1085,7 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = e->fuse_ln_dec = value != 0 && e->cfg.precision == 1; return SC_OK; }
   if (strcmp(name, "fuse_layernorm_decoder") == 0) { e->fuse_ln_dec = value != 0 && e->cfg.precision == 1; return SC_OK; }
   if (strcmp(name, "mma_attention") == 0) {
-    e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= 16;
+    e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= (value >= 2 ? 32 : 16);   // 2: allow the tiled kernel
     e->mma_enc = value != 0 && e->cfg.precision == 1;
     return SC_OK;
   }

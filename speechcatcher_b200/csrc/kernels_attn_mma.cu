@@ -18,7 +18,7 @@ constexpr int A_KPW = 32;          // keys per warp per step (each warp runs its
 constexpr int A_STEP = 4 * A_KPW;  // keys per CTA step
 constexpr int A_NT = A_KPW / 8;    // score n-tiles per warp
 constexpr int A_KK = A_KPW / 16;   // k-steps of the P*V product per warp
-constexpr int MMA_MAXB = 16;       // rows of the m16 tile
+constexpr int MMA_MAXB = 32;       // hypotheses per stream: one m16 tile, or two tiles over blockIdx.z (WIDE)
 constexpr int MMA_KEYS_SMEM = 768;  // self-attention key list entries staged in shared memory (longer lists spill to global)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -116,7 +116,11 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, ex2(-inf) = 
 // on raw scores with one ex2 per element (scale * log2(e) folded into an FMA), masks only where a mask can exist
 // (self: the divergent tail, found with one warp vote; cross: the last step), and fetches B fragments with x4
 // ldmatrix.
-template <int DK, int MODE>
+// WIDE = 1 (beam 17..32, opt-in, not yet run on a device): the hypotheses of a stream are split into m16 tiles over
+// blockIdx.z; a CTA loads / appends / writes only the rows h0..h0+15 of its tile and compares key owners against the
+// stream-wide hypothesis index.  A hypothesis' new token is visible to itself only, so the per-tile appends of the
+// self-attention K|V do not race.  WIDE = 0 compiles to exactly the single-tile kernel (h0 = 0 folds away).
+template <int DK, int MODE, int WIDE>
 __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __nv_bfloat16* kv_layer,
                                                            const float* __restrict__ q, int ldq, int q_off,
                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
@@ -125,7 +129,10 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
   const int s = sb.act_streams[blockIdx.x];
   const int head = blockIdx.y;
   const StreamCtl& c = sb.ctl[s];
-  const int nb = c.n_hyp, row0 = sb.row_base[s], D = sb.D, B = sb.B;
+  const int h0 = WIDE ? 16 * (int)blockIdx.z : 0;            // first hypothesis of this CTA's tile
+  if (WIDE && h0 >= c.n_hyp) return;
+  const int nb = WIDE ? min(16, c.n_hyp - h0) : c.n_hyp;     // hypotheses in the tile
+  const int row0 = sb.row_base[s] + h0, D = sb.D, B = sb.B;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int RS = DK + 8;                 // padded smem row (bf16 elements): conflict-free ldmatrix
   constexpr int CPR = DK / 8;                // 16-byte chunks per K (or V) row
@@ -159,11 +166,11 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
   int n_keys;
   const int* keys = nullptr;
   if (MODE == 0) {
-    if (tid == 0) atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * 2));
+    if (tid == 0) atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * 2));   // per tile: sums to n_hyp
     for (int i = tid; i < nb * 2 * DK; i += 128) {        // append K|V of the scored token at [len-1][b]
       const int b = i / (2 * DK), rem = i % (2 * DK), which = rem / DK, cc = rem % DK;
       const float v = q[(size_t)(row0 + b) * ldq + D + which * D + head * DK + cc];
-      base[((size_t)(len - 1) * B + b) * row_stride + which * D + cc] = __float2bfloat16(v);
+      base[((size_t)(len - 1) * B + (h0 + b)) * row_stride + which * D + cc] = __float2bfloat16(v);
     }
     n_keys = sb.self_nkeys[s];
     keys = sb.self_keys + (size_t)s * sb.key_cap;
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
     for (int i = tid; i < n_keys && i < MMA_KEYS_SMEM; i += 128) keys_s[i] = keys[i];
   } else {
     n_keys = c.Tb;
-    if (tid == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 2));
+    if (tid == 0 && h0 == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 2));
   }
   __syncthreads();                      // Qs, key list staged; appended rows visible to the loads below
   const int n_steps = (n_keys + A_STEP - 1) / A_STEP;
@@ -247,10 +254,10 @@ __global__ void __launch_bounds__(128) dec_attn_mma_kernel(SearchBuffers sb, __n
 #pragma unroll
           for (int nt = 0; nt < A_NT; ++nt) {
             const int o0 = ob[8 * nt + 2 * qd], o1 = ob[8 * nt + 2 * qd + 1];
-            if (!(o0 == -1 || o0 == r0)) sacc[nt][0] = -INFINITY;
-            if (!(o1 == -1 || o1 == r0)) sacc[nt][1] = -INFINITY;
-            if (!(o0 == -1 || o0 == r1)) sacc[nt][2] = -INFINITY;
-            if (!(o1 == -1 || o1 == r1)) sacc[nt][3] = -INFINITY;
+            if (!(o0 == -1 || o0 == h0 + r0)) sacc[nt][0] = -INFINITY;
+            if (!(o1 == -1 || o1 == h0 + r0)) sacc[nt][1] = -INFINITY;
+            if (!(o0 == -1 || o0 == h0 + r1)) sacc[nt][2] = -INFINITY;
+            if (!(o1 == -1 || o1 == h0 + r1)) sacc[nt][3] = -INFINITY;
           }
         }
       } else if (u0 + A_KPW > n_keys) {                        // cross: zero-filled rows past the last frame
@@ -480,22 +487,36 @@ static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const 
   if (MODE == 0) smem += sizeof(int) * MMA_KEYS_SMEM;
   const size_t merge = sizeof(float) * (128 + 4 * 16 * DK);
   if (stages < merge) { set_last_error("attn_mma: merge scratch does not fit"); return -1; }
+  if (sb.B > 16) {                                  // beam 17..32: one CTA per (stream, head, m16 tile of hypotheses)
+    static size_t attr_w = 0;
+    if (attr_w < smem) {
+      if (cudaFuncSetAttribute(dec_attn_mma_kernel<DK, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_last_error("attn_mma: cudaFuncSetAttribute(%zu) failed", smem);
+        return -1;
+      }
+      attr_w = smem;
+    }
+    launch_k(dec_attn_mma_kernel<DK, MODE, 1>, dim3(sb.S, sb.H, (sb.B + 15) / 16), dim3(128), smem, st, sb, kv_layer, q, ldq,
+             q_off, out, out16);
+    SCB_LAUNCH_CHECK();
+    return 0;
+  }
   static size_t attr = 0;
   if (attr < smem) {
-    if (cudaFuncSetAttribute(dec_attn_mma_kernel<DK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(dec_attn_mma_kernel<DK, MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("attn_mma: cudaFuncSetAttribute(%zu) failed", smem);
       return -1;
     }
     attr = smem;
   }
   dim3 grid(sb.S, sb.H);
-  launch_k(dec_attn_mma_kernel<DK, MODE>, grid, dim3(128), smem, st, sb, kv_layer, q, ldq, q_off, out, out16);
+  launch_k(dec_attn_mma_kernel<DK, MODE, 0>, grid, dim3(128), smem, st, sb, kv_layer, q, ldq, q_off, out, out16);
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
 // mode 0: self attention (q = fused QKV GEMM output, row stride ldq = 3D; K|V of the new token at +D);
-// mode 1: cross attention.  Requires bf16 KV caches and beam <= 16.
+// mode 1: cross attention.  Requires bf16 KV caches and beam <= 32 (beam > 16 takes the tiled WIDE variant).
 int launch_dec_attention_mma(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
                              __nv_bfloat16* out16, cudaStream_t st) {
   if (!sb.kv_bf16 || sb.B > MMA_MAXB) { set_last_error("attn_mma: needs bf16 KV and beam <= %d", MMA_MAXB); return -1; }

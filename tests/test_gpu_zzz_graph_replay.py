@@ -61,3 +61,39 @@ def test_graph_replay_same_search_in_bf16():
     for x, y in zip(base, got):
         for a, b in zip(x, y):
             assert a[0] == b[0] and a[2] == b[2]
+
+
+def test_wide_mma_attention_beam20_tracks_cuda_core_attention():
+    """BASELINE config 5 (beam 20, bf16): the tiled tensor-core decoder attention (option mma_attention = 2: two m16
+    tiles of hypotheses per stream) against the CUDA-core attention the engine uses for beam > 16 by default.
+    Decoder log-probs must agree to bf16 accuracy for as long as both searches hold the same beams."""
+    from speechcatcher_b200 import StreamGroup
+    from speechcatcher_b200.synthetic import synth_audio
+    md = model_dir("xl_d4")
+    S, n = 2, 4 * 16000
+    audio = [synth_audio(70 + s, n) for s in range(S)]
+
+    def run(wide):
+        g = StreamGroup(md, n_streams=S, beam_size=20, dtype="bfloat16", max_seconds=6.0)
+        if wide:
+            g.set_option("mma_attention", 2)
+        logs, beams = [], []
+        for i in range(0, n, 8192):
+            fin = i + 8192 >= n
+            g.push(list(range(S)), [a[i:i + 8192] for a in audio], [fin] * S)
+            logs.append(g.buffer("dlogp").view(-1, 1024)[: S * 20].clone().cpu().numpy())
+            beams.append([g.beam(s)[0] for s in range(S)])
+        g.close()
+        return logs, beams
+
+    a_logs, a_beams = run(False)
+    b_logs, b_beams = run(True)
+    agree = 0
+    for la, lb, ba, bb in zip(a_logs, b_logs, a_beams, b_beams):
+        if ba != bb:
+            break
+        agree += 1
+        if np.abs(la).sum() > 0:
+            assert np.abs(la - lb).max() < 2e-2
+    assert agree >= 4                                   # the first decode blocks take the same decisions
+    assert all(len(b) == 20 for b in b_beams[-1]) and [b[0][:4] for b in a_beams[-1]] == [b[0][:4] for b in b_beams[-1]]
