@@ -21,4 +21,6 @@ echo "ln_prologue_decoder=1: $(SCB_LN_PROLOGUE_DEC=1 timeout 60 bash scripts/ben
 echo "graph=3 + ln_prologue_decoder=1: $(SCB_BENCH_GRAPH=3 SCB_LN_PROLOGUE_DEC=1 timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
 echo "graph=3 shards=8: $(SCB_BENCH_GRAPH=3 SCB_BENCH_SHARDS=8 timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
 echo "graph=3 shards=2: $(SCB_BENCH_GRAPH=3 SCB_BENCH_SHARDS=2 timeout 60 bash scripts/bench_value.sh 2>&1 | tail -1)" >> $O/bench_graph.txt
+echo "beam20 default (CUDA-core attention): $(timeout 90 bash scripts/bench_value.sh --beam 20 2>&1 | tail -1)" >> $O/bench_graph.txt
+echo "beam20 SCB_ATTN=mma_wide: $(SCB_ATTN=mma_wide timeout 90 bash scripts/bench_value.sh --beam 20 2>&1 | tail -1)" >> $O/bench_graph.txt
 cat $O/rc.txt $O/bench_graph.txt
