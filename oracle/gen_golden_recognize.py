@@ -37,6 +37,8 @@ CASES = [
      [(0, 3011), (3011, 6142), (6142, 9143), (9143, 11834), (11834, 14835), (14835, 17836), (17836, 20757),
       (20757, 23758), (23758, 26759), (26759, 29760), (29760, 33333), (33333, 38000)]),
     ("tiny_2s", 6, 2 * 16000, 8192, None),
+    ("empty_file", 7, 0, 8192, None),
+    ("one_sample", 8, 1, 8192, None),
 ]
 INTERP = [[3, 3, 3, 7, 9, 9, 12], [0, 0, 5, 5, 6], [1, 2, 3], [4, 4, 4, 4], [], [0], [2, 2, 10, 10, 10, 11, 30, 30]]
 
