@@ -141,10 +141,13 @@ def main():
     ap.add_argument("--streams", type=int, default=256, help="streams per GPU")
     ap.add_argument("--beam", type=int, default=10)
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--dtype", default=os.environ.get("SCB_BENCH_DTYPE", "bfloat16"), choices=["float32", "bfloat16"],
-                    help="bfloat16: tensor-core GEMMs/attention with fp32 accumulation (throughput mode, north_star); "
-                         "float32: CUDA-core parity mode (n-best identical to the reference)")
-    ap.add_argument("--no-fp32", action="store_true", help="skip the extra fp32 parity-mode measurement")
+    ap.add_argument("--dtype", default=os.environ.get("SCB_BENCH_DTYPE", "float32_tc"),
+                    choices=["float32_tc", "float32_simt", "float32", "bfloat16"],
+                    help="float32_tc (default): fp32 results with every Linear on the tcgen05 tensor cores as a split-fp16 "
+                         "GEMM (parity mode, n-best identical to the reference on the goldens); float32_simt: the same on "
+                         "the CUDA cores; bfloat16: bf16 operands (fast, but random-init weights flip the n-best)")
+    ap.add_argument("--no-fp32", action="store_true",
+                    help="skip the float32_simt pass (its throughput, and the `parity` agreement of the benched mode with it)")
     ap.add_argument("--no-extra-rooflines", action="store_true",
                     help="skip the per-kernel roofline passes on a dedicated single 256-stream group")
     ap.add_argument("--cpu-sample-seconds", type=float, default=None,
@@ -299,6 +302,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def final_beams(glist):
+        """(yseq per hyp, scores, xpos per hyp, process_idx) of every stream of this rank after a finished pass."""
+        torch.cuda.synchronize()
+        return [b for g_ in glist for b in g_.beams_all()]
+
+    def common_prefix(a, b):
+        n = 0
+        for x, y in zip(a, b):
+            if x != y:
+                break
+            n += 1
+        return n
+
     for _ in range(args.warmup):
         one_pass_resident()
     # one extra untimed pass with every kernel wrapped in CUDA events (decode steps sampled 1 in 8): the share of
@@ -417,21 +433,26 @@ def main():
             tag = g1.profile_begin(kname)
             pass1()
             torch.cuda.synchronize()
-            extra_roof.append(g1.profile_end(tag))
+            r_ = g1.profile_end(tag)
+            if r_["launches"] > 0:                     # e.g. enc_ffn1 does not exist as a kernel when the FFN is fused
+                extra_roof.append(r_)
         g1.close()
         del g1
         torch.cuda.empty_cache()
 
-    # the fp32 parity mode (CUDA-core GEMMs, results identical to the reference) measured on the same workload
+    # the CUDA-core fp32 mode on the same workload: its throughput, and the agreement of the benched mode's final
+    # beams with it on every stream (`parity`)
     fp32_mode = None
-    if args.dtype == "bfloat16" and not args.no_fp32:
+    parity = None
+    if args.dtype not in ("float32_simt",) and not args.no_fp32:
+        beams_main = final_beams(groups)
         for g_ in groups:
             g_.close()
         if sg is not None:
             sg.pool.shutdown(wait=True)
         del grp, groups, sg, resident
         torch.cuda.empty_cache()
-        sg32, groups32 = make_groups("float32")
+        sg32, groups32 = make_groups("float32_simt")
         res32 = host.to(dev)
 
         def pass32():
@@ -450,10 +471,26 @@ def main():
             t = torch.tensor([ms32], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms32 = float(t.item())
+        beams32 = final_beams(groups32)
         for g_ in groups32:
             g_.close()
         fp32_mode = {"value": world * S * args.seconds / (ms32 / 1000.0), "unit": "audio-s/s", "ms_per_step": ms32,
-                     "steps": 1, "warmup": 1, "note": "parity mode: true-fp32 CUDA-core GEMMs, n-best identical to the reference"}
+                     "steps": 1, "warmup": 1, "note": "float32_simt: true-fp32 CUDA-core GEMMs, n-best identical to the reference"}
+        same1 = sum(1 for a, b in zip(beams_main, beams32) if a[0][:1] == b[0][:1])
+        samen = sum(1 for a, b in zip(beams_main, beams32) if a[0] == b[0])
+        pre = [common_prefix(a[0][0], b[0][0]) / max(1, len(b[0][0])) for a, b in zip(beams_main, beams32)]
+        cnt = [same1, samen, len(beams32)]
+        if world > 1:
+            t = torch.tensor(cnt + [sum(pre)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            cnt, pre_sum = [int(v) for v in t[:3].tolist()], float(t[3].item())
+        else:
+            pre_sum = float(sum(pre))
+        parity = {"mode": args.dtype, "against": "float32_simt pass of this run (CUDA-core fp32 GEMMs; n-best identical to "
+                  "the reference on every golden)", "streams_compared": cnt[2], "audio_seconds_per_stream": args.seconds,
+                  "same_1best_frac": cnt[0] / cnt[2], "same_nbest_frac": cnt[1] / cnt[2],
+                  "mean_1best_common_prefix_frac": pre_sum / cnt[2],
+                  "tokens_per_1best": float(np.mean([len(b[0][0]) for b in beams32]))}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -469,15 +506,21 @@ def main():
         line = {"metric": "audio-sec/sec (RTFx)", "value": value, "unit": "audio-s/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.dtype == "float32" else "bf16", "data": "synthetic",
+                "dtype": "bf16" if args.dtype == "bfloat16" else "f32", "data": "synthetic",
                 "config": {"workload": workload, "l2": f"inputs larger than L2 ({S * n_chunks * CHUNK * 4 / 1e6:.0f} MB of waveforms per GPU)",
+                           "mode": {"float32_tc": "float32_tc: fp32 activations, every Linear a split-fp16 (hi + lo) tcgen05 GEMM "
+                                                  "with fp32 accumulation (3 UMMAs per product), fp32 attention / KV caches",
+                                    "float32_simt": "float32_simt: true-fp32 CUDA-core GEMMs",
+                                    "float32": "float32 (engine default fp32 GEMM)",
+                                    "bfloat16": "bfloat16: bf16 tcgen05 GEMMs / attention, bf16 KV caches"}[args.dtype],
                            "shards_per_gpu": G, "cuda_graphs": args.graph,
                            "decode_scheduling": ("strict: every push drains its decode blocks" if lazy == 0 else
                                                  f"deferred: a push stops iterating below {lazy} active streams; final calls drain"),
                            "decode_steps_per_pass": timed_stats["steps"] // max(1, args.steps),
                            "encoder_blocks_per_pass": timed_stats["blocks"] // max(1, args.steps)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": timed_stats["launches"],
-                "roofline": roof, "roofline_single_group": extra_roof, "cpu_baseline": cpu_base, "fp32_mode": fp32_mode,
+                "roofline": roof, "parity": parity, "roofline_single_group": extra_roof, "cpu_baseline": cpu_base,
+                "fp32_mode": fp32_mode,
                 "kernel_breakdown_sampled": breakdown}
         print(json.dumps(line))
     if world > 1:

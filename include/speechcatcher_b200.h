@@ -44,7 +44,8 @@ typedef struct ScConfig {
   int32_t max_chunk;     /* largest number of samples one stream may push per call */
   int32_t max_frames;    /* capacity of the per-stream encoder buffer (frames of 40 ms) */
   int32_t use_bbd;       /* Speech2TextStreaming(use_bbd=...) */
-  int32_t precision;     /* 0 = fp32 (parity mode), 1 = bf16 tensor-core GEMMs */
+  int32_t precision;     /* 0 = fp32 on the CUDA cores, 1 = bf16 tensor-core GEMMs, 2 = fp32 results on the tensor
+                          * cores: every Linear as a split-fp16 (hi + lo 2^-11) tcgen05 GEMM, everything else as 0 */
   float ctc_weight;      /* 0.3; decoder weight is 1 - ctc_weight (speech2text_streaming.py:143-150) */
 } ScConfig;
 
@@ -131,6 +132,18 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
  * while a kernel is being profiled. */
 int sc_engine_set_option(void* handle, const char* name, int32_t value);
 
+/* Step trace (direct parity tests of the decoder log-probs / CTC prefix scores / pre-beam against the reference's
+ * batch_score_hypotheses, beam_search.py:71-185): the next `max_steps` search iterations each copy one fixed-size
+ * record into the caller-owned device buffer, taken after score combination and before pruning.  Record fields
+ * (byte offsets in offsets8): 0 n_rows int32[1], 1 row_sh int32[R] (row -> stream * beam + hyp), 2 logp float[R][V]
+ * (decoder log-softmax), 3 pre_ids int32[R][40], 4 psi float[R][40] (CTC log_psi of the 40 candidates), 5 psi_eos
+ * float[R], 6 ctc_s float[2][S][beam] (s_prev of both beam buffers), 7 ctl int32[S][16]; R = S * beam.
+ * dev_buf = NULL switches the trace off.  Graph replay is suspended while a trace is being recorded. */
+int sc_engine_trace_layout(void* handle, int64_t* offsets8, int64_t* record_bytes);
+int sc_engine_set_trace(void* handle, void* dev_buf, size_t bytes, int32_t max_steps);
+/* Named host-side counters: "graphs_replayed" (cudaGraphLaunch calls so far), "graph_failed", "trace_steps". */
+int sc_engine_counter(void* handle, const char* name, int64_t* value);
+
 /* Live kernel timing with CUDA-event pairs on the launching stream (bench.py roofline and step breakdown).
  * tag > 0: every launch of that kernel; tag = -1: every kernel, decode steps sampled every `stride` steps.
  * Tags: 1 ctc_prefix, 2 dec_self_attn, 3 dec_cross_attn, 4 dec_ffn1, 5 enc_ffn1, 6 prebeam, 7 enc_attn, 8 conv2,
@@ -185,6 +198,11 @@ int sc_layernorm_f32(const float* x, const float* w, const float* b, float* y, i
 /* y = act(x W^T + bias) + residual  (torch.nn.functional.linear; fp32 CUDA-core path) */
 int sc_linear_f32(const float* x, const float* w, const float* bias, const float* residual, float* y,
                   int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
+/* same contract (fp32 in, fp32 out, fp32-class accuracy) on the tcgen05 tensor cores: x is split into fp16 hi / lo
+ * parts inside the kernel, w_planes_f16 = [2][n][k] fp16 (hi plane, then (w - hi) * 2^11) built once per weight
+ * (speechcatcher_b200/weights.py:split_f16); three UMMAs per K step into two TMEM accumulators (precision 2) */
+int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, const float* residual, float* y,
+                 int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
 /* same contract on the tcgen05 tensor-core path: bf16 operands, fp32 accumulate */
 int sc_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual,
                    float* y_f32, void* y_bf16, int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);

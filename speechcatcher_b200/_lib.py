@@ -53,6 +53,9 @@ SYMBOLS = {
     "sc_engine_token_capacity": (C.c_int, [_vp, _pi32]),
     "sc_engine_last_plan": (C.c_int, [_vp, _i32, C.POINTER(ScStreamPlan)]),
     "sc_engine_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_sz)]),
+    "sc_engine_trace_layout": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sc_engine_set_trace": (C.c_int, [_vp, _vp, _sz, _i32]),
+    "sc_engine_counter": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
     "sc_engine_set_option": (C.c_int, [_vp, C.c_char_p, _i32]),
     "sc_engine_profile_begin": (C.c_int, [_vp, _i32, _i32, _i32]),
     "sc_engine_profile_end": (C.c_int, [_vp, _i32, _pi32, _pd, _pd, C.POINTER(C.c_uint64)]),
@@ -67,6 +70,7 @@ SYMBOLS = {
     "sc_segment_search": (C.c_int, [_pd, C.c_int64, C.POINTER(ScSegmentParams), C.POINTER(C.c_int64), _i32, _pi32]),
     "sc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "sc_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "sc_linear_x3": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "sc_linear_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "sc_linear_bf16_lnA": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "sc_ffn_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

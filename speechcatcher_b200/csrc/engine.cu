@@ -33,6 +33,8 @@ int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
                         int K, int relu, const int* n_rows_dev, const float* ln_w, const float* ln_b,
                         __nv_bfloat16* ln_out, cudaStream_t st);
 
+int launch_gemm_x3(const GemmArgs& g, const void* W2, cudaStream_t st);
+
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Caps {
@@ -72,6 +74,8 @@ struct Engine {
   Caps cap;
   Planner planner;
   std::unordered_map<std::string, const void*> wmap;
+  // precision 2 (fp32 results on the tensor cores): fp32 weight pointer -> its two fp16 planes (kernels_gemm_x3.cu)
+  std::unordered_map<const float*, const void*> x3map;
   bool finalized = false;
   // weights
   const float *pe = nullptr, *c1w = nullptr, *c1b = nullptr, *c2w = nullptr, *c2b = nullptr, *eow = nullptr, *eob = nullptr;
@@ -150,6 +154,12 @@ struct Engine {
   int step_graph_launches = 0;
   struct EncGraph { cudaGraphExec_t exec; int launches; int uses; };
   std::unordered_map<int, EncGraph> enc_graphs;    // n_blk -> captured encoder stack
+
+  // step trace (tests): the first `trace_max` search iterations after sc_engine_set_trace copy their score tensors
+  // into a caller-owned device buffer (one fixed-size record per iteration, layout: sc_engine_trace_layout)
+  unsigned char* trace_buf = nullptr;
+  int trace_max = 0, trace_used = 0;
+  int graphs_replayed = 0;                  // cudaGraphLaunch calls since creation (tests assert that capture happened)
 
   explicit Engine(const ScConfig& c) : cfg(c), cap(make_caps(c)), planner(c.n_streams), pending_bound(c.n_streams, 0), last_plan(c.n_streams) {}
 };
@@ -251,6 +261,16 @@ struct Lin {
 
 static Lin with_ln(Lin l, const float* w, const float* b, __nv_bfloat16* out) { l.ln_w = w; l.ln_b = b; l.ln_out = out; return l; }
 
+// fp32-result GEMM: CUDA-core kernel (precision 0) or the split-fp16 tensor-core kernel (precision 2)
+static int gemm_fp32(Engine& e, const GemmArgs& g, cudaStream_t st) {
+  if (e.cfg.precision == 2) {
+    auto it = e.x3map.find(g.W);
+    if (it == e.x3map.end()) { set_last_error("precise tensor-core mode: no fp16 planes registered for a %dx%dx%d linear", g.M, g.N, g.K); return -1; }
+    return launch_gemm_x3(g, it->second, st);
+  }
+  return launch_gemm_f32(g, st);
+}
+
 static int linear(Engine& e, const Lin& l, cudaStream_t st) {
   e.launches++;
   if (e.cfg.precision == 1) {
@@ -261,7 +281,7 @@ static int linear(Engine& e, const Lin& l, cudaStream_t st) {
   GemmArgs g;
   g.A = l.A; g.lda = l.lda; g.W = l.W; g.bias = l.bias; g.R = l.R; g.ldr = l.ldr; g.C = l.C; g.ldc = l.ldc;
   g.M = l.M; g.N = l.N; g.K = l.K; g.relu = l.relu; g.n_rows_dev = l.n_rows_dev; g.c_row_off = l.c_row_off;
-  return launch_gemm_f32(g, st);
+  return gemm_fp32(e, g, st);
 }
 
 #define TRY(x) do { int _r = (x); if (_r != 0) return _r; } while (0)
@@ -371,6 +391,36 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------- step trace (direct K6/K7/K8 parity tests)
+// Record of one search iteration, taken after score combination and before pruning (all sizes in bytes, 256-aligned):
+//   0 n_rows int[1] | 1 row_sh int[R] | 2 logp float[R][V] | 3 pre_ids int[R][40] | 4 psi float[R][40] | 5 psi_eos float[R]
+//   | 6 ctc_s float[2][S][B] | 7 ctl int[S][16]
+static void trace_layout(const Engine& e, int64_t off[8], int64_t* rec_bytes) {
+  const int64_t R = e.cap.R, V = e.cfg.vocab, S = e.cfg.n_streams, B = e.cfg.beam;
+  const int64_t sz[8] = {4, 4 * R, 4 * R * V, 4 * R * kPreBeam, 4 * R * kPreBeam, 4 * R, 4 * 2 * S * B, (int64_t)sizeof(StreamCtl) * S};
+  int64_t o = 0;
+  for (int i = 0; i < 8; ++i) { off[i] = o; o += (int64_t)align_up((size_t)sz[i]); }
+  *rec_bytes = o;
+}
+
+static int trace_step(Engine& e, cudaStream_t st) {
+  int64_t off[8], rec; trace_layout(e, off, &rec);
+  unsigned char* d = e.trace_buf + (size_t)rec * e.trace_used;
+  const SearchBuffers& sb = e.sb;
+  const size_t R = e.cap.R, V = e.cfg.vocab, S = e.cfg.n_streams, B = e.cfg.beam;
+  auto cp = [&](int i, const void* src, size_t bytes) { return cudaMemcpyAsync(d + off[i], src, bytes, cudaMemcpyDeviceToDevice, st); };
+  SCB_CUDA_CHECK(cp(0, sb.n_rows, 4));
+  SCB_CUDA_CHECK(cp(1, sb.row_sh, 4 * R));
+  SCB_CUDA_CHECK(cp(2, e.dlogp, 4 * R * V));
+  SCB_CUDA_CHECK(cp(3, sb.pre_ids, 4 * R * kPreBeam));
+  SCB_CUDA_CHECK(cp(4, sb.psi, 4 * R * kPreBeam));
+  SCB_CUDA_CHECK(cp(5, sb.psi_eos, 4 * R));
+  SCB_CUDA_CHECK(cp(6, sb.ctc_s, 4 * 2 * S * B));
+  SCB_CUDA_CHECK(cp(7, sb.ctl, sizeof(StreamCtl) * S));
+  e.trace_used++;
+  return 0;
+}
+
 // ---------------------------------------------------------------- one search iteration for all active streams
 static int run_decode_step(Engine& e, cudaStream_t st) {
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, V = c.vocab, R = e.cap.R;
@@ -421,6 +471,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   PD(T_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
   PD(T_CTC_PREFIX, launch_ctc_prefix(sb, st));
   PD(T_COMBINE, launch_combine_topk(sb, e.dlogp, st));
+  if (e.trace_buf && e.trace_used < e.trace_max) TRY(trace_step(e, st));
   PD(T_PRUNE, launch_beam_prune(sb, st));
   PD(T_CTC_UPDATE, launch_ctc_state_update(sb, st));
   PD(T_STEP_FINISH, launch_step_finish(sb, st));
@@ -465,13 +516,14 @@ static int capture_graph(Engine& e, cudaStream_t st, Fn fn, cudaGraphExec_t* exe
 }
 
 static int decode_step(Engine& e, cudaStream_t st) {
-  if (!e.graph_decode || e.graph_failed || e.prof_tag != 0) return run_decode_step(e, st);
+  if (!e.graph_decode || e.graph_failed || e.prof_tag != 0 || (e.trace_buf && e.trace_used < e.trace_max)) return run_decode_step(e, st);
   if (!e.step_graph) {
     if (e.graph_warm < 2) { e.graph_warm++; return run_decode_step(e, st); }
     TRY(capture_graph(e, st, [&](cudaStream_t s) { return run_decode_step(e, s); }, &e.step_graph, &e.step_graph_launches));
     if (!e.step_graph) return run_decode_step(e, st);
   }
   SCB_CUDA_CHECK(cudaGraphLaunch(e.step_graph, st));
+  e.graphs_replayed++;
   e.launches += e.step_graph_launches;
   e.step_seq++;
   return 0;
@@ -492,6 +544,7 @@ static int encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
     if (!g.exec) return run_encoder_layers(e, n_blk, st);
   }
   SCB_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+  e.graphs_replayed++;
   e.launches += g.launches;
   g.uses++;
   return 0;
@@ -514,6 +567,7 @@ static int check_cfg(const ScConfig* c) {
                    c->d_model, c->vocab, c->ffn);
     return SC_ERR_ARG;
   }
+  if (c->precision < 0 || c->precision > 2) { set_last_error("precision %d out of range [0, 2]", c->precision); return SC_ERR_ARG; }
   if (c->beam < 1 || c->beam > 20) { set_last_error("beam %d out of range [1, 20]", c->beam); return SC_ERR_ARG; }
   if (c->n_streams < 1 || c->max_chunk < 1 || c->max_frames < 32) { set_last_error("bad capacities"); return SC_ERR_ARG; }
   // the positional table holds 5000 positions like the reference's (positional_encoding.py:31,72): an un-reset
@@ -666,6 +720,28 @@ int sc_engine_finalize(void* handle) {
     w.f1w = getf(p + "ff1.w"); w.f1b = getf(p + "ff1.b"); w.f2w = getf(p + "ff2.w"); w.f2b = getf(p + "ff2.b");
     w.sqkvw16 = geth(p + "self_qkv.w"); w.sow16 = geth(p + "self_o.w"); w.cqw16 = geth(p + "src_q.w");
     w.ckvw16 = geth(p + "src_kv.w"); w.cow16 = geth(p + "src_o.w"); w.f1w16 = geth(p + "ff1.w"); w.f2w16 = geth(p + "ff2.w");
+  }
+  if (e->cfg.precision == 2) {
+    // every GEMM weight needs its fp16 hi / lo planes ("<name>.x3", weights.split_f16)
+    e->x3map.clear();
+    for (auto& kv : e->wmap) {
+      const std::string& n = kv.first;
+      if (n.size() > 3 && n.compare(n.size() - 3, 3, ".x3") == 0) {
+        auto base = e->wmap.find(n.substr(0, n.size() - 3));
+        if (base != e->wmap.end()) e->x3map[(const float*)base->second] = kv.second;
+      }
+    }
+    auto need = [&](const float* w, const std::string& n) { if (w && !e->x3map.count(w)) missing += n + ".x3 "; };
+    need(e->c2w, "enc.conv2.w"); need(e->eow, "enc.out.w"); need(e->ctcw, "ctc.w"); need(e->doutw, "dec.out.w");
+    for (int l = 0; l < e->cfg.enc_layers; ++l) {
+      const EncLayerW& w = e->enc[l]; const std::string p = "enc." + std::to_string(l) + ".";
+      need(w.qkvw, p + "qkv.w"); need(w.ow, p + "o.w"); need(w.f1w, p + "ff1.w"); need(w.f2w, p + "ff2.w");
+    }
+    for (int l = 0; l < e->cfg.dec_layers; ++l) {
+      const DecLayerW& w = e->dec[l]; const std::string p = "dec." + std::to_string(l) + ".";
+      need(w.sqkvw, p + "self_qkv.w"); need(w.sow, p + "self_o.w"); need(w.cqw, p + "src_q.w"); need(w.ckvw, p + "src_kv.w");
+      need(w.cow, p + "src_o.w"); need(w.f1w, p + "ff1.w"); need(w.f2w, p + "ff2.w");
+    }
   }
   if (!missing.empty()) { set_last_error("missing weights: %.400s", missing.c_str()); return SC_ERR_STATE; }
   // conv2 implicit-GEMM segment offsets: K = (kt, kf, c) -> ((kt * 39) + kf) * D
@@ -881,7 +957,7 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
       g.A = e.h1; g.a_row_off = e.d_c2_a; g.a_seg_off = e.d_c2_seg; g.seg_len = D; g.W = e.c2w; g.bias = e.c2b;
       g.C = e.h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
       if (e.prof_tag == T_CONV2) e.prof_flops += 2.0 * g.M * (double)g.N * g.K;
-      PE(T_CONV2, launch_gemm_f32(g, st));
+      PE(T_CONV2, gemm_fp32(e, g, st));
     }
     {
       Lin o{e.h2, 19 * D, e.h2_16, e.eow, e.eow16, e.eob, nullptr, 0, e.subbuf, 0, nullptr, sub_rows, D, 19 * D, 0, nullptr};
@@ -915,7 +991,7 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
       g.A = e->encbuf; g.a_row_off = e->d_en_a; g.W = e->ctcw; g.bias = e->ctcb; g.C = e->ctcx; g.c_row_off = e->d_en_ctc;
       g.M = n_en; g.N = V; g.K = D;
 #define e eref
-      PE(T_CTC_HEAD, launch_gemm_f32(g, st));
+      PE(T_CTC_HEAD, gemm_fp32(e, g, st));
 #undef e
     }
     TRY(launch_logsoftmax_rows(e->ctcx, e->d_en_ctc, e->d_en_flag, n_en, V, st));
@@ -933,7 +1009,7 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
         kv.A = e->encbuf; kv.a_row_off = e->d_en_a; kv.W = e->dec[l].ckvw; kv.bias = e->dec[l].ckvb;
         kv.C = dst; kv.c_row_off = e->d_en_kv; kv.M = n_en; kv.N = 2 * D; kv.K = D;
 #define e eref
-        PE(T_XKV, launch_gemm_f32(kv, st));
+        PE(T_XKV, gemm_fp32(e, kv, st));
 #undef e
       }
     }
@@ -1064,6 +1140,32 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
   return SC_OK;
 }
 
+int sc_engine_trace_layout(void* handle, int64_t* offsets8, int64_t* record_bytes) {
+  Engine* e = (Engine*)handle;
+  if (!e || !offsets8 || !record_bytes) { set_last_error("trace_layout: null argument"); return SC_ERR_ARG; }
+  trace_layout(*e, offsets8, record_bytes);
+  return SC_OK;
+}
+
+int sc_engine_set_trace(void* handle, void* dev_buf, size_t bytes, int32_t max_steps) {
+  Engine* e = (Engine*)handle;
+  if (!e) { set_last_error("set_trace: null handle"); return SC_ERR_ARG; }
+  int64_t off[8], rec; trace_layout(*e, off, &rec);
+  if (dev_buf && (max_steps < 0 || (size_t)rec * (size_t)max_steps > bytes)) { set_last_error("set_trace: buffer too small (%zu < %lld x %d)", bytes, (long long)rec, max_steps); return SC_ERR_ARG; }
+  e->trace_buf = (unsigned char*)dev_buf; e->trace_max = dev_buf ? max_steps : 0; e->trace_used = 0;
+  return SC_OK;
+}
+
+int sc_engine_counter(void* handle, const char* name, int64_t* value) {
+  Engine* e = (Engine*)handle;
+  if (!e || !name || !value) { set_last_error("counter: null argument"); return SC_ERR_ARG; }
+  if (strcmp(name, "graphs_replayed") == 0) { *value = e->graphs_replayed; return SC_OK; }
+  if (strcmp(name, "trace_steps") == 0) { *value = e->trace_used; return SC_OK; }
+  if (strcmp(name, "graph_failed") == 0) { *value = e->graph_failed ? 1 : 0; return SC_OK; }
+  set_last_error("unknown counter %s", name);
+  return SC_ERR_ARG;
+}
+
 int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   Engine* e = (Engine*)handle;
   if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
@@ -1166,6 +1268,12 @@ int sc_linear_f32(const float* x, const float* w, const float* bias, const float
   GemmArgs g;
   g.A = x; g.lda = k; g.W = w; g.bias = bias; g.R = residual; g.ldr = n; g.C = y; g.ldc = n; g.M = m; g.N = n; g.K = k; g.relu = relu;
   return launch_gemm_f32(g, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, const float* residual, float* y, int32_t m,
+                 int32_t n, int32_t k, int32_t relu, void* stream) {
+  GemmArgs g;
+  g.A = x; g.lda = k; g.bias = bias; g.R = residual; g.ldr = n; g.C = y; g.ldc = n; g.M = m; g.N = n; g.K = k; g.relu = relu;
+  return launch_gemm_x3(g, w_planes_f16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }
 int sc_linear_bf16(const void* x, const void* w, const float* bias, const float* residual, float* y, void* y16, int32_t m,
                    int32_t n, int32_t k, int32_t relu, void* stream) {

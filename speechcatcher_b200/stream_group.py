@@ -18,7 +18,11 @@ import yaml
 from . import _lib
 from ._lib import ScConfig, ScPushStats, ScStreamPlan
 from .model_files import find_checkpoint, find_stats, read_stats, state_dict_of
-from .weights import bf16_names, pack_weights
+from .weights import bf16_names, pack_weights, split_f16
+
+# engine precision codes (include/speechcatcher_b200.h ScConfig.precision)
+PRECISIONS = {"float32_simt": 0, "bfloat16": 1, "float32_tc": 2}
+DEFAULT_FP32 = "float32_simt"     # what dtype="float32" means
 
 EOS_FILTER_ID = 1023   # hard-coded in the reference's output filter (speech2text_streaming.py:474)
 
@@ -53,9 +57,14 @@ class StreamGroup:
         self.device = torch.device(device)
         self.model_dir = Path(model_dir)
         self.n_streams, self.beam_size, self.ctc_weight, self.use_bbd = n_streams, beam_size, ctc_weight, use_bbd
-        if dtype not in ("float32", "bfloat16"):
-            raise ValueError("dtype must be 'float32' (parity mode) or 'bfloat16' (tensor-core mode)")
-        self.precision = 0 if dtype == "float32" else 1
+        import os
+        if dtype == "float32":          # which GEMM kernel serves the fp32 mode: SCB_FP32_GEMM = "tc" | "simt"
+            dtype = {"tc": "float32_tc", "simt": "float32_simt"}.get(os.environ.get("SCB_FP32_GEMM", ""), DEFAULT_FP32)
+        if dtype not in PRECISIONS:
+            raise ValueError("dtype must be 'float32' (parity mode; 'float32_tc' = split-fp16 tensor-core GEMMs, "
+                             "'float32_simt' = CUDA-core GEMMs) or 'bfloat16' (bf16 tensor-core mode)")
+        self.dtype = dtype
+        self.precision = PRECISIONS[dtype]
         ckpt = torch.load(_find_checkpoint(self.model_dir), map_location="cpu")
         sd = state_dict_of(ckpt)
         vocab = sd["decoder.embed.0.weight"].shape[0]
@@ -90,6 +99,9 @@ class StreamGroup:
             if self.precision == 1:
                 for k in bf16_names(self.cfg.enc_layers, self.cfg.dec_layers):
                     self.weights[k + ".bf16"] = self.weights[k].to(torch.bfloat16).contiguous()
+            if self.precision == 2:
+                for k in bf16_names(self.cfg.enc_layers, self.cfg.dec_layers):
+                    self.weights[k + ".x3"] = split_f16(self.weights[k])
             for k, v in self.weights.items():
                 _lib.check(self.lib.sc_engine_set_weight(self.handle, k.encode(), C.c_void_p(v.data_ptr()),
                                                          v.numel()), f"set_weight({k})")
@@ -103,7 +115,6 @@ class StreamGroup:
         # The engine runs on the stream that is current at construction.  own_stream=True gives it a stream of its own
         # (ordered after the caller's stream at every push): needed for the CUDA-graph replay when the caller works on
         # the legacy default stream, which cannot be captured.
-        import os
         own_stream = own_stream or os.environ.get("SCB_OWN_STREAM") == "1"     # switch for whole-suite validation runs
         self.own_stream = bool(own_stream)
         self.stream = torch.cuda.Stream(device=self.device) if own_stream else torch.cuda.current_stream(self.device)
@@ -240,6 +251,47 @@ class StreamGroup:
         n, l = n_hyp.value, ln.value
         return ([yseq[h, :l].tolist() for h in range(n)], score[:n].tolist(),
                 [xpos[h, :l].tolist() for h in range(n)], pidx.value)
+
+    # ------------------------------------------------------------------ step trace / counters (parity tests)
+    def counter(self, name: str) -> int:
+        v = C.c_int64()
+        _lib.check(self.lib.sc_engine_counter(self.handle, name.encode(), C.byref(v)), f"counter({name})")
+        return int(v.value)
+
+    def trace_begin(self, max_steps: int):
+        """Record the score tensors of the next `max_steps` search iterations (sc_engine_set_trace)."""
+        off = (C.c_int64 * 8)()
+        rec = C.c_int64()
+        _lib.check(self.lib.sc_engine_trace_layout(self.handle, off, C.byref(rec)), "trace_layout")
+        self._trace_off, self._trace_rec = [int(o) for o in off], int(rec.value)
+        self._trace_dev = torch.zeros(max(1, max_steps) * self._trace_rec, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.sc_engine_set_trace(self.handle, C.c_void_p(self._trace_dev.data_ptr()),
+                                                self._trace_dev.numel(), max_steps), "set_trace")
+
+    def trace_end(self) -> List[dict]:
+        """One dict per recorded iteration with the active rows only: rows (stream, hyp), logp [n, V], pre_ids [n, 40],
+        psi [n, 40], psi_eos [n], s_prev [n] (CTC prefix score of each row's hypothesis)."""
+        n_steps = self.counter("trace_steps")
+        torch.cuda.synchronize(self.device)
+        raw = self._trace_dev.cpu().numpy()
+        _lib.check(self.lib.sc_engine_set_trace(self.handle, None, 0, 0), "set_trace(off)")
+        S, B, V, R = self.n_streams, self.beam_size, self.cfg.vocab, self.n_streams * self.beam_size
+        o = self._trace_off
+        out = []
+        for i in range(n_steps):
+            r = raw[i * self._trace_rec:(i + 1) * self._trace_rec]
+            f32 = lambda k, n: r[o[k]:o[k] + 4 * n].view(np.float32)
+            i32 = lambda k, n: r[o[k]:o[k] + 4 * n].view(np.int32)
+            n = int(i32(0, 1)[0])
+            row_sh = i32(1, R)[:n].copy()
+            ctl = i32(7, S * 16).reshape(S, 16)
+            ctc_s = f32(6, 2 * S * B).reshape(2, S, B)
+            st, hy = row_sh // B, row_sh % B
+            out.append(dict(rows=list(zip(st.tolist(), hy.tolist())), logp=f32(2, R * V).reshape(R, V)[:n].copy(),
+                            pre_ids=i32(3, R * 40).reshape(R, 40)[:n].copy(), psi=f32(4, R * 40).reshape(R, 40)[:n].copy(),
+                            psi_eos=f32(5, R)[:n].copy(), s_prev=ctc_s[ctl[st, 0], st, hy].copy(),
+                            Tb=ctl[st, 7].copy(), length=ctl[st, 2].copy()))
+        return out
 
     # ------------------------------------------------------------------ live kernel timing (bench.py roofline)
     PROF_TAGS = {"ctc_prefix": 1, "dec_self_attn": 2, "dec_cross_attn": 3, "dec_ffn1": 4, "enc_ffn1": 5, "prebeam": 6,

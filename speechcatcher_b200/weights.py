@@ -88,7 +88,18 @@ def pack_weights(sd: Dict[str, torch.Tensor], enc_layers: int, dec_layers: int, 
     return out
 
 
-# GEMM weights that get a bf16 copy in the tensor-core mode
+def split_f16(w: torch.Tensor) -> torch.Tensor:
+    """fp32 weight [N][K] -> the two fp16 planes [2][N][K] of the split-precision tensor-core GEMM
+    (csrc/kernels_gemm_x3.cu): hi = fp16(w), lo = fp16((w - hi) * 2^11); w == hi + lo * 2^-11 to 2^-22 relative."""
+    w = w.detach().to(torch.float32)
+    hi = w.to(torch.float16)
+    if not torch.isfinite(hi).all():
+        raise ValueError("weight magnitude exceeds the fp16 range of the split-precision GEMM")
+    lo = ((w - hi.to(torch.float32)) * 2048.0).to(torch.float16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+# GEMM weights that get a bf16 copy in the tensor-core mode (and fp16 hi / lo planes in the precise tensor-core mode)
 def bf16_names(enc_layers: int, dec_layers: int):
     names = ["enc.out.w", "enc.conv2.w", "ctc.w", "dec.out.w"]
     for l in range(enc_layers):

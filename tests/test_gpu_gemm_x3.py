@@ -1,0 +1,86 @@
+"""GPU: the split-precision tensor-core GEMM (sc_linear_x3: fp32 in, fp32 out, fp16 hi/lo operands on tcgen05) against
+an fp64 PyTorch reference of the same op, next to the CUDA-core fp32 GEMM it replaces.
+
+Bar: fp32-class accuracy -- the error against fp64 must stay within a small multiple of what the true-fp32 FMA kernel
+(sc_linear_f32) shows on the same operands, and far below anything a bf16 operand rounding (2^-9) would give."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # (M, N, K, relu, residual)
+    (128, 128, 64, 0, False),
+    (128, 64, 256, 0, False),
+    (333, 768, 256, 0, False),        # ragged M, QKV shape
+    (77, 256, 2048, 0, True),         # FFN2 with in-place residual, small M (BN = 64 path)
+    (130, 2048, 256, 1, False),       # FFN1 + ReLU
+    (5, 1024, 256, 0, False),         # output layer, tiny M
+    (64, 256, 4864, 0, False),        # embed.out
+    (2560, 256, 256, 0, True),        # decoder projections with residual
+    (2560, 768, 256, 0, False),
+    (10752, 2048, 256, 1, False),     # encoder FFN1 at 256 streams x 1 block (BN = 128 path)
+    (10752, 256, 2048, 0, True),
+    (21504, 768, 256, 0, False),      # BN = 128, many tiles
+    (3000, 256, 2304, 1, False),      # conv2 shape (dense A)
+    (640, 512, 256, 0, False),        # cross K|V
+]
+
+
+def _planes(w):
+    from speechcatcher_b200.weights import split_f16
+    return split_f16(w)
+
+
+@pytest.mark.parametrize("M,N,K,relu,res", SHAPES)
+def test_linear_x3_fp32_class_accuracy(M, N, K, relu, res):
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g, device="cuda") * 1.7 + 0.1
+    w = torch.randn(N, K, generator=g, device="cuda") / K ** 0.5
+    bias = torch.randn(N, generator=g, device="cuda")
+    r = torch.randn(M, N, generator=g, device="cuda")
+    w2 = _planes(w)
+    y = r.clone() if res else torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.sc_linear_x3(a.data_ptr(), w2.data_ptr(), bias.data_ptr(), y.data_ptr() if res else None,
+                                y.data_ptr(), M, N, K, relu, None), "linear_x3")
+    y32 = r.clone() if res else torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.sc_linear_f32(a.data_ptr(), w.data_ptr(), bias.data_ptr(), y32.data_ptr() if res else None,
+                                 y32.data_ptr(), M, N, K, relu, None), "linear_f32")
+    torch.cuda.synchronize()
+    want = a.double() @ w.double().t() + bias.double()
+    if relu:
+        want = want.relu()
+    if res:
+        want = want + r.double()
+    assert torch.isfinite(y).all()
+    err = (y.double() - want).abs()
+    err32 = (y32.double() - want).abs()
+    scale = want.abs().max().item()
+    # fp32-class: max error within 4x of the CUDA-core fp32 kernel's (plus one fp32 ulp of the row scale), rms likewise
+    assert err.max().item() <= 4.0 * err32.max().item() + 2.0 ** -22 * scale, \
+        f"x3 max err {err.max().item():.3e} vs fp32 kernel {err32.max().item():.3e} (scale {scale:.2f})"
+    assert err.pow(2).mean().sqrt().item() <= 4.0 * err32.pow(2).mean().sqrt().item() + 2.0 ** -24 * scale
+    # and nowhere near a bf16 / fp16 single-pass result
+    assert err.max().item() <= 2e-5 * max(1.0, scale)
+
+
+def test_linear_x3_small_and_large_magnitudes():
+    """Operands far from 1: tiny values (below the fp16 normal range) and large ones (up to ~1e3) keep fp32-class
+    *absolute* accuracy relative to the output scale."""
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 256, 256, 256
+    for a_scale, w_scale in [(1e-4, 1.0), (300.0, 0.05), (1.0, 1e-5), (1e-6, 1e-3)]:
+        a = torch.randn(M, K, generator=g, device="cuda") * a_scale
+        w = torch.randn(N, K, generator=g, device="cuda") * w_scale
+        y = torch.empty(M, N, device="cuda")
+        _lib.check(lib.sc_linear_x3(a.data_ptr(), _planes(w).data_ptr(), None, None, y.data_ptr(), M, N, K, 0, None), "x3")
+        torch.cuda.synchronize()
+        want = a.double() @ w.double().t()
+        scale = want.abs().max().item()
+        floor = 2.0 ** -33 * K * max(a_scale, 1e-30) * max(w_scale, 1e-30) * 16      # fp16 subnormal floor of the low parts
+        assert (y.double() - want).abs().max().item() <= 3e-6 * scale + floor, (a_scale, w_scale)

@@ -48,7 +48,7 @@ def test_layernorm_and_linear_ops():
         assert (out.cpu().double() - want).abs().max() < 2e-5, (m, n, k)
 
 
-def _run_case(case, check_internals=True):
+def _run_case(case, check_internals=True, dtype="float32"):
     from speechcatcher_b200 import Speech2TextStreaming
     from speechcatcher_b200.synthetic import synth_audio
     meta, calls, _ = load_golden(case)
@@ -56,7 +56,7 @@ def _run_case(case, check_internals=True):
     audio = synth_audio(meta["stream"], meta["n_samples"], meta["kind"])
     max_chunk = max(8192, max(e - s for s, e, _ in meta["calls"]))
     gpu = Speech2TextStreaming(md, beam_size=meta["beam"], ctc_weight=0.3, device="cuda:0", use_bbd=meta["use_bbd"],
-                               max_chunk=max_chunk)
+                               max_chunk=max_chunk, dtype=dtype)
     grp = gpu.group
     cap_feat = grp.buffer("featbuf").numel() // 80
     enc_seen = 0
@@ -85,7 +85,14 @@ def _run_case(case, check_internals=True):
 
 @pytest.mark.parametrize("case", [c for c in GOLDEN_CASES])
 def test_golden_nbest_exact(case):
-    _run_case(case)
+    _run_case(case, dtype="float32_simt")
+
+
+@pytest.mark.parametrize("case", [c for c in GOLDEN_CASES])
+def test_golden_nbest_exact_tensor_core(case):
+    """Same bar (n-best, timestamps, order, process_idx exact; encoder 1e-3) with every Linear on the tcgen05 tensor
+    cores as a split-fp16 GEMM (precision 2, csrc/kernels_gemm_x3.cu)."""
+    _run_case(case, dtype="float32_tc")
 
 
 def test_frontend_features_vs_golden():
