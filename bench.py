@@ -236,7 +236,7 @@ def main():
         kw = dict(beam_size=args.beam, ctc_weight=0.3, dtype=dtype, use_bbd=False, max_chunk=CHUNK,
                   max_seconds=args.seconds + 1.0)
         if G == 1:
-            g = StreamGroup(md, n_streams=S, device=dev, **kw)
+            g = StreamGroup(md, n_streams=S, device=dev, own_stream=True, **kw)     # own high-priority stream
             g.set_option("lazy_threshold", lazy)
             sg_, shards = None, [g]
         else:

@@ -43,6 +43,12 @@ CASES = {
     "xl_d4_b10_eos": ("xl_d4", 10, 6 * 16000 + 999, "noise", "A", False, 1.0, 2, 7.0),
     # live-server pattern (speechcatcher_server.py:252-270): utterances finalised mid-stream, NO reset in between
     "m_d2_b5_eos_live": ("m_d2", 5, 16 * CHUNK, "noise", "L", False, 1.0, 0, 7.0),
+    # the benchmark's own regime: 60 s utterances that run into the global 500-step cap
+    # (beam_search.py:701,821,827-836; T up to 1500, L up to 500) and a full-depth XL case; "lite" records hold the
+    # beams of every call (int16 arrays) but no feature / encoder tensors
+    "m_d2_b5_60s": ("m_d2", 5, 60 * 16000, "noise", "A", False, 1.0, 0, 0.0, True),
+    "xl_d4_b10_60s": ("xl_d4", 10, 60 * 16000, "noise", "A", False, 1.0, 0, 0.0, True),
+    "xl_b10_20s": ("xl", 10, 20 * 16000, "noise", "A", False, 1.0, 0, 0.0, True),
 }
 
 
@@ -152,15 +158,24 @@ def compare(ref, orc, name):
     return dev
 
 
-def pack(rec, trace, meta):
+def pack(rec, trace, meta, lite=False):
     out = {"meta": np.array(json.dumps(meta))}
     for i, r in enumerate(rec):
+        out[f"c{i}_score"] = np.array(r["score"], dtype=np.float64)
+        out[f"c{i}_process_idx"] = np.array(r["process_idx"])
+        if lite:
+            # beams as int16 arrays [n_hyp][len] (block-synchronous: equal lengths); "called" = the frontend emitted
+            out[f"c{i}_called"] = np.array(r["feats"] is not None)
+            out[f"c{i}_nfeat"] = np.array(0 if r["feats"] is None else r["feats"].shape[0])
+            out[f"c{i}_nenc"] = np.array(0 if r["enc"] is None else r["enc"].shape[0])
+            out[f"c{i}_yseq"] = np.array(r["yseq"], dtype=np.int16).reshape(len(r["yseq"]), -1)
+            out[f"c{i}_xpos"] = np.array(r["xpos"], dtype=np.int16).reshape(len(r["xpos"]), -1)
+            out[f"c{i}_results"] = np.array(json.dumps(r["results"]))
+            continue
         if r["feats"] is not None:
             out[f"c{i}_feats"] = r["feats"].astype(np.float32)
         if r["enc"] is not None:
             out[f"c{i}_enc"] = r["enc"].astype(np.float32)
-        out[f"c{i}_score"] = np.array(r["score"], dtype=np.float64)
-        out[f"c{i}_process_idx"] = np.array(r["process_idx"])
         out[f"c{i}_json"] = np.array(json.dumps(dict(yseq=r["yseq"], xpos=r["xpos"], results=r["results"])))
     for j, t in enumerate(trace):
         for k in ("dec", "ctc", "comb"):
@@ -176,6 +191,7 @@ def main(only=None):
     for name, case in CASES.items():
         arch, beam, n, kind, pattern, bbd, sharpen, n_trace = case[:8]
         eos_bias = case[8] if len(case) > 8 else 0.0
+        lite = bool(case[9]) if len(case) > 9 else False
         if only and name not in only:
             continue
         with tempfile.TemporaryDirectory() as td:
@@ -191,9 +207,9 @@ def main(only=None):
                 dev["trace_" + k] = max(dev.get("trace_" + k, 0.0), d)
         meta = dict(arch=arch, beam=beam, n_samples=n, kind=kind, pattern=pattern, use_bbd=bbd,
                     sharpen=sharpen, eos_bias=eos_bias, seed=0, stream=0, calls=calls, chunk=CHUNK,
-                    ref_seconds=tr, oracle_seconds=to, oracle_vs_ref_dev=dev,
-                    torch=torch.__version__)
-        np.savez_compressed(outdir / f"{name}.npz", **pack(ref, rtrace, meta))
+                    ref_seconds=tr, oracle_seconds=to, oracle_vs_ref_dev=dev, lite=lite,
+                    final_process_idx=ref[-1]["process_idx"], torch=torch.__version__)
+        np.savez_compressed(outdir / f"{name}.npz", **pack(ref, rtrace, meta, lite))
         print(f"{name}: ref {tr:.1f}s oracle {to:.1f}s calls {len(calls)} "
               f"final_len {len(ref[-1]['yseq'][0]) if ref[-1]['yseq'] else 0} dev {dev}")
 

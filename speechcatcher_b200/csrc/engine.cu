@@ -609,7 +609,13 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   }
   cudaEventCreateWithFlags(&e->ev[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev[1], cudaEventDisableTiming);
-  cudaStreamCreateWithFlags(&e->st_enc, cudaStreamNonBlocking);
+  {
+    // frontend + encoder stream: lowest priority, so that the search chain (small dependent kernels on the caller's
+    // stream, which callers create with a higher priority) is never queued behind a wave of encoder GEMM CTAs
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&e->st_enc, cudaStreamNonBlocking, lo);
+  }
   cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_wave, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_enc, cudaEventDisableTiming);
@@ -798,10 +804,29 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
   }
   if (n < 0 || n > S) { set_last_error("push: n=%d out of range", n); return SC_ERR_ARG; }
   // ---------------- plan on the host
+  // The planner advances the host-side stream state; nothing reaches the device before every stream of the push has
+  // been validated, so any error up to the descriptor upload rolls the planner (and last_plan) back: a failed push
+  // leaves every stream exactly where it was.
   std::vector<StreamPush> plans(n);
+  struct Rollback {
+    Engine* e; std::vector<std::pair<int, StreamHost>> saved; std::vector<ScStreamPlan> plans_before; bool armed = true;
+    ~Rollback() {
+      if (!armed) return;
+      for (size_t i = saved.size(); i-- > 0;) { e->planner.restore(saved[i].first, saved[i].second); e->last_plan[saved[i].first] = plans_before[i]; }
+    }
+  } rollback{e, {}, {}};
+  rollback.saved.reserve(n); rollback.plans_before.reserve(n);
+  {
+    std::vector<char> seen(S, 0);
+    for (int i = 0; i < n; ++i) {
+      const int s = streams[i];
+      if (s < 0 || s >= S) { set_last_error("bad stream id %d", s); return SC_ERR_ARG; }
+      if (seen[s]) { set_last_error("stream %d listed twice in one push", s); return SC_ERR_ARG; }
+      seen[s] = 1;
+    }
+  }
   for (int i = 0; i < n; ++i) {
     const int s = streams[i];
-    if (s < 0 || s >= S) { set_last_error("bad stream id %d", s); return SC_ERR_ARG; }
     if (feats_dev) {
       // every capacity downstream (conv rows, sub-sampled frames, blocks) is sized for 12 carried + fmax new frames,
       // fmax = STFT frames of the largest waveform slab = feat_cap - 16 (make_caps)
@@ -818,7 +843,8 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
       }
       if (n_samples[i] > ld_wave) { set_last_error("ld_wave too small"); return SC_ERR_ARG; }
     }
-    const StreamHost before = e->planner.state(s);
+    rollback.saved.emplace_back(s, e->planner.state(s));
+    rollback.plans_before.push_back(e->last_plan[s]);
     plans[i] = feats_dev ? e->planner.push_features(s, n_samples[i], is_final[i] != 0)
                          : e->planner.push(s, n_samples[i], is_final[i] != 0);
     StreamPush& p = plans[i];
@@ -834,7 +860,6 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
     lp.called = p.called; lp.n_feat = p.n_feat; lp.n_sub = p.run_sub ? p.sd.t2 : 0; lp.n_blocks = (int)p.blocks.size();
     lp.n_enc_out = p.n_enc_out; lp.enc_len = e->planner.state(s).enc_len; lp.n_decode_blocks = (int)p.dq_T.size();
     lp.last_T = p.dq_T.empty() ? 0 : p.dq_T.back();
-    (void)before;
   }
   // ---------------- flatten into pinned staging
   unsigned char* hp = e->h_stage;
@@ -898,6 +923,7 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
       n_q++;
     }
   }
+  rollback.armed = false;      // validated: from here on device work is enqueued and the host state stands
   // ---------------- upload descriptors
   auto up = [&](void* dst, const void* src, size_t bytes) -> int {
     if (bytes == 0) return 0;

@@ -108,11 +108,14 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
   const float* w_ptr = w_ok ? p.W + (size_t)wn * p.K : nullptr;
 
   const int tx = tid & 15, ty = tid >> 4;   // thread -> 4 cols (tx*4..), 4 rows (ty*4..)
-  float acc[4][4];
+  // Two-level accumulation: FMA chains of 128 products (`acc`) are added into `tot` with round-to-nearest adds, so the
+  // rounding error of a K = 2048 dot product is that of 16 partial sums instead of one 2048-term chain (closer to the
+  // blocked summation of the reference's CPU GEMM; the decisions of the beam search hinge on ~1e-6 differences).
+  float acc[4][4], tot[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
 
   auto load_a = [&](int k0) -> float4 {
     if (!a_ok) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -145,8 +148,18 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    if (((k0 / GBK) & 7) == 7) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+    }
     __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] += tot[i][j];
   // epilogue
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -52,6 +52,7 @@ class Planner {
   explicit Planner(int n_streams) : hs_(n_streams) {}
   void reset(int s) { hs_[s] = StreamHost(); }
   const StreamHost& state(int s) const { return hs_[s]; }
+  void restore(int s, const StreamHost& h) { hs_[s] = h; }      // roll a failed push back (engine.cu push_impl)
 
   StreamPush push(int s, int n_new, bool is_final) {
     StreamHost& h = hs_[s];

@@ -22,7 +22,8 @@ class ShardedStreamGroup:
         assert n_streams % n_shards == 0, "n_streams must be a multiple of n_shards"
         self.device = torch.device(device)
         self.n_streams, self.n_shards, self.per = n_streams, n_shards, n_streams // n_shards
-        self.cuda_streams = [torch.cuda.Stream(device=self.device) for _ in range(n_shards)]
+        # high priority: the search chains of small kernels go ahead of the engines' (low-priority) encoder streams
+        self.cuda_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(n_shards)]
         self.shards: List[StreamGroup] = []
         for st in self.cuda_streams:                    # built one after another: shared constant tables
             with torch.cuda.stream(st):

@@ -136,8 +136,16 @@ class Speech2TextStreaming:
             raise ValueError("the engine can only be resized right after reset()")
         args = {**self._group_args, "n_streams": max(n_streams, g.n_streams),
                 "max_seconds": max(max_seconds, g.max_seconds)}
-        g.close()
-        self.group = self.model = StreamGroup(max_chunk=max(max_chunk, g.max_chunk), **args)
+        new_chunk = max(max_chunk, g.max_chunk)
+        StreamGroup.check_capacity(args["max_seconds"], new_chunk)      # raise BEFORE the old engine is given up
+        old_chunk = g.max_chunk
+        g.close()                                   # free the old workspace first: two engines may not fit side by side
+        try:
+            self.group = self.model = StreamGroup(max_chunk=new_chunk, **args)
+        except Exception:
+            # e.g. out of device memory: the facade must stay usable, so bring the previous engine back
+            self.group = self.model = StreamGroup(max_chunk=old_chunk, **self._group_args)
+            raise
         self._group_args = args
 
     def recognize(self, speech):

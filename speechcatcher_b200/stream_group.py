@@ -22,7 +22,7 @@ from .weights import bf16_names, pack_weights, split_f16
 
 # engine precision codes (include/speechcatcher_b200.h ScConfig.precision)
 PRECISIONS = {"float32_simt": 0, "bfloat16": 1, "float32_tc": 2}
-DEFAULT_FP32 = "float32_simt"     # what dtype="float32" means
+DEFAULT_FP32 = "float32_tc"       # what dtype="float32" means (both pass the reference goldens exactly)
 
 EOS_FILTER_ID = 1023   # hard-coded in the reference's output filter (speech2text_streaming.py:474)
 
@@ -73,10 +73,7 @@ class StreamGroup:
         enc, dec = conf.get("encoder_conf", {}), conf.get("decoder_conf", {})
         self.max_chunk = int(max_chunk)
         self.max_seconds = float(max_seconds)
-        max_frames = int(max_seconds * 25) + 64
-        if max_frames + 64 > 5000:
-            raise ValueError(f"max_seconds={max_seconds:g} exceeds what one un-reset stream can hold: the model's positional "
-                             "table has 5000 positions (reference positional_encoding.py:31), i.e. at most 194 s")
+        max_frames = self.check_capacity(max_seconds, max_chunk)
         self.cfg = ScConfig(
             d_model=enc.get("output_size", 256), enc_heads=enc.get("attention_heads", 4),
             enc_layers=enc.get("num_blocks", 12), dec_heads=dec.get("attention_heads", 4),
@@ -117,12 +114,27 @@ class StreamGroup:
         # the legacy default stream, which cannot be captured.
         own_stream = own_stream or os.environ.get("SCB_OWN_STREAM") == "1"     # switch for whole-suite validation runs
         self.own_stream = bool(own_stream)
-        self.stream = torch.cuda.Stream(device=self.device) if own_stream else torch.cuda.current_stream(self.device)
+        # the search is a chain of small dependent kernels: its stream gets the high priority so that its CTAs are
+        # scheduled ahead of the (large) encoder kernels of the engine's second stream
+        self.stream = (torch.cuda.Stream(device=self.device, priority=-1) if own_stream
+                       else torch.cuda.current_stream(self.device))
         self._wave_dev = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32, device=self.device)
         self._wave_host = torch.zeros(n_streams, self.max_chunk, dtype=torch.float32).pin_memory()
         self._h2d_done = None
         self.last_stats = ScPushStats()
         self.total_launches = 0
+
+    @staticmethod
+    def check_capacity(max_seconds: float, max_chunk: int) -> int:
+        """Validates the per-stream capacities an engine would be created with (before anything is allocated) and
+        returns the encoder-frame capacity."""
+        if int(max_chunk) < 1:
+            raise ValueError(f"max_chunk={max_chunk} must be positive")
+        max_frames = int(max_seconds * 25) + 64
+        if max_frames + 64 > 5000:
+            raise ValueError(f"max_seconds={max_seconds:g} exceeds what one un-reset stream can hold: the model's positional "
+                             "table has 5000 positions (reference positional_encoding.py:31), i.e. at most 194 s")
+        return max_frames
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -212,7 +224,12 @@ class StreamGroup:
         if L > self.max_chunk:
             raise ValueError(f"chunk of {L} samples exceeds max_chunk={self.max_chunk}")
         with torch.cuda.device(self.device):
-            self._wave_dev[:, :L].copy_(wave_host, non_blocking=True)
+            # like push(): with an engine-owned stream the copy is issued there, so that it is ordered after the previous
+            # push's reads of the staging buffer (a deferred / overlapped push returns before they have drained);
+            # otherwise the engine works on the caller's current stream and plain stream order does the same
+            copy_stream = self.stream if self.own_stream else torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(copy_stream):
+                self._wave_dev[:, :L].copy_(wave_host, non_blocking=True)
         return self.push_device(ids, self._wave_dev, lens, fin)
 
     def push_device(self, ids: np.ndarray, wave_dev: torch.Tensor, lens: np.ndarray, fin: np.ndarray,

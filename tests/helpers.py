@@ -25,6 +25,14 @@ def load_golden(name):
     meta = json.loads(str(z["meta"]))
     calls = []
     for i in range(len(meta["calls"])):
+        if meta.get("lite"):
+            # long-utterance goldens: beams only (int16 arrays), no feature / encoder tensors
+            calls.append(dict(
+                feats=None, enc=None, called=bool(z[f"c{i}_called"]), n_feat=int(z[f"c{i}_nfeat"]), n_enc=int(z[f"c{i}_nenc"]),
+                score=z[f"c{i}_score"], process_idx=int(z[f"c{i}_process_idx"]),
+                yseq=z[f"c{i}_yseq"].astype(int).tolist(), xpos=z[f"c{i}_xpos"].astype(int).tolist(),
+                results=json.loads(str(z[f"c{i}_results"]))))
+            continue
         j = json.loads(str(z[f"c{i}_json"]))
         calls.append(dict(
             feats=z[f"c{i}_feats"] if f"c{i}_feats" in z else None,

@@ -63,21 +63,24 @@ def _run_case(case, check_internals=True, dtype="float32"):
     for ci, ((s, e, fin), g) in enumerate(zip(meta["calls"], calls)):
         res = gpu(audio[s:e], is_final=fin, finalize_all=fin)
         plan = grp.last_plan(0)
-        assert bool(plan.called) == (g["feats"] is not None), f"call {ci}"
-        if g["feats"] is None:
+        lite = bool(meta.get("lite"))              # long-utterance goldens hold beams and shapes only
+        called = g["called"] if lite else g["feats"] is not None
+        assert bool(plan.called) == called, f"call {ci}"
+        if not called:
             assert res == []
             continue
-        assert plan.n_feat == g["feats"].shape[0], f"call {ci}"
-        n_enc = 0 if g["enc"] is None else g["enc"].shape[0]
+        assert plan.n_feat == (g["n_feat"] if lite else g["feats"].shape[0]), f"call {ci}"
+        n_enc = g["n_enc"] if lite else (0 if g["enc"] is None else g["enc"].shape[0])
         assert plan.n_enc_out == n_enc, f"call {ci}: enc frames {plan.n_enc_out} != {n_enc}"
-        if check_internals and n_enc:
+        if check_internals and n_enc and not lite:
             enc = grp.buffer("encbuf").view(-1, 256)[enc_seen: enc_seen + n_enc].cpu().numpy()
             np.testing.assert_allclose(enc, g["enc"], atol=1e-3, rtol=0, err_msg=f"call {ci} encoder output")
         enc_seen += n_enc
         ys, sc, xp, pidx = gpu.beam_state
         assert ys == g["yseq"], f"call {ci}: n-best token sequences differ"
         assert xp == g["xpos"], f"call {ci}: token timestamps differ"
-        np.testing.assert_allclose(sc, g["score"], atol=2e-3, rtol=0, err_msg=f"call {ci} scores")
+        # scores are sums of up to 600 fp32 increments of magnitude ~7: 2e-3 absolute up to ~130 tokens, relative beyond
+        np.testing.assert_allclose(sc, g["score"], atol=2e-3, rtol=2e-6, err_msg=f"call {ci} scores")
         assert pidx == g["process_idx"], f"call {ci}"
         assert [r[2] for r in res] == g["results"], f"call {ci}"
     return gpu

@@ -6,7 +6,9 @@ import pytest
 
 from helpers import GOLDEN_CASES, load_golden, model_dir
 
-FAST = [c for c in GOLDEN_CASES if c not in ("xl_b10_4s", "m_b5_8s")]
+# full-depth / long cases the generator already checked against the reference; replayed on the GPU only
+SLOW = ("xl_b10_4s", "m_b5_8s", "xl_b10_20s", "xl_d4_b10_60s")
+FAST = [c for c in GOLDEN_CASES if c not in SLOW]
 
 
 @pytest.mark.parametrize("case", FAST + ["xl_b10_4s"])
@@ -23,7 +25,11 @@ def test_oracle_replays_reference(case):
     for (s, e, fin), g in zip(meta["calls"], calls):
         o.search.last_enc_out = None
         res = o(audio[s:e], is_final=fin, finalize_all=fin)
-        if g["feats"] is not None:
+        if meta.get("lite"):                       # long-utterance goldens: shapes and beams only
+            assert (o.last_feats is not None) == g["called"]
+            if g["called"]:
+                assert o.last_feats.shape[0] == g["n_feat"]
+        elif g["feats"] is not None:
             f = o.last_feats.numpy()
             assert f.shape == g["feats"].shape
             assert np.abs(f - g["feats"]).max() <= 1e-4 * max(1.0, np.abs(g["feats"]).max())
@@ -36,13 +42,22 @@ def test_oracle_replays_reference(case):
         hyps = o.hyps or []
         assert [list(h.yseq) for h in hyps] == g["yseq"]
         assert [list(h.xpos) for h in hyps] == g["xpos"]
-        np.testing.assert_allclose([h.score for h in hyps], g["score"], atol=1e-3, rtol=0)
+        np.testing.assert_allclose([h.score for h in hyps], g["score"], atol=1e-3, rtol=1e-6)
         assert [list(r[2]) for r in res] == g["results"]
         assert o.search.process_idx == g["process_idx"]
     for a, b in zip(got_trace, trace):
         real = b["ctc"] > -1e9
         np.testing.assert_allclose(a["dec"].numpy(), b["dec"], atol=1e-3, rtol=0)
         np.testing.assert_allclose(a["ctc"].numpy()[real], b["ctc"][real], atol=1e-3, rtol=1e-5)
+
+
+def test_long_goldens_reach_the_step_cap():
+    """The 60 s goldens end at the reference's global step cap (beam_search.py:701,821: process_idx < 500, rewound to
+    499 at the end of every block), the regime every stream of the benchmark runs in."""
+    for case in ("m_d2_b5_60s", "xl_d4_b10_60s"):
+        meta, calls, _ = load_golden(case)
+        assert meta["final_process_idx"] == 499 and calls[-1]["process_idx"] == 499, case
+        assert len(calls[-1]["yseq"][0]) > 500, case
 
 
 def test_mel_filterbank_matches_torchaudio():
