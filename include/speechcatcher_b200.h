@@ -203,6 +203,16 @@ int sc_linear_f32(const float* x, const float* w, const float* bias, const float
  * (speechcatcher_b200/weights.py:split_f16); three UMMAs per K step into two TMEM accumulators (precision 2) */
 int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, const float* residual, float* y,
                  int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
+/* The engine's own form of that GEMM: the activation arrives as split fp16 planes written by its producer
+ * (x_planes_f16: hi plane [x_rows][k], lo plane x_plane_elems further, x_rows = row capacity >= m) and is staged by
+ * TMA like the weights; the result is written as fp32 rows (y, may be NULL) and / or as split planes for the next
+ * Linear (y_planes_f16, may be NULL). */
+int sc_linear_x3_planes(const void* x_planes_f16, int64_t x_plane_elems, int32_t x_rows, const void* w_planes_f16,
+                        const float* bias, const float* residual, float* y, void* y_planes_f16, int64_t y_plane_elems,
+                        int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
+/* LayerNorm eps=1e-12 whose result is written as split fp16 planes (hi [rows][d], lo y_plane_elems further) */
+int sc_layernorm_split(const float* x, const float* w, const float* b, void* y_planes_f16, int64_t y_plane_elems,
+                       int32_t rows, int32_t d, void* stream);
 /* same contract on the tcgen05 tensor-core path: bf16 operands, fp32 accumulate */
 int sc_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, const float* residual,
                    float* y_f32, void* y_bf16, int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);

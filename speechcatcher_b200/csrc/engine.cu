@@ -33,8 +33,6 @@ int launch_gemm_bf16_ln(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W,
                         int K, int relu, const int* n_rows_dev, const float* ln_w, const float* ln_b,
                         __nv_bfloat16* ln_out, cudaStream_t st);
 
-int launch_gemm_x3(const GemmArgs& g, const void* W2, cudaStream_t st);
-
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Caps {
@@ -262,13 +260,35 @@ struct Lin {
 static Lin with_ln(Lin l, const float* w, const float* b, __nv_bfloat16* out) { l.ln_w = w; l.ln_b = b; l.ln_out = out; return l; }
 
 // fp32-result GEMM: CUDA-core kernel (precision 0) or the split-fp16 tensor-core kernel (precision 2)
-static int gemm_fp32(Engine& e, const GemmArgs& g, cudaStream_t st) {
+static int gemm_fp32(Engine& e, const GemmArgs& g, cudaStream_t st, const X3Extra& x = X3Extra()) {
   if (e.cfg.precision == 2) {
     auto it = e.x3map.find(g.W);
     if (it == e.x3map.end()) { set_last_error("precise tensor-core mode: no fp16 planes registered for a %dx%dx%d linear", g.M, g.N, g.K); return -1; }
-    return launch_gemm_x3(g, it->second, st);
+    return launch_gemm_x3(g, x, it->second, st);
   }
   return launch_gemm_f32(g, st);
+}
+
+// ---------------------------------------------------------------- precise tensor-core mode (precision 2)
+// Activations that feed a Linear are handed over as split fp16 planes (x3_split.cuh) written by their producer
+// (LayerNorm, attention, the FFN1 / conv2 epilogue); the fp32 scratch buffers of the fp32 mode are reused for the planes
+// (2 planes x 2 bytes = the 4 bytes per element they were carved with).  The residual stream, Q|K|V and the KV caches
+// stay fp32.
+struct Planes { void* base; size_t plane; int rows; };
+static inline SplitOut split_out(const Planes& p, int ld) { SplitOut so; so.base = (__half*)p.base; so.plane = p.plane; so.ld = ld; return so; }
+
+// C (fp32, += R) and / or C2 (planes) = act(A2 * W^T + bias)
+static int x3_linear(Engine& e, const Planes& a, int K, const float* W, const float* bias, const float* R, float* C, int ldc,
+                     const Planes* c2, int M, int N, int relu, const int* n_rows_dev, cudaStream_t st,
+                     const int64_t* c_row_off = nullptr) {
+  e.launches++;
+  GemmArgs g;
+  g.lda = K; g.W = W; g.bias = bias; g.R = R; g.ldr = ldc; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.relu = relu;
+  g.n_rows_dev = n_rows_dev; g.c_row_off = c_row_off;
+  X3Extra x;
+  x.A2 = a.base; x.a2_plane = a.plane; x.a2_rows = a.rows;
+  if (c2) { x.C2 = c2->base; x.c2_plane = c2->plane; x.ldc2 = N; }
+  return gemm_fp32(e, g, st, x);
 }
 
 static int linear(Engine& e, const Lin& l, cudaStream_t st) {
@@ -346,7 +366,29 @@ static int ffn_auto_splits(const Engine& e, int rows, int F) {
 }
 
 // ---------------------------------------------------------------- encoder layers over all blocks of the push
+static int run_encoder_layers_x3(Engine& e, int n_blk, cudaStream_t st) {
+  const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, rows = n_blk * kSlots, cap = e.cap.rows_max;
+  const Planes nrm{e.Nrm, (size_t)cap * D, cap}, att{e.Att, (size_t)cap * D, cap}, ff{e.FF, (size_t)cap * F, cap};
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const EncLayerW& w = e.enc[l];
+    PE(T_ENC_LN, launch_layernorm_split(e.X, D, w.ln1w, w.ln1b, nrm.base, nrm.plane, D, rows, D, nullptr, st));
+    if (e.prof_tag == T_ENC_QKV) e.prof_flops += 2.0 * n_blk * 41 * 3.0 * D * D;
+    PE(T_ENC_QKV, x3_linear(e, nrm, D, w.qkvw, w.qkvb, nullptr, e.QKV, 3 * D, nullptr, rows, 3 * D, 0, nullptr, st));
+    PE(T_ENC_ATTN, launch_enc_attention(e.QKV, nullptr, nullptr, e.d_blk, n_blk, c.enc_heads, D, st, split_out(att, D)));
+    PE(T_ENC_O, x3_linear(e, att, D, w.ow, w.ob, e.X, e.X, D, nullptr, rows, D, 0, nullptr, st));
+    PE(T_ENC_LN, launch_layernorm_split(e.X, D, w.ln2w, w.ln2b, nrm.base, nrm.plane, D, rows, D, nullptr, st));
+    // algorithmic FLOPs of the roofline: 41 useful rows per block; 42 are executed
+    if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * n_blk * 41 * (double)F * D;
+    PE(T_ENC_FFN1, x3_linear(e, nrm, D, w.f1w, w.f1b, nullptr, nullptr, F, &ff, rows, F, 1, nullptr, st));
+    PE(T_ENC_FFN2, x3_linear(e, ff, F, w.f2w, w.f2b, e.X, e.X, D, nullptr, rows, D, 0, nullptr, st));
+    PE(T_ENC_HANDOVER, launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, nullptr, nullptr, nullptr, st));
+    e.launches += 4;
+  }
+  return 0;
+}
+
 static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
+  if (e.cfg.precision == 2) return run_encoder_layers_x3(e, n_blk, st);
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, rows = n_blk * kSlots;
   const bool tc = c.precision == 1;
   const bool fl = tc && e.fuse_ln;
@@ -368,12 +410,13 @@ static int run_encoder_layers(Engine& e, int n_blk, cudaStream_t st) {
       if (fl) o = with_ln(o, w.ln2w, w.ln2b, e.Nrm16);
       PE(T_ENC_O, linear(e, o, st));
     }
-    if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
+    // algorithmic FLOPs of the roofline: 41 useful rows per block; 42 are executed
+    if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * n_blk * 41 * (double)F * D;
     if (tc && e.fused_ffn && !fl && !e.ln_prologue && rows >= e.fused_ffn_min_rows) {
       // LayerNorm -> one fused FFN kernel (hidden activation stays in TMEM / shared memory); timed under the FFN2 tag
       e.launches += 2;
       PE(T_ENC_LN, launch_layernorm_bf16(e.X, D, w.ln2w, w.ln2b, e.Nrm16, D, rows, D, nullptr, st));
-      if (e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * rows * (double)F * D;
+      if (e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * n_blk * 41 * (double)F * D;
       PE(T_ENC_FFN2, launch_ffn_fused_bf16(e.Nrm16, D, w.f1w16, w.f1b, w.f2w16, w.f2b, e.X, D, 1, rows, F,
                                            ffn_auto_splits(e, rows, F), nullptr, st));
     } else {
@@ -422,6 +465,35 @@ static int trace_step(Engine& e, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- one search iteration for all active streams
+static int decode_tail(Engine& e, cudaStream_t st);
+
+static int run_decode_step_x3(Engine& e, cudaStream_t st) {
+  const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, V = c.vocab, R = e.cap.R;
+  const SearchBuffers& sb = e.sb;
+  const int* nr = sb.n_rows;
+  const Planes dn{e.dn, (size_t)R * D, R}, da{e.dattn, (size_t)R * D, R}, df{e.dffn, (size_t)R * F, R};
+  PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, nullptr, nullptr, nullptr, st));
+  for (int l = 0; l < c.dec_layers; ++l) {
+    const DecLayerW& w = e.dec[l];
+    PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln1w, w.ln1b, dn.base, dn.plane, D, R, D, nr, st));
+    PD(T_DEC_QKV, x3_linear(e, dn, D, w.sqkvw, w.sqkvb, nullptr, e.dqkv, 3 * D, nullptr, R, 3 * D, 0, nr, st));
+    PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, nullptr, nullptr, st, split_out(da, D)));
+    PD(T_DEC_SO, x3_linear(e, da, D, w.sow, w.sob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
+    PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln2w, w.ln2b, dn.base, dn.plane, D, R, D, nr, st));
+    PD(T_DEC_CQ, x3_linear(e, dn, D, w.cqw, w.cqb, nullptr, e.dq, D, nullptr, R, D, 0, nr, st));
+    PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, nullptr, nullptr, st, split_out(da, D)));
+    PD(T_DEC_CO, x3_linear(e, da, D, w.cow, w.cob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
+    PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln3w, w.ln3b, dn.base, dn.plane, D, R, D, nr, st));
+    PD(T_DEC_FFN1, x3_linear(e, dn, D, w.f1w, w.f1b, nullptr, nullptr, F, &df, R, F, 1, nr, st));
+    PD(T_DEC_FFN2, x3_linear(e, df, F, w.f2w, w.f2b, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
+    e.launches += 5;
+  }
+  PD(T_DEC_LN, launch_layernorm_split(e.dx, D, e.daw, e.dab, dn.base, dn.plane, D, R, D, nr, st));
+  PD(T_DEC_OUT, x3_linear(e, dn, D, e.doutw, e.doutb, nullptr, e.dlogp, V, nullptr, R, V, 0, nr, st));
+  e.launches += 2;
+  return decode_tail(e, st);
+}
+
 static int run_decode_step(Engine& e, cudaStream_t st) {
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, V = c.vocab, R = e.cap.R;
   const SearchBuffers& sb = e.sb;
@@ -430,6 +502,11 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   e.prof_sample = (e.step_seq++ % e.prof_stride) == 0;
   const bool ptot = prof_on(e, T_DEC_STEP_TOTAL, true);
   if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, true);
+  if (c.precision == 2) {
+    TRY(run_decode_step_x3(e, st));
+    if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, false);
+    return 0;
+  }
   const bool fl = tc && e.fuse_ln_dec;
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, fl ? e.dec[0].ln1w : nullptr, fl ? e.dec[0].ln1b : nullptr, e.dn16, st));
   if (e.mma_attn) PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
@@ -468,6 +545,14 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
     e.launches += fl ? 2 : 5;
   }
   TRY(ln_linear(e, T_DEC_LN, T_DEC_OUT, true, e.dx, D, e.daw, e.dab, R, Lin{e.dn, D, e.dn16, e.doutw, e.doutw16, e.doutb, nullptr, 0, e.dlogp, V, nullptr, R, V, D, 0, nr}, st));
+  TRY(decode_tail(e, st));
+  if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, false);
+  return 0;
+}
+
+// log-softmax + pre-beam, CTC prefix scores, score combination, pruning, state update, commit (shared by all modes)
+static int decode_tail(Engine& e, cudaStream_t st) {
+  const SearchBuffers& sb = e.sb;
   PD(T_PREBEAM, launch_logsoftmax_prebeam(sb, e.dlogp, st));
   PD(T_CTC_PREFIX, launch_ctc_prefix(sb, st));
   PD(T_COMBINE, launch_combine_topk(sb, e.dlogp, st));
@@ -475,7 +560,6 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   PD(T_PRUNE, launch_beam_prune(sb, st));
   PD(T_CTC_UPDATE, launch_ctc_state_update(sb, st));
   PD(T_STEP_FINISH, launch_step_finish(sb, st));
-  if (ptot) prof_mark(e, T_DEC_STEP_TOTAL, st, false);
   e.launches += 9;
   return 0;
 }
@@ -983,9 +1067,17 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
       g.A = e.h1; g.a_row_off = e.d_c2_a; g.a_seg_off = e.d_c2_seg; g.seg_len = D; g.W = e.c2w; g.bias = e.c2b;
       g.C = e.h2; g.ldc = D; g.M = sub_rows * 19; g.N = D; g.K = 9 * D; g.relu = 1;
       if (e.prof_tag == T_CONV2) e.prof_flops += 2.0 * g.M * (double)g.N * g.K;
-      PE(T_CONV2, gemm_fp32(e, g, st));
+      X3Extra x;
+      if (c.precision == 2) {      // the conv2 output only feeds embed.out: written as split planes [sub_rows * 19][D]
+        g.C = nullptr; x.C2 = e.h2; x.c2_plane = (size_t)k.sub_rows_max * 19 * D; x.ldc2 = D;
+      }
+      PE(T_CONV2, gemm_fp32(e, g, st, x));
     }
-    {
+    if (c.precision == 2) {
+      const Planes h2p{e.h2, (size_t)k.sub_rows_max * 19 * D, k.sub_rows_max};      // the same planes viewed as [sub_rows][19 D]
+      PE(T_SUBOUT, x3_linear(e, h2p, 19 * D, e.eow, e.eob, nullptr, e.subbuf, 0, nullptr, sub_rows, D, 0, nullptr, st, e.d_c2_c));
+      e.launches--;
+    } else {
       Lin o{e.h2, 19 * D, e.h2_16, e.eow, e.eow16, e.eob, nullptr, 0, e.subbuf, 0, nullptr, sub_rows, D, 19 * D, 0, nullptr};
       o.c_row_off = e.d_c2_c;
       PE(T_SUBOUT, linear(e, o, st));
@@ -1299,7 +1391,21 @@ int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, co
                  int32_t n, int32_t k, int32_t relu, void* stream) {
   GemmArgs g;
   g.A = x; g.lda = k; g.bias = bias; g.R = residual; g.ldr = n; g.C = y; g.ldc = n; g.M = m; g.N = n; g.K = k; g.relu = relu;
-  return launch_gemm_x3(g, w_planes_f16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+  return launch_gemm_x3(g, X3Extra(), w_planes_f16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+int sc_linear_x3_planes(const void* x_planes_f16, int64_t x_plane_elems, int32_t x_rows, const void* w_planes_f16,
+                        const float* bias, const float* residual, float* y, void* y_planes_f16, int64_t y_plane_elems,
+                        int32_t m, int32_t n, int32_t k, int32_t relu, void* stream) {
+  GemmArgs g;
+  g.lda = k; g.bias = bias; g.R = residual; g.ldr = n; g.C = y; g.ldc = n; g.M = m; g.N = n; g.K = k; g.relu = relu;
+  X3Extra x;
+  x.A2 = x_planes_f16; x.a2_plane = (size_t)x_plane_elems; x.a2_rows = x_rows;
+  x.C2 = y_planes_f16; x.c2_plane = (size_t)y_plane_elems; x.ldc2 = n;
+  return launch_gemm_x3(g, x, w_planes_f16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+int sc_layernorm_split(const float* x, const float* w, const float* b, void* y_planes_f16, int64_t y_plane_elems,
+                       int32_t rows, int32_t d, void* stream) {
+  return launch_layernorm_split(x, d, w, b, y_planes_f16, (size_t)y_plane_elems, d, rows, d, nullptr, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }
 int sc_linear_bf16(const void* x, const void* w, const float* bias, const float* residual, float* y, void* y16, int32_t m,
                    int32_t n, int32_t k, int32_t relu, void* stream) {

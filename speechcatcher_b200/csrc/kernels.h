@@ -2,6 +2,7 @@
 // All launchers return 0 on success, -1 on failure (message via scb::get_last_error()).
 #pragma once
 #include "common.cuh"
+#include "x3_split.cuh"
 
 namespace scb {
 
@@ -69,6 +70,21 @@ struct GemmArgs {
 };
 int launch_gemm_f32(const GemmArgs& g, cudaStream_t st);
 
+// ---------------------------------------------------------------- GEMM (fp32 results on the tensor cores, split fp16)
+// Extra operands of launch_gemm_x3 (kernels_gemm_x3.cu, x3_split.cuh): A and / or C as split fp16 planes.
+struct X3Extra {
+  const void* A2 = nullptr;   // A as planes: hi [a2_rows][K] (leading dimension GemmArgs::lda), lo at + a2_plane elements
+  size_t a2_plane = 0;
+  int a2_rows = 0;            // row capacity of the A buffer (>= M)
+  void* C2 = nullptr;         // output as planes, dense rows of leading dimension ldc2; lo plane at + c2_plane elements
+  size_t c2_plane = 0;
+  int ldc2 = 0;
+};
+int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);
+// LayerNorm (eps 1e-12, same arithmetic as launch_layernorm) whose result is written as split fp16 planes
+int launch_layernorm_split(const float* x, int ldx, const float* w, const float* b, void* y2, size_t plane, int ldy,
+                           int rows, int D, const int* n_rows_dev, cudaStream_t st);
+
 // ---------------------------------------------------------------- frontend
 int frontend_upload_tables(const float* window400, const float* mel_fb_257x80);
 int launch_frontend(const float* wave_in, int ld_wave, const float* wbuf, int ld_wbuf, const FrontendDesc* desc,
@@ -99,8 +115,9 @@ int launch_carry_rows(float* buf, int cap, int width, const int* stream, const i
                       int n_desc, cudaStream_t st);
 int launch_block_assemble(const float* subbuf, int sub_cap, const float* pe, const BlockDesc* blk, int n_blk,
                           float* addin, float* prev_addin, float* X, int D, cudaStream_t st);
+// out (fp32 rows) or, when so.base is set, split fp16 planes (precise tensor-core mode)
 int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
-                         int n_head, int d_model, cudaStream_t st);
+                         int n_head, int d_model, cudaStream_t st, SplitOut so = SplitOut());
 int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                              int n_head, int d_model, cudaStream_t st);
 int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const BlockDesc* blk, int n_blk,
@@ -182,13 +199,13 @@ int launch_search_begin(const SearchBuffers& sb, const int* q_stream, const int*
 int launch_dec_embed(const SearchBuffers& sb, const float* emb, const float* pe, float* x, const float* ln_w,
                      const float* ln_b, __nv_bfloat16* out16, cudaStream_t st);
 int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
-                              __nv_bfloat16* out16, cudaStream_t st);
+                              __nv_bfloat16* out16, cudaStream_t st, SplitOut so = SplitOut());
 // Key list of the self-attention KV tree, built once per search iteration and shared by all layers and heads:
 // key u < Lc = position u of the beam's common ancestor chain; later keys = (hypothesis, position) pairs of the
 // divergent tail.  Packed as position | slot << 16 | (owner + 1) << 24 (owner 0 = visible to every hypothesis).
 int launch_build_self_keys(const SearchBuffers& sb, cudaStream_t st);
 int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
-                               __nv_bfloat16* out16, cudaStream_t st);
+                               __nv_bfloat16* out16, cudaStream_t st, SplitOut so = SplitOut());
 int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st);
 int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st);
 int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st);

@@ -219,7 +219,7 @@ int launch_block_assemble(const float* subbuf, int sub_cap, const float* pe, con
 template <int DK>
 __global__ void __launch_bounds__(128) enc_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                             __nv_bfloat16* __restrict__ out16,
-                                                            const BlockDesc* __restrict__ blk, int D) {
+                                                            const BlockDesc* __restrict__ blk, int D, SplitOut so) {
   const BlockDesc b = blk[blockIdx.x];
   const int head = blockIdx.y;
   __shared__ float Q[kSlots][DK + 1], Kt[kSlots][DK + 1], Vv[kSlots][DK + 1];
@@ -263,18 +263,19 @@ __global__ void __launch_bounds__(128) enc_attention_kernel(const float* __restr
     float acc = 0.f;
     if (qi >= q_lo && qi < q_hi)
       for (int ki = k_lo; ki < k_hi; ++ki) acc = fmaf(P[qi][ki], Vv[ki][c], acc);
-    obase[(size_t)qi * D + c] = acc;     // rows outside [q_lo, q_hi) get 0 (fully masked rows)
+    if (so.base) so.put((size_t)blockIdx.x * kSlots + qi, head * DK + c, acc);
+    else obase[(size_t)qi * D + c] = acc;     // rows outside [q_lo, q_hi) get 0 (fully masked rows)
     if (out16) out16[((size_t)blockIdx.x * kSlots + qi) * D + head * DK + c] = __float2bfloat16(acc);
   }
 }
 
 int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
-                         int n_head, int d_model, cudaStream_t st) {
+                         int n_head, int d_model, cudaStream_t st, SplitOut so) {
   if (n_blk <= 0) return 0;
   dim3 grid(n_blk, n_head);
   int dk = d_model / n_head;
-  if (dk == 32) enc_attention_kernel<32><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model);
-  else if (dk == 64) enc_attention_kernel<64><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model);
+  if (dk == 32) enc_attention_kernel<32><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model, so);
+  else if (dk == 64) enc_attention_kernel<64><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model, so);
   else { set_last_error("enc_attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;

@@ -6,7 +6,9 @@
 // in kernels_gemm_tc.cu instead.
 #include <stdarg.h>
 #include <mutex>
+#include <type_traits>
 #include "kernels.h"
+#include "x3_split.cuh"
 
 namespace scb {
 
@@ -24,10 +26,12 @@ bool g_use_pdl = false;
 
 // ------------------------------------------------------------------ LayerNorm
 // One warp per row; the row stays in registers between the mean and variance passes.
+// OutT = float / __nv_bfloat16: plain rows.  OutT = __half: split fp16 planes (hi at y, lo at y + plane; x3_split.cuh),
+// the operand format of the precise tensor-core GEMM.
 template <typename OutT, int MAXV>
 __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                  const float* __restrict__ b, OutT* __restrict__ y, int ldy, int rows,
-                                 int D, const int* __restrict__ n_rows_dev) {
+                                 int D, const int* __restrict__ n_rows_dev, size_t plane) {
   pdl_sync();
   if (n_rows_dev) rows = min(rows, *n_rows_dev);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -53,17 +57,24 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
     if (i < nv) {
       int c = lane + 32 * i;
       float o = (v[i] - mean) * rstd * w[c] + b[c];
-      yr[c] = (OutT)o;
+      if constexpr (sizeof(OutT) == 2 && !std::is_same<OutT, __nv_bfloat16>::value) {
+        __half h, l;
+        x3_split(o, h, l);
+        yr[c] = h;
+        yr[plane + c] = l;
+      } else {
+        yr[c] = (OutT)o;
+      }
     }
 }
 
 template <typename OutT>
 static int ln_launch(const float* x, int ldx, const float* w, const float* b, OutT* y, int ldy, int rows,
-                     int D, const int* n_rows_dev, cudaStream_t st) {
+                     int D, const int* n_rows_dev, cudaStream_t st, size_t plane = 0) {
   if (rows <= 0) return 0;
   if (D % 32 != 0 || D > 512) { set_last_error("layernorm: unsupported D=%d", D); return -1; }
   const int warps = 8;
-  launch_k(layernorm_kernel<OutT, 16>, dim3(cdiv(rows, warps)), dim3(warps * 32), 0, st, x, ldx, w, b, y, ldy, rows, D, n_rows_dev);
+  launch_k(layernorm_kernel<OutT, 16>, dim3(cdiv(rows, warps)), dim3(warps * 32), 0, st, x, ldx, w, b, y, ldy, rows, D, n_rows_dev, plane);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -74,6 +85,11 @@ int launch_layernorm(const float* x, int ldx, const float* w, const float* b, fl
 int launch_layernorm_bf16(const float* x, int ldx, const float* w, const float* b, __nv_bfloat16* y,
                           int ldy, int rows, int D, const int* n_rows_dev, cudaStream_t st) {
   return ln_launch<__nv_bfloat16>(x, ldx, w, b, y, ldy, rows, D, n_rows_dev, st);
+}
+
+int launch_layernorm_split(const float* x, int ldx, const float* w, const float* b, void* y2, size_t plane, int ldy,
+                           int rows, int D, const int* n_rows_dev, cudaStream_t st) {
+  return ln_launch<__half>(x, ldx, w, b, (__half*)y2, ldy, rows, D, n_rows_dev, st, plane);
 }
 
 // ------------------------------------------------------------------ fp32 GEMM

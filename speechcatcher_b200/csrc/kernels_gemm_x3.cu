@@ -35,30 +35,19 @@
 #include <stdlib.h>
 #include "kernels.h"
 #include "tc_ptx.cuh"
+#include "x3_split.cuh"
 
 namespace scb {
 
 constexpr int X3_THREADS = 192;
 constexpr int X3_CONV_THREADS = 128;         // warps 2..5
-constexpr float X3_SCALE = 2048.0f;          // 2^11
-constexpr float X3_INV_SCALE = 1.0f / 2048.0f;
 
 struct X3Params {
   const float* A; int lda; const int64_t* a_row_off; const int* a_seg_off; int seg_len;
   const float* bias; const float* R; int ldr; float* C; int ldc; const int64_t* c_row_off;
   int M, N, K, relu; const int* n_rows_dev;
+  __half* C2; size_t c2_plane; int ldc2;      // optional split-plane output (hi plane, lo plane at + c2_plane elements)
 };
-
-// x -> (fp16 hi, fp16 lo * 2^11), saturating instead of producing inf (|x| > 65504 cannot occur for LayerNorm / ReLU /
-// attention outputs of this model; saturation keeps a stray value finite)
-__device__ __forceinline__ void x3_split(float x, __half& hi, __half& lo) {
-  unsigned short h;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
-  hi = __ushort_as_half(h);
-  const float r = (x - __half2float(hi)) * X3_SCALE;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(r));
-  lo = __ushort_as_half(h);
-}
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -71,9 +60,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 
 constexpr int x3_tmem_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
 
-template <int BN, int STAGES, int J>
+// A_TMA: the A operand already exists as split planes in global memory (written by the producing kernel) and is staged
+// by TMA like the weights; otherwise the converter warps build the planes from fp32 rows (gathered A: conv2).
+template <int BN, int STAGES, int J, bool A_TMA>
 __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_constant__ CUtensorMap map_wh,
                                                                 const __grid_constant__ CUtensorMap map_wl,
+                                                                const __grid_constant__ CUtensorMap map_ah,
+                                                                const __grid_constant__ CUtensorMap map_al,
                                                                 X3Params p) {
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -93,6 +86,10 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+    if (A_TMA) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
+    }
     for (int i = 0; i < STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&a_full[i], X3_CONV_THREADS); mbar_init(&empty_bar[i], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -121,8 +118,13 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
       const int s = kb % STAGES, ph = (kb / STAGES) & 1;
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (elect_one_sync()) {
-        unsigned char* sW = smem + s * STAGE_BYTES + 2 * A_BYTES;
-        mbar_expect_tx(&w_full[s], 2 * B_BYTES);
+        unsigned char* sA = smem + s * STAGE_BYTES;
+        unsigned char* sW = sA + 2 * A_BYTES;
+        mbar_expect_tx(&w_full[s], A_TMA ? 2 * A_BYTES + 2 * B_BYTES : 2 * B_BYTES);
+        if (A_TMA) {
+          tma_load_2d(&map_ah, &w_full[s], sA, kb * TC_BK, m0);
+          tma_load_2d(&map_al, &w_full[s], sA + A_BYTES, kb * TC_BK, m0);
+        }
         tma_load_2d(&map_wh, &w_full[s], sW, kb * TC_BK, n0);
         tma_load_2d(&map_wl, &w_full[s], sW + B_BYTES, kb * TC_BK, n0);
       }
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES, ph = (kb / STAGES) & 1;
       mbar_wait(&w_full[s], ph);
-      mbar_wait(&a_full[s], ph);
+      if (!A_TMA) mbar_wait(&a_full[s], ph);
       tc_fence_after();
       if (elect_one_sync()) {
         unsigned char* st = smem + s * STAGE_BYTES;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
     }
   } else {
     // ===================== A converters (warps 2..5), then the epilogue =====================
+    if (!A_TMA) {
     const int ct = threadIdx.x - 64;          // 0..127
     const int ch = ct & 7;                    // 16-byte chunk of the fp16 row = 8 consecutive k
     const int rg = ct >> 3;                   // rows rg + 16 i
@@ -195,18 +198,8 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
       for (int i = 0; i < 8; ++i) {
         const int Rr = rg + 16 * i;
         const float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
-        __half hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x3_split(x[j], hi[j], lo[j]);
         uint4 uh, ul;
-        uh.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
-        uh.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
-        uh.z = (uint32_t)__half_as_ushort(hi[4]) | ((uint32_t)__half_as_ushort(hi[5]) << 16);
-        uh.w = (uint32_t)__half_as_ushort(hi[6]) | ((uint32_t)__half_as_ushort(hi[7]) << 16);
-        ul.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
-        ul.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
-        ul.z = (uint32_t)__half_as_ushort(lo[4]) | ((uint32_t)__half_as_ushort(lo[5]) << 16);
-        ul.w = (uint32_t)__half_as_ushort(lo[6]) | ((uint32_t)__half_as_ushort(lo[7]) << 16);
+        x3_split8(x, uh, ul);
         const int off = Rr * 128 + ((ch ^ (Rr & 7)) << 4);
         *reinterpret_cast<uint4*>(sAh + off) = uh;
         *reinterpret_cast<uint4*>(sAl + off) = ul;
@@ -215,6 +208,7 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
       fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core (async proxy)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_full[s])) : "memory");
     }
+    }
 
     // ---- epilogue: thread <-> accumulator row (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
@@ -222,9 +216,11 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
     const bool row_ok = m < M;
     float* crow = nullptr;
     const float* rrow = nullptr;
+    __half* c2row = nullptr;
     if (row_ok) {
-      crow = p.c_row_off ? p.C + p.c_row_off[m] : p.C + (size_t)m * p.ldc;
+      if (p.C) crow = p.c_row_off ? p.C + p.c_row_off[m] : p.C + (size_t)m * p.ldc;
       if (p.R) rrow = p.R + (size_t)m * p.ldr;
+      if (p.C2) c2row = p.C2 + (size_t)m * p.ldc2;
     }
     float4 rn[4];
     if (rrow) {
@@ -262,6 +258,11 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
             a += __uint_as_float(v0[1][j]);
             a += __uint_as_float(v0[2][j]) + __uint_as_float(v0[3][j]);
           }
+          if (J == 7) {
+            a += __uint_as_float(v0[1][j]);
+            a += __uint_as_float(v0[2][j]) + __uint_as_float(v0[3][j]);
+            a += (__uint_as_float(v0[4][j]) + __uint_as_float(v0[5][j])) + __uint_as_float(v0[6][j]);
+          }
           o[j] = fmaf(__uint_as_float(v1[j]), X3_INV_SCALE, a);
         }
 #pragma unroll
@@ -274,9 +275,20 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 4; ++i) { o[4 * i] += rr[i].x; o[4 * i + 1] += rr[i].y; o[4 * i + 2] += rr[i].z; o[4 * i + 3] += rr[i].w; }
         }
+        if (crow) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(crow + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(crow + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+        if (c2row) {                         // the consumer is another Linear: hand the result over as split planes
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            uint4 uh, ul;
+            x3_split8(o + j, uh, ul);
+            *reinterpret_cast<uint4*>(c2row + n + j) = uh;
+            *reinterpret_cast<uint4*>(c2row + p.c2_plane + n + j) = ul;
+          }
+        }
       }
     }
     tc_fence_before();
@@ -288,42 +300,61 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
   }
 }
 
-template <int BN, int STAGES, int J>
-static int x3_launch(const CUtensorMap& mh, const CUtensorMap& ml, const X3Params& p, cudaStream_t st) {
+template <int BN, int STAGES, int J, bool A_TMA>
+static int x3_launch(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mah, const CUtensorMap& mal,
+                     const X3Params& p, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (2 * TC_BM * TC_BK * 2 + 2 * BN * TC_BK * 2) + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_x3_kernel<BN, STAGES, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_x3_kernel<BN, STAGES, J, A_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(gemm_x3, smem=%zu) failed", smem);
       return -1;
     }
     attr_set = true;
   }
   dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
-  launch_k(gemm_x3_kernel<BN, STAGES, J>, grid, dim3(X3_THREADS), smem, st, mh, ml, p);
+  launch_k(gemm_x3_kernel<BN, STAGES, J, A_TMA>, grid, dim3(X3_THREADS), smem, st, mh, ml, mah, mal, p);
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
 // W2: the two fp16 planes [2][N][K] produced by weights.split_f16 (hi plane, then lo plane scaled by 2^11).
-int launch_gemm_x3(const GemmArgs& g, const void* W2, cudaStream_t st) {
+// A: fp32 rows (g.A, optionally gathered) or split planes (x.A2: hi plane [a2_rows][K] with leading dimension g.lda,
+// lo plane a2_plane elements further; a2_rows = row capacity of the buffer, so that one tensor map serves every M).
+// Output: fp32 rows (g.C, optional when x.C2 is given) and / or split planes (x.C2).
+int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
-  if (g.K % TC_BK != 0 || g.N % 64 != 0 || (g.a_seg_off && g.seg_len % TC_BK != 0) || (!g.a_row_off && g.lda % 4 != 0) || !W2 || !g.C) {
+  const bool a_tma = x.A2 != nullptr;
+  if (g.K % TC_BK != 0 || g.N % 64 != 0 || (g.a_seg_off && g.seg_len % TC_BK != 0) || (!g.a_row_off && g.lda % 8 != 0) || !W2 ||
+      (!g.C && !x.C2) || (a_tma && (g.a_row_off || x.a2_rows < g.M)) || (x.C2 && x.ldc2 % 8 != 0)) {
     set_last_error("gemm_x3: unsupported shape M=%d N=%d K=%d lda=%d seg=%d", g.M, g.N, g.K, g.lda, g.seg_len);
     return -1;
   }
-  const bool small = (g.N % 128 != 0) || ((long)cdiv(g.M, TC_BM) * (g.N / 128) < kNumSMs);
+  // tile shapes: 128-wide N tiles with 2 main accumulators when that still fills the GPU, else 64-wide with 4; long-K
+  // products (FFN2, conv2, embed.out: 128+ tensor-core instructions per output) take 7 main accumulators so that
+  // the truncating accumulation stays at the error level of a K = 256 product
+  const bool long_k = g.K >= 1024;
+  const bool small = long_k || (g.N % 128 != 0) || ((long)cdiv(g.M, TC_BM) * (g.N / 128) < kNumSMs);
   const int BN = small ? 64 : 128;
   const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(W2);        // 16-bit elements: the map only moves bytes
   const __nv_bfloat16* wl = wh + (size_t)g.N * g.K;
-  CUtensorMap mh, ml;
+  CUtensorMap mh, ml, mah, mal;
   if (tc_get_map(wh, g.N, g.K, g.K, BN, &mh)) return -1;
   if (tc_get_map(wl, g.N, g.K, g.K, BN, &ml)) return -1;
+  if (a_tma) {
+    const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(x.A2);
+    if (tc_get_map(ah, x.a2_rows, g.K, g.lda, TC_BM, &mah)) return -1;
+    if (tc_get_map(ah + x.a2_plane, x.a2_rows, g.K, g.lda, TC_BM, &mal)) return -1;
+  } else { mah = mh; mal = ml; }
   X3Params p{g.A, g.lda, g.a_row_off, g.a_seg_off, g.seg_len, g.bias, g.R, g.ldr, g.C, g.ldc, g.c_row_off,
-             g.M, g.N, g.K, g.relu, g.n_rows_dev};
+             g.M, g.N, g.K, g.relu, g.n_rows_dev, (__half*)x.C2, x.c2_plane, x.ldc2};
   // stage = 32 KB (A hi + lo) + 2 * BN * 128 B (W hi + lo): BN 128 -> 64 KB (3 stages), BN 64 -> 48 KB (4 stages)
-  // main-term accumulators: 4 x 64 or 2 x 128 columns (+ the correction accumulator) of the 512 TMEM columns
-  return small ? x3_launch<64, 4, 4>(mh, ml, p, st) : x3_launch<128, 3, 2>(mh, ml, p, st);
+  if (a_tma) {
+    if (long_k) return x3_launch<64, 4, 7, true>(mh, ml, mah, mal, p, st);
+    return small ? x3_launch<64, 4, 4, true>(mh, ml, mah, mal, p, st) : x3_launch<128, 3, 2, true>(mh, ml, mah, mal, p, st);
+  }
+  if (long_k) return x3_launch<64, 4, 7, false>(mh, ml, mah, mal, p, st);
+  return small ? x3_launch<64, 4, 4, false>(mh, ml, mah, mal, p, st) : x3_launch<128, 3, 2, false>(mh, ml, mah, mal, p, st);
 }
 
 }  // namespace scb

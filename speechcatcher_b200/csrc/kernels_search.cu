@@ -244,7 +244,8 @@ constexpr int AMAXB = 20;     // beam capacity of the attention and pruning kern
 template <int DK, typename KVT>
 __global__ void __launch_bounds__(128) dec_cross_attn_kernel(SearchBuffers sb, const KVT* __restrict__ xkv_layer,
                                                              const float* __restrict__ q, int ldq,
-                                                             float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+                                                             float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
+                                                             SplitOut so) {
   pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
@@ -380,7 +381,8 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(SearchBuffers sb, c
     const int b = g + i * G;
     if (b < nb) {
       const float o = acc[i] / sm_l[b];
-      out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
+      if (so.base) so.put((size_t)(row0 + b), head * DK + cdim, o);
+      else out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
       if (out16) out16[(size_t)(row0 + b) * D + head * DK + cdim] = __float2bfloat16(o);
     }
   }
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(SearchBuffers sb, c
 
 template <typename KVT>
 static int launch_cross_t(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
-                          __nv_bfloat16* out16, cudaStream_t st) {
+                          __nv_bfloat16* out16, cudaStream_t st, SplitOut so) {
   const int dk = sb.D / sb.H;
   const KVT* base = reinterpret_cast<const KVT*>(sb.xkv) + (size_t)layer * sb.S * sb.Tcap * 2 * sb.D;
   dim3 grid(sb.S, sb.H);
@@ -397,21 +399,21 @@ static int launch_cross_t(const SearchBuffers& sb, int layer, const float* q, in
   if (dk == 32) {
     static bool a = false;
     if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
-    launch_k(dec_cross_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16);
+    launch_k(dec_cross_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16, so);
   } else if (dk == 64) {
     static bool a = false;
     if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
-    launch_k(dec_cross_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16);
+    launch_k(dec_cross_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16, so);
   } else { set_last_error("cross attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
-                               __nv_bfloat16* out16, cudaStream_t st) {
+                               __nv_bfloat16* out16, cudaStream_t st, SplitOut so) {
   if (sb.B > AMAXB) { set_last_error("cross attention: beam %d > %d", sb.B, AMAXB); return -1; }
-  return sb.kv_bf16 ? launch_cross_t<__nv_bfloat16>(sb, layer, q, ldq, out, out16, st)
-                    : launch_cross_t<float>(sb, layer, q, ldq, out, out16, st);
+  return sb.kv_bf16 ? launch_cross_t<__nv_bfloat16>(sb, layer, q, ldq, out, out16, st, so)
+                    : launch_cross_t<float>(sb, layer, q, ldq, out, out16, st, so);
 }
 
 // ---------------------------------------------------------------- self attention over the KV tree, shared-memory staged
@@ -423,7 +425,8 @@ int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* 
 template <int DK, typename KVT>
 __global__ void __launch_bounds__(128) dec_self_attn_kernel(SearchBuffers sb, KVT* skv_layer,
                                                             const float* __restrict__ qkv, int ldq,
-                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out16) {
+                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
+                                                            SplitOut so) {
   pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
   const int s = sb.act_streams[blockIdx.x];
@@ -637,7 +640,8 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(SearchBuffers sb, KV
     const int b = g + i * G;
     if (b < nb) {
       const float o = acc[i] / sm_l[b];
-      out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
+      if (so.base) so.put((size_t)(row0 + b), head * DK + cdim, o);
+      else out[(size_t)(row0 + b) * D + head * DK + cdim] = o;
       if (out16) out16[(size_t)(row0 + b) * D + head * DK + cdim] = __float2bfloat16(o);
     }
   }
@@ -645,7 +649,7 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(SearchBuffers sb, KV
 
 template <typename KVT>
 static int launch_self_t(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
-                         __nv_bfloat16* out16, cudaStream_t st) {
+                         __nv_bfloat16* out16, cudaStream_t st, SplitOut so) {
   const int dk = sb.D / sb.H;
   KVT* base = reinterpret_cast<KVT*>(sb.skv) + (size_t)layer * sb.S * sb.Lcap * sb.B * 2 * sb.D;
   dim3 grid(sb.S, sb.H);
@@ -655,21 +659,21 @@ static int launch_self_t(const SearchBuffers& sb, int layer, const float* qkv, i
   if (dk == 32) {
     static size_t a = 0;
     if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
-    launch_k(dec_self_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16);
+    launch_k(dec_self_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16, so);
   } else if (dk == 64) {
     static size_t a = 0;
     if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
-    launch_k(dec_self_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16);
+    launch_k(dec_self_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16, so);
   } else { set_last_error("self attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* qkv, int ldq, float* out,
-                              __nv_bfloat16* out16, cudaStream_t st) {
+                              __nv_bfloat16* out16, cudaStream_t st, SplitOut so) {
   if (sb.B > AMAXB) { set_last_error("self attention: beam %d > %d", sb.B, AMAXB); return -1; }
-  return sb.kv_bf16 ? launch_self_t<__nv_bfloat16>(sb, layer, qkv, ldq, out, out16, st)
-                    : launch_self_t<float>(sb, layer, qkv, ldq, out, out16, st);
+  return sb.kv_bf16 ? launch_self_t<__nv_bfloat16>(sb, layer, qkv, ldq, out, out16, st, so)
+                    : launch_self_t<float>(sb, layer, qkv, ldq, out, out16, st, so);
 }
 
 // ---------------------------------------------------------------- log-softmax + pre-beam top-40

@@ -86,3 +86,62 @@ def test_linear_x3_small_and_large_magnitudes():
         # lo = (x - hi) * 2^11 sits at the bottom of the normal range) instead of a relative one
         floor = 4.0 * K * 2.0 ** -36 * (a.abs().max().item() + w.abs().max().item())
         assert (y.double() - want).abs().max().item() <= 3e-6 * scale + floor, (a_scale, w_scale)
+
+
+def _act_planes(x):
+    """Split fp16 planes of an activation matrix, with the device's arithmetic (x3_split.cuh)."""
+    hi = x.to(torch.float16)
+    lo = ((x - hi.float()) * 2048.0).to(torch.float16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,relu,res", [(333, 768, 256, 0, False), (2560, 256, 2048, 0, True), (10752, 2048, 256, 1, False),
+                                            (77, 1024, 256, 0, False), (3000, 256, 4864, 0, False)])
+def test_linear_x3_planes_in_equals_converter_path(M, N, K, relu, res):
+    """The TMA-fed form (activation already stored as split planes by its producer) computes exactly what the converter
+    form computes from the fp32 rows: same split, same tensor-core instruction sequence."""
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    cap = M + 200                                             # row capacity of the plane buffer > M (stale rows behind)
+    a = torch.randn(cap, K, generator=g, device="cuda") * 1.3
+    w = torch.randn(N, K, generator=g, device="cuda") / K ** 0.5
+    bias = torch.randn(N, generator=g, device="cuda")
+    r = torch.randn(M, N, generator=g, device="cuda")
+    w2, a2 = _planes(w), _act_planes(a)
+    y0 = r.clone() if res else torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.sc_linear_x3(a.data_ptr(), w2.data_ptr(), bias.data_ptr(), y0.data_ptr() if res else None, y0.data_ptr(),
+                                M, N, K, relu, None), "x3")
+    y1 = r.clone() if res else torch.full((M, N), float("nan"), device="cuda")
+    yp = torch.zeros(2, M, N, dtype=torch.float16, device="cuda")
+    _lib.check(lib.sc_linear_x3_planes(a2.data_ptr(), cap * K, cap, w2.data_ptr(), bias.data_ptr(),
+                                       y1.data_ptr() if res else None, y1.data_ptr(), yp.data_ptr(), M * N,
+                                       M, N, K, relu, None), "x3_planes")
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+    # the plane output represents the fp32 result to 2^-22 relative (2^-36 absolute for tiny values)
+    rec = yp[0].double() + yp[1].double() / 2048.0
+    assert ((rec - y1.double()).abs() <= 2.0 ** -21 * y1.double().abs() + 2.0 ** -34).all()
+    # planes only (no fp32 output), as FFN1 hands its result to FFN2
+    if not res:
+        yp2 = torch.zeros_like(yp)
+        _lib.check(lib.sc_linear_x3_planes(a2.data_ptr(), cap * K, cap, w2.data_ptr(), bias.data_ptr(), None, None,
+                                           yp2.data_ptr(), M * N, M, N, K, relu, None), "x3_planes_only")
+        torch.cuda.synchronize()
+        assert torch.equal(yp, yp2)
+
+
+def test_layernorm_split_planes():
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rows = 1234
+    x = torch.randn(rows, 256, generator=g, device="cuda") * 3 + 0.5
+    w = 1.0 + 0.1 * torch.randn(256, generator=g, device="cuda")
+    b = 0.1 * torch.randn(256, generator=g, device="cuda")
+    y = torch.empty_like(x)
+    _lib.check(lib.sc_layernorm_f32(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, 256, None), "ln")
+    yp = torch.zeros(2, rows, 256, dtype=torch.float16, device="cuda")
+    _lib.check(lib.sc_layernorm_split(x.data_ptr(), w.data_ptr(), b.data_ptr(), yp.data_ptr(), rows * 256, rows, 256, None), "ln_split")
+    torch.cuda.synchronize()
+    assert torch.equal(yp, _act_planes(y))          # the fp32 LayerNorm's result, split
