@@ -102,6 +102,8 @@ struct Engine {
   std::unordered_map<std::string, std::pair<void*, size_t>> named;
   std::vector<ScStreamPlan> last_plan;
   int launches = 0;
+  bool attn_f32_rows = true;        // fp32 modes: warp-per-head decoder attention (kernels_attn_f32.cu) instead of the
+                                    // first CTA-per-(stream, head) kernels (SCB_ATTN=cta / option "attn_f32_rows")
   bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
   bool mma_enc = false;             // bf16 mode: tensor-core encoder block attention
   // bf16 mode, experimental: fuse every LayerNorm into the epilogue of the GEMM producing its input (BN = 256 tiles).
@@ -473,15 +475,18 @@ static int run_decode_step_x3(Engine& e, cudaStream_t st) {
   const int* nr = sb.n_rows;
   const Planes dn{e.dn, (size_t)R * D, R}, da{e.dattn, (size_t)R * D, R}, df{e.dffn, (size_t)R * F, R};
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, nullptr, nullptr, nullptr, st));
+  if (e.attn_f32_rows) { PD(T_DEC_EMBED, launch_build_self_keys(sb, st)); e.launches++; }
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
     PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln1w, w.ln1b, dn.base, dn.plane, D, R, D, nr, st));
     PD(T_DEC_QKV, x3_linear(e, dn, D, w.sqkvw, w.sqkvb, nullptr, e.dqkv, 3 * D, nullptr, R, 3 * D, 0, nr, st));
-    PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, nullptr, nullptr, st, split_out(da, D)));
+    if (e.attn_f32_rows) PD(T_DEC_SELF_ATTN, launch_dec_attention_f32(sb, 0, l, e.dqkv, 3 * D, nullptr, split_out(da, D), st));
+    else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, nullptr, nullptr, st, split_out(da, D)));
     PD(T_DEC_SO, x3_linear(e, da, D, w.sow, w.sob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
     PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln2w, w.ln2b, dn.base, dn.plane, D, R, D, nr, st));
     PD(T_DEC_CQ, x3_linear(e, dn, D, w.cqw, w.cqb, nullptr, e.dq, D, nullptr, R, D, 0, nr, st));
-    PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, nullptr, nullptr, st, split_out(da, D)));
+    if (e.attn_f32_rows) PD(T_DEC_CROSS_ATTN, launch_dec_attention_f32(sb, 1, l, e.dq, D, nullptr, split_out(da, D), st));
+    else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, nullptr, nullptr, st, split_out(da, D)));
     PD(T_DEC_CO, x3_linear(e, da, D, w.cow, w.cob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
     PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln3w, w.ln3b, dn.base, dn.plane, D, R, D, nr, st));
     PD(T_DEC_FFN1, x3_linear(e, dn, D, w.f1w, w.f1b, nullptr, nullptr, F, &df, R, F, 1, nr, st));
@@ -509,12 +514,14 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
   }
   const bool fl = tc && e.fuse_ln_dec;
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, fl ? e.dec[0].ln1w : nullptr, fl ? e.dec[0].ln1b : nullptr, e.dn16, st));
-  if (e.mma_attn) PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
+  const bool rows32 = !tc && e.attn_f32_rows;      // fp32 mode: warp-per-head attention over the per-step key list
+  if (e.mma_attn || rows32) PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
     // bf16 mode: norm1 comes fused from dec_embed / the previous layer's FFN2, norm2 from self-O, norm3 from cross-O
     TRY(ln_linear(e, T_DEC_LN, T_DEC_QKV, true, e.dx, D, w.ln1w, w.ln1b, R, Lin{e.dn, D, e.dn16, w.sqkvw, w.sqkvw16, w.sqkvb, nullptr, 0, e.dqkv, 3 * D, nullptr, R, 3 * D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_SELF_ATTN, launch_dec_attention_mma(sb, 0, l, e.dqkv, 3 * D, e.dattn, e.dattn16, st));
+    else if (rows32) PD(T_DEC_SELF_ATTN, launch_dec_attention_f32(sb, 0, l, e.dqkv, 3 * D, e.dattn, SplitOut(), st));
     else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, e.dattn, tc ? e.dattn16 : nullptr, st));
     {
       Lin o{e.dattn, D, e.dattn16, w.sow, w.sow16, w.sob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr};
@@ -523,6 +530,7 @@ static int run_decode_step(Engine& e, cudaStream_t st) {
     }
     TRY(ln_linear(e, T_DEC_LN, T_DEC_CQ, true, e.dx, D, w.ln2w, w.ln2b, R, Lin{e.dn, D, e.dn16, w.cqw, w.cqw16, w.cqb, nullptr, 0, e.dq, D, nullptr, R, D, D, 0, nr}, st));
     if (e.mma_attn) PD(T_DEC_CROSS_ATTN, launch_dec_attention_mma(sb, 1, l, e.dq, D, e.dattn, e.dattn16, st));
+    else if (rows32) PD(T_DEC_CROSS_ATTN, launch_dec_attention_f32(sb, 1, l, e.dq, D, e.dattn, SplitOut(), st));
     else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, e.dattn, tc ? e.dattn16 : nullptr, st));
     {
       Lin o{e.dattn, D, e.dattn16, w.cow, w.cow16, w.cob, e.dx, D, e.dx, D, nullptr, R, D, D, 0, nr};
@@ -710,6 +718,7 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     const int mma_beam = (a && strcmp(a, "mma_wide") == 0) ? 32 : 16;
     e->mma_attn = cfg->precision == 1 && cfg->beam <= mma_beam && !(a && strcmp(a, "simt") == 0);
     e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
+    e->attn_f32_rows = !(a && strcmp(a, "cta") == 0);
     const char* lp = getenv("SCB_LN_PROLOGUE");
     // measured slower than a separate LayerNorm kernel (every N-tile CTA re-normalises its 128 rows): opt-in only
     e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && lp && strcmp(lp, "1") == 0;
@@ -1304,6 +1313,7 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (strcmp(name, "ffn_splits") == 0) { e->ffn_splits = value < 0 ? 0 : value; return SC_OK; }
   if (strcmp(name, "fuse_layernorm") == 0) { e->fuse_ln = e->fuse_ln_dec = value != 0 && e->cfg.precision == 1; return SC_OK; }
   if (strcmp(name, "fuse_layernorm_decoder") == 0) { e->fuse_ln_dec = value != 0 && e->cfg.precision == 1; return SC_OK; }
+  if (strcmp(name, "attn_f32_rows") == 0) { e->attn_f32_rows = value != 0; return SC_OK; }
   if (strcmp(name, "mma_attention") == 0) {
     e->mma_attn = value != 0 && e->cfg.precision == 1 && e->cfg.beam <= (value >= 2 ? 32 : 16);   // 2: allow the tiled kernel
     e->mma_enc = value != 0 && e->cfg.precision == 1;

@@ -206,6 +206,10 @@ int launch_dec_self_attention(const SearchBuffers& sb, int layer, const float* q
 int launch_build_self_keys(const SearchBuffers& sb, cudaStream_t st);
 int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* q, int ldq, float* out,
                                __nv_bfloat16* out16, cudaStream_t st, SplitOut so = SplitOut());
+// fp32 K|V caches, warp-per-head pipelines (kernels_attn_f32.cu).  mode 0: self-attention over the per-step key list
+// (launch_build_self_keys must have run in this search iteration; also appends this step's K|V), 1: cross-attention.
+int launch_dec_attention_f32(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
+                             SplitOut so, cudaStream_t st);
 int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st);
 int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st);
 int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st);

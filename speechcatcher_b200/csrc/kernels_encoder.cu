@@ -7,6 +7,7 @@
 //           speechcatcher/model/encoder/contextual_block_transformer_encoder.py:278-419, 500-528
 //           speechcatcher/model/encoder/contextual_block_encoder_layer.py:178-271
 //           speechcatcher/model/attention/multi_head_attention.py:92-133 (masked vanilla attention)
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace scb {
@@ -269,11 +270,114 @@ __global__ void __launch_bounds__(128) enc_attention_kernel(const float* __restr
   }
 }
 
+
+// Register-tiled version (fp32 modes): one CTA per block, one thread per (head, query row) task.  K and V of all heads
+// are staged once in shared memory ([42][D] each); a task keeps its query row, its 42 scores and its output row in
+// registers, so the inner loops are FMAs fed by warp-broadcast LDS.128 of K / V rows (4 FMAs per shared-memory
+// instruction) and the softmax needs no cross-lane traffic.  Same arithmetic per element as enc_attention_kernel:
+// score = (FMA chain over c) / sqrt(dk), p = exp(s - max) / sum, out = FMA chain over keys.
+template <int DK>
+__global__ void __launch_bounds__(192) enc_attention_rows_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                                 const BlockDesc* __restrict__ blk, int D, int H, SplitOut so) {
+  const BlockDesc b = blk[blockIdx.x];
+  extern __shared__ __align__(16) float sm_kv[];          // K [42][D] then V [42][D]
+  float* Ks = sm_kv;
+  float* Vs = sm_kv + kSlots * D;
+  const float* base = qkv + (size_t)blockIdx.x * kSlots * 3 * D;
+  const int k_hi = b.short_path ? b.n_rows : kBlock + 1;                        // keys [0, k_hi)
+  const int q_lo = b.short_path ? 0 : 1, q_hi = b.short_path ? b.n_rows : kSlots;   // queries [q_lo, q_hi)
+  const int d4 = D / 4;
+  for (int i = threadIdx.x; i < k_hi * d4; i += blockDim.x) {
+    const int r = i / d4, c4 = i % d4;
+    const float4* row = reinterpret_cast<const float4*>(base + (size_t)r * 3 * D);
+    reinterpret_cast<float4*>(Ks)[r * d4 + c4] = row[d4 + c4];
+    reinterpret_cast<float4*>(Vs)[r * d4 + c4] = row[2 * d4 + c4];
+  }
+  __syncthreads();
+  const float sqrt_dk = sqrtf((float)DK);
+  for (int task = threadIdx.x; task < H * kSlots; task += blockDim.x) {
+    const int head = task / kSlots, qi = task % kSlots;
+    float o[DK];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) o[c] = 0.f;
+    if (qi >= q_lo && qi < q_hi) {
+      float q[DK];
+      const float4* qrow = reinterpret_cast<const float4*>(base + (size_t)qi * 3 * D + head * DK);
+#pragma unroll
+      for (int c = 0; c < DK / 4; ++c) { const float4 v = qrow[c]; q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w; }
+      float sc[kSlots];
+      float m = -INFINITY;
+#pragma unroll
+      for (int ki = 0; ki < kSlots; ++ki) {
+        sc[ki] = -INFINITY;
+        if (ki < k_hi) {
+          const float4* kr = reinterpret_cast<const float4*>(Ks + ki * D + head * DK);
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < DK / 4; ++c) {
+            const float4 kv = kr[c];
+            acc = fmaf(q[4 * c], kv.x, acc); acc = fmaf(q[4 * c + 1], kv.y, acc);
+            acc = fmaf(q[4 * c + 2], kv.z, acc); acc = fmaf(q[4 * c + 3], kv.w, acc);
+          }
+          sc[ki] = acc / sqrt_dk;
+          m = fmaxf(m, sc[ki]);
+        }
+      }
+      float ssum = 0.f;
+#pragma unroll
+      for (int ki = 0; ki < kSlots; ++ki) if (ki < k_hi) { sc[ki] = expf(sc[ki] - m); ssum += sc[ki]; }
+#pragma unroll
+      for (int ki = 0; ki < kSlots; ++ki) {
+        if (ki < k_hi) {
+          const float pk = sc[ki] / ssum;
+          const float4* vr = reinterpret_cast<const float4*>(Vs + ki * D + head * DK);
+#pragma unroll
+          for (int c = 0; c < DK / 4; ++c) {
+            const float4 vv = vr[c];
+            o[4 * c] = fmaf(pk, vv.x, o[4 * c]); o[4 * c + 1] = fmaf(pk, vv.y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(pk, vv.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pk, vv.w, o[4 * c + 3]);
+          }
+        }
+      }
+    }
+    // rows outside [q_lo, q_hi) get 0 (fully masked rows)
+    const size_t row = (size_t)blockIdx.x * kSlots + qi;
+    if (so.base) {
+#pragma unroll
+      for (int c = 0; c < DK; c += 8) {
+        uint4 uh, ul;
+        x3_split8(o + c, uh, ul);
+        *reinterpret_cast<uint4*>(so.base + row * so.ld + head * DK + c) = uh;
+        *reinterpret_cast<uint4*>(so.base + so.plane + row * so.ld + head * DK + c) = ul;
+      }
+    } else {
+      float4* orow = reinterpret_cast<float4*>(out + row * D + head * DK);
+#pragma unroll
+      for (int c = 0; c < DK / 4; ++c) orow[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    }
+  }
+}
+
 int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                          int n_head, int d_model, cudaStream_t st, SplitOut so) {
   if (n_blk <= 0) return 0;
   dim3 grid(n_blk, n_head);
   int dk = d_model / n_head;
+  static const bool rows_kernel = [] { const char* v = getenv("SCB_ENC_ATTN"); return !(v && v[0] == 'c'); }();   // "cta": old kernel
+  if (!out16 && rows_kernel && (dk == 32 || dk == 64) && d_model % 8 == 0) {
+    const size_t smem = sizeof(float) * 2 * kSlots * d_model;
+    if (dk == 32) {
+      static bool a = false;
+      if (!a) { cudaFuncSetAttribute(enc_attention_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+      enc_attention_rows_kernel<32><<<n_blk, 192, smem, st>>>(qkv, out, blk, d_model, n_head, so);
+    } else {
+      static bool a = false;
+      if (!a) { cudaFuncSetAttribute(enc_attention_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+      enc_attention_rows_kernel<64><<<n_blk, 192, smem, st>>>(qkv, out, blk, d_model, n_head, so);
+    }
+    SCB_LAUNCH_CHECK();
+    return 0;
+  }
   if (dk == 32) enc_attention_kernel<32><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model, so);
   else if (dk == 64) enc_attention_kernel<64><<<grid, 128, 0, st>>>(qkv, out, out16, blk, d_model, so);
   else { set_last_error("enc_attention: unsupported head dim %d", dk); return -1; }
