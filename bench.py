@@ -75,59 +75,99 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------- CPU baseline (oracle port)
+# --------------------------------------------------------------------------- CPU baseline (the reference on host cores)
+# oracle/_ref (scripts/make_oracle_ref.sh, git-ignored, travels with gpurun) is the UNMODIFIED reference package: when
+# it is present the CPU legs time the reference's own Speech2TextStreaming (kind "reference"), otherwise the oracle
+# port of the same path (kind "port").  Both legs of a run (`--impl reference` and `cpu_baseline`) use the same
+# sample length, a function of the number of passes only.
 _ORACLE_CACHE = {}
+REF_DIR = REPO / "oracle" / "_ref"
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_kind():
+    return "reference" if (REF_DIR / "speechcatcher" / "speech2text_streaming.py").exists() else "port"
 
 
 def _cpu_worker(args):
-    md, stream, n_samples, beam = args
+    md, stream, n_samples, beam, kind = args
+    import contextlib
+    import io
+    import logging
     import torch
     torch.set_num_threads(1)
-    from oracle.speech2text import OracleSpeech2Text
+    logging.disable(logging.CRITICAL)
     from speechcatcher_b200.synthetic import synth_audio
     audio = synth_audio(stream, n_samples)
-    key = (md, beam)
-    if key not in _ORACLE_CACHE:                      # one model load per worker process, reused across steps
-        _ORACLE_CACHE[key] = OracleSpeech2Text(md, beam_size=beam, ctc_weight=0.3)
-    o = _ORACLE_CACHE[key]
-    o.reset()
-    t0 = time.perf_counter()
-    lat = []
-    for i in range(0, n_samples, CHUNK):
-        fin = i + CHUNK >= n_samples
-        t1 = time.perf_counter()
-        o(audio[i:i + CHUNK], is_final=fin, finalize_all=fin)
-        lat.append(time.perf_counter() - t1)
-    return time.perf_counter() - t0, lat
+    key = (md, beam, kind)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):     # the reference prints debug lines
+        if key not in _ORACLE_CACHE:                  # one model load per worker process, reused across steps
+            if kind == "reference":
+                if str(REF_DIR) not in sys.path:
+                    sys.path.insert(0, str(REF_DIR))
+                from speechcatcher.speech2text_streaming import Speech2TextStreaming as RefS2T
+                _ORACLE_CACHE[key] = RefS2T(md, beam_size=beam, ctc_weight=0.3, device="cpu", dtype="float32", use_bbd=False)
+            else:
+                from oracle.speech2text import OracleSpeech2Text
+                _ORACLE_CACHE[key] = OracleSpeech2Text(md, beam_size=beam, ctc_weight=0.3)
+        o = _ORACLE_CACHE[key]
+        o.reset()
+        t0 = time.perf_counter()
+        lat = []
+        for i in range(0, n_samples, CHUNK):
+            fin = i + CHUNK >= n_samples
+            t1 = time.perf_counter()
+            o(audio[i:i + CHUNK], is_final=fin, finalize_all=fin)
+            lat.append(time.perf_counter() - t1)
+        dt = time.perf_counter() - t0
+    return dt, lat
 
 
 class CpuBaseline:
     """`procs` single-threaded worker processes, one stream each per pass (mirrors the reference CLI's process pool,
-    speechcatcher.py:481-497).  A pass returns (aggregate audio-s/s, p50 per-chunk latency in ms)."""
+    speechcatcher.py:481-497, 816-819).  A pass returns (aggregate audio-s/s, p50 per-chunk latency in ms)."""
 
     def __init__(self, md, beam, procs):
         from concurrent.futures import ProcessPoolExecutor
         import multiprocessing as mp
-        self.md, self.beam, self.procs = str(md), beam, procs
+        self.md, self.beam, self.procs, self.kind = str(md), beam, procs, cpu_kind()
         self.pool = ProcessPoolExecutor(max_workers=procs, mp_context=mp.get_context("spawn"))
 
     def run(self, sample_seconds, first_stream=0):
         n = int(sample_seconds * SR)
-        jobs = [(self.md, first_stream + i, n, self.beam) for i in range(self.procs)]
+        jobs = [(self.md, first_stream + i, n, self.beam, self.kind) for i in range(self.procs)]
         res = list(self.pool.map(_cpu_worker, jobs))
         lat = [x for _, l in res for x in l]
         compute = max(r[0] for r in res)          # excludes process start-up / model load
         return self.procs * sample_seconds / compute, 1000.0 * statistics.median(lat)
 
+    def describe(self, sample_seconds):
+        what = ("the reference's own Speech2TextStreaming (oracle/_ref, unmodified)" if self.kind == "reference"
+                else "oracle port of the reference path (oracle/_ref absent)")
+        return (f"{self.procs} streams x {sample_seconds:g} s (first seconds of the workload's streams), one single-threaded "
+                f"process per stream, {what}; the reference's per-step cost grows with utterance length, so a sample "
+                f"shorter than the workload's 60 s over-states its throughput")
+
     def close(self):
         self.pool.shutdown(wait=True)
 
 
-def auto_sample_seconds(n_passes, budget_s=150.0):
-    """Sample length per stream so that `n_passes` CPU passes take about `budget_s` seconds in total: one
-    single-threaded oracle process decodes roughly 0.5 audio-seconds per second on this workload's first seconds."""
+def cpu_sample_seconds(n_passes, budget_s=240.0):
+    """Audio seconds per stream of one CPU pass, the same in both CPU legs of a run: 20 s when the
+    passes fit the time budget, shorter otherwise (one single-threaded process decodes roughly 0.5 audio-seconds per
+    second on this workload, slower as the utterance grows)."""
     per_pass = budget_s / max(1, n_passes)
-    return float(min(8.0, max(3.0, 0.5 * (per_pass - 2.0))))
+    return float(min(20.0, max(4.0, 0.45 * (per_pass - 2.0))))
 
 
 # --------------------------------------------------------------------------- main
@@ -181,7 +221,7 @@ def main():
             return
         sys.path.insert(0, str(REPO))
         procs = cores
-        sample_s = args.cpu_sample_seconds or auto_sample_seconds(args.warmup + args.steps)
+        sample_s = args.cpu_sample_seconds or cpu_sample_seconds(args.warmup + args.steps)
         cpu = CpuBaseline(md, args.beam, procs)
         vals, p50s = [], []
         for i in range(args.warmup + args.steps):
@@ -190,16 +230,14 @@ def main():
                 vals.append(v); p50s.append(p50)
         cpu.close()
         v = float(np.mean(vals))
-        sample = (f"{procs} streams x {sample_s:g} s (first seconds of the workload's streams), one "
-                  f"single-threaded process per stream; per-step cost of the reference grows with utterance length, "
-                  f"so a short sample over-states its 60 s throughput")
+        sample = cpu.describe(sample_s)
         line = {"impl": "reference", "metric": "audio-sec/sec (RTFx)", "value": v, "unit": "audio-s/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * procs * sample_s / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "inputs": "host"},
-                "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": procs, "kind": "port", "sample": sample,
-                                 "p50_chunk_ms": float(np.mean(p50s))},
+                "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": procs, "kind": cpu.kind, "sample": sample,
+                                 "p50_chunk_ms": float(np.mean(p50s)), "cpu_model": cpu_model()},
                 "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -494,14 +532,13 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_s = args.cpu_sample_seconds or 6.0
+        sample_s = args.cpu_sample_seconds or cpu_sample_seconds(args.warmup + args.steps)   # = the reference arm's
         cpu = CpuBaseline(md, args.beam, cores)
+        cpu.run(min(sample_s, 2.0))                     # warm-up: model load, thread pools
         v, p50 = cpu.run(sample_s)
         cpu.close()
-        cpu_base = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                    "sample": f"{cores} streams x {sample_s:g} s of the same workload, one single-threaded "
-                              f"process per stream (oracle port of the reference path; short sample flatters the CPU)",
-                    "p50_chunk_ms": p50}
+        cpu_base = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": cpu.kind, "sample": cpu.describe(sample_s),
+                    "p50_chunk_ms": p50, "cpu_model": cpu_model()}
     if rank == 0:
         line = {"metric": "audio-sec/sec (RTFx)", "value": value, "unit": "audio-s/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

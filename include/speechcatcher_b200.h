@@ -237,7 +237,7 @@ int sc_ffn_bf16(const void* x_bf16, const void* w1_bf16, const float* b1, const 
                 float* y_f32, int32_t accumulate, int32_t m, int32_t f, int32_t splits, void* stream);
 
 /* Same kernel with a device-side timeline: `stamps` (device, >= 1024 int64) receives clock64() stamps of the first
- * CTA's MMA-issue warp and of one epilogue thread per hidden chunk (performance diagnosis, tests/ffn_timeline.py). */
+ * CTA's MMA-issue warp and of one epilogue thread per hidden chunk (performance diagnosis, scripts/ffn_timeline.py). */
 int sc_ffn_bf16_timeline(const void* x_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
                          float* y_f32, int32_t accumulate, int32_t m, int32_t f, int64_t* stamps, void* stream);
 

@@ -1,7 +1,7 @@
 """Measure how the bf16 tensor-core mode tracks the fp32 oracle (not a pytest file; prints a table)."""
 import sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 from helpers import GOLDEN_CASES, load_golden, model_dir

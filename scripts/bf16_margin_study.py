@@ -7,7 +7,7 @@ This script runs the CPU oracle twice per stream -- plain fp32, and with every L
 (fp32 accumulation: exactly what a tensor-core GEMM does; attention, LayerNorm, softmax, CTC recursion stay fp32) -- and
 reports how often the 1-best survives, per weight set.  The emulation has no kernels in it at all.
 
-    python tests/bf16_margin_study.py [--streams 16] [--seconds 8] [--arch m_d2] [--beam 10]
+    python scripts/bf16_margin_study.py [--streams 16] [--seconds 8] [--arch m_d2] [--beam 10]
 """
 import argparse
 import sys

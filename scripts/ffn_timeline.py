@@ -1,5 +1,5 @@
 """Device-side timeline of the fused FFN kernel (first CTA): where a hidden chunk's time goes.
-Run on a B200: python tests/ffn_timeline.py [M]"""
+Run on a B200: python scripts/ffn_timeline.py [M]"""
 import ctypes as C
 import sys
 from pathlib import Path

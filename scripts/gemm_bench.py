@@ -1,6 +1,6 @@
 """Micro-benchmark of the tcgen05 GEMM (sc_linear_bf16) on the encoder / decoder shapes of the XL model.
 
-Not a pytest module: run on a B200 as `python tests/gemm_bench.py`.  Each shape rotates over enough distinct
+Not a pytest module: run on a B200 as `python scripts/gemm_bench.py`.  Each shape rotates over enough distinct
 activation buffers to exceed L2 only when `--cold` is given; the default (warm) mirrors the engine, where the A
 operand has just been written by the preceding kernel.  Times are CUDA-event averages over `--iters` launches.
 """

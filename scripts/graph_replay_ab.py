@@ -1,7 +1,7 @@
 """Round-2 check for the opt-in CUDA-graph replay (engine options "graph_decode" / "graph_encoder"): NOT collected by
 pytest (the options were written without GPU time left in round 1 and have never run on a device).
 
-    python tests/graph_replay_ab.py            # on a B200 box
+    python scripts/graph_replay_ab.py            # on a B200 box
 
 1. parity: three ragged streams on an explicit (non-default) CUDA stream with graphs on must give exactly the beams of
    the same engine with graphs off (fp32 mode is bit-exact run to run) and of the CPU oracle;

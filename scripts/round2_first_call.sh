@@ -9,7 +9,7 @@ O=gpurun_out/r2_first
 timeout 150 python -m pytest tests -q -m gpu -x > $O/tests_gpu.txt 2>&1; echo "tests_rc=$?" > $O/rc.txt
 timeout 60 python -m pytest tests/test_gpu_zz_feats_input.py -q -m gpu -rxX > $O/feats_input_tests.txt 2>&1   # XPASS -> drop the xfail marker
 timeout 60 python -m pytest tests/test_gpu_zzz_graph_replay.py -q -m gpu -rxX > $O/graph_tests.txt 2>&1
-timeout 60 python tests/graph_replay_ab.py > $O/graph_ab.txt 2>&1; echo "graph_ab_rc=$?" >> $O/rc.txt
+timeout 60 python scripts/graph_replay_ab.py > $O/graph_ab.txt 2>&1; echo "graph_ab_rc=$?" >> $O/rc.txt
 SCB_GRAPH=3 timeout 60 python -m pytest tests/test_gpu_multistream.py -q -m gpu -k "sharded or batch_invariance" > $O/graph_sharded_tests.txt 2>&1; echo "graph_sharded_rc=$?" >> $O/rc.txt
 # the whole parity suite with every engine on its own stream and both graphs on (engines on the default stream would
 # silently keep plain launches)

@@ -19,7 +19,7 @@
 // epilogue warps convert chunk j; acc1 and H are double-buffered.  TMEM: 2 x 128 + 256 = 512 columns.
 // Shared memory: A 64 KB + H 2 x 32 KB + weight ring 3 x 32 KB = 224 KB -> one CTA per SM.
 //
-// Measured design points (tests/ffn_timeline.py, clock64 stamps inside the kernel):
+// Measured design points (scripts/ffn_timeline.py, clock64 stamps inside the kernel):
 //   * the MMA-issue and TMA-issue loops are executed by whole warps with one elected lane issuing; under
 //     `if (lane == 0)` ptxas wraps every UTCHMMA in a lane-serialising R2UR loop (~100 cycles per MMA);
 //   * UTCHMMA issue is paced by the tensor pipe (shallow queue), so every barrier wait of the issuing warp is pipe idle

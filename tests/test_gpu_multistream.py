@@ -217,3 +217,44 @@ def test_batch_invariance_large_group():
         assert a[0] == b[0] and a[2] == b[2] and a[3] == b[3], f"stream {s}"
         np.testing.assert_array_equal(np.asarray(a[1]), np.asarray(b[1]))     # fp64 scores bit-identical
     sg.close()
+
+
+def test_failed_push_leaves_every_stream_untouched():
+    """A push that is rejected after some of its streams were already planned (here: stream 1 sends a final chunk the
+    reference itself cannot process) must roll the host planner back: stream 0 then continues exactly as if the failed
+    call had never happened.  Also: duplicate stream ids in one push are rejected."""
+    from oracle.speech2text import OracleSpeech2Text
+    from speechcatcher_b200 import StreamGroup
+    from speechcatcher_b200.synthetic import synth_audio
+    md = model_dir("m_d2")
+    n = 4 * 16000 + 321
+    audio = synth_audio(77, n)
+    grp = StreamGroup(md, n_streams=2, beam_size=5, device="cuda:0", max_seconds=8.0)
+    orc = OracleSpeech2Text(md, beam_size=5)
+    pos = 0
+    k = 0
+    while pos < n:
+        a = audio[pos: pos + 8192]
+        fin = pos + 8192 >= n
+        if k in (1, 4):
+            with pytest.raises(RuntimeError):          # 100 samples, final, nothing buffered: conv2d would raise upstream
+                grp.push([0, 1], [a, np.zeros(100, np.float32)], [fin, True])
+            with pytest.raises(RuntimeError):
+                grp.push([0, 0], [a, a], [fin, fin])
+        grp.push([0], [a], [fin])
+        orc(a, is_final=fin, finalize_all=fin)
+        if grp.last_plan(0).called:
+            ys, sc, xp, pidx = grp.beam(0)
+            assert ys == [list(h.yseq) for h in orc.hyps], f"chunk {k}"
+            assert xp == [list(h.xpos) for h in orc.hyps]
+            assert pidx == orc.search.process_idx
+        pos += 8192
+        k += 1
+    # stream 1 was never advanced by the failed pushes: a regular utterance on it still matches
+    orc1 = OracleSpeech2Text(md, beam_size=5)
+    b = synth_audio(78, 2 * 16000 + 999)
+    for i in range(0, len(b), 8192):
+        fin = i + 8192 >= len(b)
+        grp.push([1], [b[i:i + 8192]], [fin])
+        orc1(b[i:i + 8192], is_final=fin, finalize_all=fin)
+    assert grp.beam(1)[0] == [list(h.yseq) for h in orc1.hyps]

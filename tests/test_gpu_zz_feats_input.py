@@ -2,9 +2,7 @@
 produced by the reference, plus the reference's own feature-driven tests (tests/test_speech2text_streaming.py:93-222)
 restated on the B200 class.
 
-The feature-input push (`sc_engine_push_features`) was written after round 1's GPU minutes were spent: these tests are
-marked xfail(strict=False) until they have run on a device once, and the file name sorts last among the GPU tests, so
-a defect here (even one that poisons the CUDA context) cannot mask the rest of the suite."""
+(First device run: round 2; the round-1 xfail markers are gone.)"""
 import json
 
 import numpy as np
@@ -13,7 +11,7 @@ import pytest
 from helpers import GOLDEN, model_dir
 from oracle.gen_golden_feats import feature_chunks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180), pytest.mark.xfail(strict=False, reason="feature-input path not yet run on a device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 G = json.loads((GOLDEN / "feats_input.json").read_text())
 
 

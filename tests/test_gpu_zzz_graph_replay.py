@@ -1,16 +1,16 @@
 """GPU: opt-in CUDA-graph replay of the search iteration / encoder stack (engine options graph_decode, graph_encoder)
 gives exactly the results of plain launches.
 
-Written after round 1's GPU minutes were spent: xfail(strict=False) until it has run on a device once, and the file
-name sorts last so that nothing here can disturb the rest of the suite.  tests/graph_replay_ab.py is the same check as a
-script with timings."""
+The engine falls back to plain launches when a capture is refused, so every graph run also asserts that graphs were
+really replayed (engine counter "graphs_replayed").  scripts/graph_replay_ab.py is the same check as a script with
+timings."""
 import numpy as np
 import pytest
 import torch
 
 from helpers import model_dir
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180), pytest.mark.xfail(strict=False, reason="graph replay not yet run on a device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 
 def _run(md, graph, dtype, lengths):
@@ -37,7 +37,13 @@ def _run(md, graph, dtype, lengths):
             g.push(ids, chunks, fins)
             beams.append([g.beam(s) for s in ids])
         st.synchronize()
+    replayed, failed = g.counter("graphs_replayed"), g.counter("graph_failed")
     g.close()
+    if graph:
+        assert not failed, "graph capture was refused: the run silently used plain launches"
+        assert replayed > 0, "no CUDA graph was replayed"
+    else:
+        assert replayed == 0
     return beams
 
 
@@ -45,12 +51,13 @@ def _run(md, graph, dtype, lengths):
 def test_graph_replay_is_bit_identical_in_fp32(graph):
     md = model_dir("xl_d4")
     lengths = [9 * 16000 + 77, 7 * 16000, 10 * 16000 + 4000]
-    base = _run(md, 0, "float32", lengths)
-    got = _run(md, graph, "float32", lengths)
-    for x, y in zip(base, got):
-        for a, b in zip(x, y):
-            assert a[0] == b[0] and a[2] == b[2] and a[3] == b[3]
-            np.testing.assert_array_equal(a[1], b[1])
+    for dtype in ("float32_tc", "float32_simt"):
+        base = _run(md, 0, dtype, lengths)
+        got = _run(md, graph, dtype, lengths)
+        for x, y in zip(base, got):
+            for a, b in zip(x, y):
+                assert a[0] == b[0] and a[2] == b[2] and a[3] == b[3]
+                np.testing.assert_array_equal(a[1], b[1])
 
 
 def test_graph_replay_same_search_in_bf16():
