@@ -8,7 +8,8 @@
  * Conventions
  *   - plain pointers and sizes only, no torch types; `stream` is a cudaStream_t passed as void*
  *   - the caller owns every device buffer (including the engine workspace); the library allocates no
- *     per-engine device memory and keeps no global mutable state besides small constant tables
+ *     device memory (every table, including the frontend's window / mel matrix, lives in the engine workspace) and keeps
+ *     no global mutable state besides a cache of TMA descriptors and per-device "attribute set" flags
  *   - every function returns 0 on success and a negative code on failure; sc_last_error() explains
  *   - functions never throw across the boundary; one driver thread per engine handle
  */
@@ -192,6 +193,22 @@ int sc_segment_search(const double* smoothed_host, int64_t n_frames, const ScSeg
                       int32_t max_cuts, int32_t* n_cuts);
 
 /* ---- single operators over raw device pointers (used by the parity tests) ---- */
+/* K1, the frontend of one waveform slab (speech2text_streaming.py:350-358 + stft_frontend.py:87-154): centred STFT
+ * (n_fft 512, hop 160, hann 400, reflect padding) -> power -> 257x80 mel -> log(clamp 1e-10) -> (x - mean) / std in fp64
+ * (mean_dev may be NULL: no normalisation).  workspace_dev: sc_frontend_workspace_bytes() of caller-owned device memory,
+ * initialised once with the host tables by sc_frontend_init.  feats_dev receives 1 + n_samples / 160 rows of 80 floats. */
+size_t sc_frontend_workspace_bytes(void);
+int sc_frontend_init(void* workspace_dev, const float* window400, const float* mel_fb);
+int sc_frontend_fbank_mvn(void* workspace_dev, const float* wave_dev, int32_t n_samples, const double* mean_dev,
+                          const double* std_dev, float* feats_dev, int32_t* n_frames, void* stream);
+/* K7, one call of the batched CTC prefix scorer (ctc_prefix_score_full.py:88-291, CTCPrefixScoreTH.__call__) for n_hyp
+ * hypotheses of equal length over explicit tensors: x_dev [t][v] emission store, r_prev_dev [n_hyp][t][2] forward
+ * variables (non-blank, blank) of every hypothesis, last_tok_dev [n_hyp], prefix_len = len(yseq) - 1, cand_ids_dev
+ * [n_hyp][40] pre-beam candidates.  Outputs: psi_dev [n_hyp][40] = log_psi of the candidates, psi_eos_dev [n_hyp] =
+ * r_sum[t-1] (the <eos> entry), r_new_dev (may be NULL) [n_hyp][40][t][2] = the forward variables select_state hands on. */
+int sc_ctc_prefix_step(const float* x_dev, int32_t t, int32_t v, const float* r_prev_dev, const int32_t* last_tok_dev,
+                       int32_t prefix_len, const int32_t* cand_ids_dev, int32_t n_hyp, float* psi_dev, float* psi_eos_dev,
+                       float* r_new_dev, void* stream);
 /* LayerNorm eps=1e-12 (model/layers/normalization.py:23) */
 int sc_layernorm_f32(const float* x, const float* w, const float* b, float* y, int32_t rows, int32_t d,
                      void* stream);

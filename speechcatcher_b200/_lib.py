@@ -68,6 +68,10 @@ SYMBOLS = {
     "sc_segment_filterbank_bins": (C.c_int, [_pd]),
     "sc_segment_energy": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_double, _vp]),
     "sc_segment_search": (C.c_int, [_pd, C.c_int64, C.POINTER(ScSegmentParams), C.POINTER(C.c_int64), _i32, _pi32]),
+    "sc_frontend_workspace_bytes": (C.c_size_t, []),
+    "sc_frontend_init": (C.c_int, [_vp, _vp, _vp]),
+    "sc_frontend_fbank_mvn": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _pi32, _vp]),
+    "sc_ctc_prefix_step": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "sc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "sc_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "sc_linear_x3": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

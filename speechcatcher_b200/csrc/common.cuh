@@ -60,6 +60,13 @@ __device__ __forceinline__ float lse2(float a, float b) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Function attributes (cudaFuncSetAttribute) and __constant__ / __device__ symbols are per DEVICE, not per process: a
+// "done" flag (or the largest dynamic shared-memory size set so far) is therefore kept per device ordinal.
+struct PerDeviceMark {
+  size_t v[64] = {};
+  size_t& cur() { int d = 0; cudaGetDevice(&d); return v[d & 63]; }
+};
+
 // Programmatic dependent launch (PDL): the decode step is a chain of ~170 small dependent kernels, so the launch
 // and CTA-scheduling latency of kernel N+1 is overlapped with the execution of kernel N.  Every kernel launched
 // through launch_k() MUST call pdl_sync() as its first statement (before any early exit): griddepcontrol.wait

@@ -85,6 +85,8 @@ struct Engine {
   // frontend stats (device, inside workspace)
   double *d_mean = nullptr, *d_std = nullptr;
   bool has_stats = false;
+  FrontendTables* d_fe_tab = nullptr;       // window / twiddles / mel matrix (workspace)
+  bool fe_tab_ready = false;
   // device buffers
   float *wbuf, *featbuf, *h1, *h2, *subbuf, *prev_addin, *enc_ctx, *addin, *X, *Nrm, *QKV, *Att, *FF, *encbuf, *ctcx;
   float *dx, *dn, *dqkv, *dq, *dattn, *dffn, *dlogp;
@@ -181,6 +183,7 @@ static void carve(Engine& e, Carver& cv) {
   const size_t S = c.n_streams, D = c.d_model, F = c.ffn, V = c.vocab, B = c.beam, R = k.R;
   auto reg = [&](const char* name, void* p, size_t n) { if (!cv.dry) e.named[name] = {p, n}; };
   e.d_mean = cv.take<double>(80); e.d_std = cv.take<double>(80);
+  e.d_fe_tab = cv.take<FrontendTables>(1);
   e.wbuf = cv.take<float>(S * 512); reg("wbuf", e.wbuf, S * 512);
   e.featbuf = cv.take<float>(S * k.feat_cap * 80); reg("featbuf", e.featbuf, S * k.feat_cap * 80);
   e.h1 = cv.take<float>(S * k.t1_cap * 39 * D);
@@ -216,6 +219,12 @@ static void carve(Engine& e, Carver& cv) {
   sb.w_dec = (float)(1.0 - (double)c.ctc_weight); sb.w_ctc = c.ctc_weight;
   sb.ctcx = e.ctcx;
   sb.kv_bf16 = c.precision == 1;
+  {
+    // precise mode, beam <= 16: K|V caches as split fp16 planes for the tensor-core attention (kernels_attn_x3.cu);
+    // SCB_ATTN = "rows" / "cta" keeps fp32 caches and the CUDA-core attention kernels
+    const char* a = getenv("SCB_ATTN");
+    sb.kv_split = c.precision == 2 && c.beam <= 16 && !(a && (strcmp(a, "rows") == 0 || strcmp(a, "cta") == 0));
+  }
   if (sb.kv_bf16) sb.xkv = reinterpret_cast<float*>(cv.take<__nv_bfloat16>((size_t)c.dec_layers * S * k.Tcap * 2 * D));
   else sb.xkv = cv.take<float>((size_t)c.dec_layers * S * k.Tcap * 2 * D);
   if (sb.kv_bf16) sb.skv = reinterpret_cast<float*>(cv.take<__nv_bfloat16>((size_t)c.dec_layers * S * k.Lcap * B * 2 * D));
@@ -475,17 +484,19 @@ static int run_decode_step_x3(Engine& e, cudaStream_t st) {
   const int* nr = sb.n_rows;
   const Planes dn{e.dn, (size_t)R * D, R}, da{e.dattn, (size_t)R * D, R}, df{e.dffn, (size_t)R * F, R};
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, nullptr, nullptr, nullptr, st));
-  if (e.attn_f32_rows) { PD(T_DEC_EMBED, launch_build_self_keys(sb, st)); e.launches++; }
+  if (e.attn_f32_rows || sb.kv_split) { PD(T_DEC_EMBED, launch_build_self_keys(sb, st)); e.launches++; }
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
     PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln1w, w.ln1b, dn.base, dn.plane, D, R, D, nr, st));
     PD(T_DEC_QKV, x3_linear(e, dn, D, w.sqkvw, w.sqkvb, nullptr, e.dqkv, 3 * D, nullptr, R, 3 * D, 0, nr, st));
-    if (e.attn_f32_rows) PD(T_DEC_SELF_ATTN, launch_dec_attention_f32(sb, 0, l, e.dqkv, 3 * D, nullptr, split_out(da, D), st));
+    if (sb.kv_split) PD(T_DEC_SELF_ATTN, launch_dec_attention_x3(sb, 0, l, e.dqkv, 3 * D, nullptr, split_out(da, D), st));
+    else if (e.attn_f32_rows) PD(T_DEC_SELF_ATTN, launch_dec_attention_f32(sb, 0, l, e.dqkv, 3 * D, nullptr, split_out(da, D), st));
     else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, nullptr, nullptr, st, split_out(da, D)));
     PD(T_DEC_SO, x3_linear(e, da, D, w.sow, w.sob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
     PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln2w, w.ln2b, dn.base, dn.plane, D, R, D, nr, st));
     PD(T_DEC_CQ, x3_linear(e, dn, D, w.cqw, w.cqb, nullptr, e.dq, D, nullptr, R, D, 0, nr, st));
-    if (e.attn_f32_rows) PD(T_DEC_CROSS_ATTN, launch_dec_attention_f32(sb, 1, l, e.dq, D, nullptr, split_out(da, D), st));
+    if (sb.kv_split) PD(T_DEC_CROSS_ATTN, launch_dec_attention_x3(sb, 1, l, e.dq, D, nullptr, split_out(da, D), st));
+    else if (e.attn_f32_rows) PD(T_DEC_CROSS_ATTN, launch_dec_attention_f32(sb, 1, l, e.dq, D, nullptr, split_out(da, D), st));
     else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, nullptr, nullptr, st, split_out(da, D)));
     PD(T_DEC_CO, x3_linear(e, da, D, w.cow, w.cob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
     PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln3w, w.ln3b, dn.base, dn.plane, D, R, D, nr, st));
@@ -767,7 +778,8 @@ int sc_engine_set_weight(void* handle, const char* name, const void* dev_ptr, si
 int sc_engine_set_frontend(void* handle, const float* window400, const float* mel_fb, const double* mean, const double* std_) {
   Engine* e = (Engine*)handle;
   if (!e || !window400 || !mel_fb) { set_last_error("set_frontend: null argument"); return SC_ERR_ARG; }
-  if (frontend_upload_tables(window400, mel_fb)) return SC_ERR_CUDA;
+  if (frontend_upload_tables(e->d_fe_tab, window400, mel_fb)) return SC_ERR_CUDA;
+  e->fe_tab_ready = true;
   e->has_stats = mean && std_;
   if (e->has_stats) {
     SCB_CUDA_CHECK(cudaMemcpy(e->d_mean, mean, 80 * sizeof(double), cudaMemcpyHostToDevice));
@@ -1038,7 +1050,7 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
   const bool petot = prof_on(e, T_ENC_TOTAL, false);
   if (petot) prof_mark(e, T_ENC_TOTAL, st, true);
   if (!feats_dev) {
-    PE(T_FRONTEND, launch_frontend(wave_dev, ld_wave, e.wbuf, 512, e.d_fd, n_fd, frame_base, e.has_stats ? e.d_mean : nullptr,
+    PE(T_FRONTEND, launch_frontend(e.fe_tab_ready ? e.d_fe_tab : nullptr, wave_dev, ld_wave, e.wbuf, 512, e.d_fd, n_fd, frame_base, e.has_stats ? e.d_mean : nullptr,
                         e.has_stats ? e.d_std : nullptr, e.featbuf, k.feat_cap, st));
   }
 #undef e
@@ -1135,8 +1147,12 @@ static int push_impl(void* handle, const float* wave_dev, int32_t ld_wave, const
         GemmArgs kv;
         kv.A = e->encbuf; kv.a_row_off = e->d_en_a; kv.W = e->dec[l].ckvw; kv.bias = e->dec[l].ckvb;
         kv.C = dst; kv.c_row_off = e->d_en_kv; kv.M = n_en; kv.N = 2 * D; kv.K = D;
+        X3Extra xs;
+        if (e->sb.kv_split) {        // cache rows as split planes [hi K|V][lo K|V] (same row pitch as fp32)
+          kv.C = nullptr; xs.C2 = dst; xs.c2_plane = 2 * (size_t)D; xs.ldc2 = 2 * D;
+        }
 #define e eref
-        PE(T_XKV, gemm_fp32(e, kv, st));
+        PE(T_XKV, gemm_fp32(e, kv, st, xs));
 #undef e
       }
     }
@@ -1388,6 +1404,37 @@ static int planner_push_any(void* planner, int32_t s, int32_t count, int32_t is_
 }
 
 // ---------------- single operators
+size_t sc_frontend_workspace_bytes(void) { return align_up(sizeof(FrontendTables)) + 256; }
+
+int sc_frontend_init(void* workspace_dev, const float* window400, const float* mel_fb) {
+  if (!workspace_dev || !window400 || !mel_fb) { set_last_error("frontend_init: null argument"); return SC_ERR_ARG; }
+  return frontend_upload_tables((FrontendTables*)workspace_dev, window400, mel_fb) ? SC_ERR_CUDA : SC_OK;
+}
+
+int sc_frontend_fbank_mvn(void* workspace_dev, const float* wave_dev, int32_t n_samples, const double* mean_dev,
+                          const double* std_dev, float* feats_dev, int32_t* n_frames, void* stream) {
+  if (!workspace_dev || !wave_dev || !feats_dev || n_samples < 1) { set_last_error("frontend_fbank_mvn: bad argument"); return SC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  FrontendDesc d{};
+  d.stream = 0; d.n_prev = 0; d.n_new = n_samples; d.slab = n_samples; d.n_frames = 1 + n_samples / 160;
+  d.emit0 = 0; d.emit1 = d.n_frames; d.feat_off = 0; d.new_buf = 0; d.frame_base = 0;
+  FrontendDesc* d_dev = (FrontendDesc*)((unsigned char*)workspace_dev + align_up(sizeof(FrontendTables)));
+  SCB_CUDA_CHECK(cudaMemcpyAsync(d_dev, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+  SCB_CUDA_CHECK(cudaStreamSynchronize(st));                   // `d` lives on this stack frame
+  if (launch_frontend((const FrontendTables*)workspace_dev, wave_dev, n_samples, wave_dev, 0, d_dev, 1, d.n_frames,
+                      mean_dev, mean_dev ? std_dev : nullptr, feats_dev, d.n_frames, st)) return SC_ERR_CUDA;
+  if (n_frames) *n_frames = d.n_frames;
+  return SC_OK;
+}
+
+int sc_ctc_prefix_step(const float* x_dev, int32_t t, int32_t v, const float* r_prev_dev, const int32_t* last_tok_dev,
+                       int32_t prefix_len, const int32_t* cand_ids_dev, int32_t n_hyp, float* psi_dev, float* psi_eos_dev,
+                       float* r_new_dev, void* stream) {
+  if (!x_dev || !r_prev_dev || !last_tok_dev || !cand_ids_dev || !psi_dev || !psi_eos_dev) { set_last_error("ctc_prefix_step: null argument"); return SC_ERR_ARG; }
+  return launch_ctc_prefix_op(x_dev, t, v, r_prev_dev, last_tok_dev, prefix_len, cand_ids_dev, n_hyp, psi_dev, psi_eos_dev,
+                              r_new_dev, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+
 int sc_layernorm_f32(const float* x, const float* w, const float* b, float* y, int32_t rows, int32_t d, void* stream) {
   return launch_layernorm(x, d, w, b, y, d, rows, d, nullptr, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }

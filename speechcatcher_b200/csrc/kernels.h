@@ -86,10 +86,16 @@ int launch_layernorm_split(const float* x, int ldx, const float* w, const float*
                            int rows, int D, const int* n_rows_dev, cudaStream_t st);
 
 // ---------------------------------------------------------------- frontend
-int frontend_upload_tables(const float* window400, const float* mel_fb_257x80);
-int launch_frontend(const float* wave_in, int ld_wave, const float* wbuf, int ld_wbuf, const FrontendDesc* desc,
-                    int n_desc, int total_frames, const double* mean, const double* std_, float* featbuf,
-                    int feat_cap, cudaStream_t st);
+struct FrontendTables {        // device-resident constants of the frontend, carved from the engine workspace
+  float window[512];
+  float2 twiddle[256];
+  int2 melrange[80];
+  float melfb[257 * 80];
+};
+int frontend_upload_tables(FrontendTables* dev, const float* window400, const float* mel_fb_257x80);
+int launch_frontend(const FrontendTables* tab, const float* wave_in, int ld_wave, const float* wbuf, int ld_wbuf,
+                    const FrontendDesc* desc, int n_desc, int total_frames, const double* mean, const double* std_,
+                    float* featbuf, int feat_cap, cudaStream_t st);
 int launch_wavebuf_update(const float* wave_in, int ld_wave, float* wbuf, int ld_wbuf,
                           const FrontendDesc* desc, int n_desc, cudaStream_t st);
 
@@ -152,6 +158,7 @@ struct SearchBuffers {
   const float* ctcx;      // [S][Tcap][V]
   float* xkv;             // [Ld][S][Tcap][2D]  cross-attention K|V (bf16 elements when kv_bf16)
   int kv_bf16;
+  int kv_split;           // K|V caches hold split fp16 planes per row: [hi K|V][lo K|V] (kernels_attn_x3.cu)
   float* skv;             // [Ld][S][Lcap][B][2D] self-attention K|V (tree storage)
   // beam (ping-pong)
   int* yseq;              // [2][S][B][Lcap]
@@ -210,8 +217,13 @@ int launch_dec_cross_attention(const SearchBuffers& sb, int layer, const float* 
 // (launch_build_self_keys must have run in this search iteration; also appends this step's K|V), 1: cross-attention.
 int launch_dec_attention_f32(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
                              SplitOut so, cudaStream_t st);
+// split-plane K|V caches, tensor cores with fp32-class accuracy (kernels_attn_x3.cu); beam <= 16
+int launch_dec_attention_x3(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
+                            SplitOut so, cudaStream_t st);
 int launch_logsoftmax_prebeam(const SearchBuffers& sb, float* logits, cudaStream_t st);
 int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st);
+int launch_ctc_prefix_op(const float* x, int T, int V, const float* r_prev, const int* last_tok, int L, const int* ids,
+                         int n_hyp, float* psi, float* psi_eos, float* r_new, cudaStream_t st);
 int launch_combine_topk(const SearchBuffers& sb, const float* logp, cudaStream_t st);
 int launch_beam_prune(const SearchBuffers& sb, cudaStream_t st);
 int launch_ctc_state_update(const SearchBuffers& sb, cudaStream_t st);

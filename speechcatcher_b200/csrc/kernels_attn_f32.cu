@@ -231,7 +231,8 @@ static int attn_f32_launch(const SearchBuffers& sb, float* kv_layer, const float
                            cudaStream_t st) {
   const int H = sb.D / DK;
   const size_t smem = sizeof(float) * ((size_t)MAXB * sb.D + (size_t)H * 2 * 32 * DK + (size_t)H * MAXB * 32);
-  static size_t attr = 0;
+  static PerDeviceMark mk;
+  size_t& attr = mk.cur();
   if (attr < smem) {
     if (cudaFuncSetAttribute(dec_attn_f32_kernel<DK, MAXB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(dec_attn_f32, smem=%zu) failed", smem);

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(128) build_self_keys_kernel(SearchBuffers sb) 
 
 int launch_build_self_keys(const SearchBuffers& sb, cudaStream_t st) {
   const size_t smem = (size_t)sb.B * sb.Lcap;
-  static size_t attr = 0;
+  static PerDeviceMark mk;
+  size_t& attr = mk.cur();
   if (smem > 48 * 1024 && attr < smem) {
     cudaFuncSetAttribute(build_self_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
@@ -488,7 +489,8 @@ static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const 
   const size_t merge = sizeof(float) * (128 + 4 * 16 * DK);
   if (stages < merge) { set_last_error("attn_mma: merge scratch does not fit"); return -1; }
   if (sb.B > 16) {                                  // beam 17..32: one CTA per (stream, head, m16 tile of hypotheses)
-    static size_t attr_w = 0;
+    static PerDeviceMark mk_w;
+    size_t& attr_w = mk_w.cur();
     if (attr_w < smem) {
       if (cudaFuncSetAttribute(dec_attn_mma_kernel<DK, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         set_last_error("attn_mma: cudaFuncSetAttribute(%zu) failed", smem);
@@ -501,7 +503,8 @@ static int launch_mma_t(const SearchBuffers& sb, __nv_bfloat16* kv_layer, const 
     SCB_LAUNCH_CHECK();
     return 0;
   }
-  static size_t attr = 0;
+  static PerDeviceMark mk;
+  size_t& attr = mk.cur();
   if (attr < smem) {
     if (cudaFuncSetAttribute(dec_attn_mma_kernel<DK, MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("attn_mma: cudaFuncSetAttribute(%zu) failed", smem);

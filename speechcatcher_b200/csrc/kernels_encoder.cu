@@ -367,12 +367,12 @@ int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, con
   if (!out16 && rows_kernel && (dk == 32 || dk == 64) && d_model % 8 == 0) {
     const size_t smem = sizeof(float) * 2 * kSlots * d_model;
     if (dk == 32) {
-      static bool a = false;
-      if (!a) { cudaFuncSetAttribute(enc_attention_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+      static PerDeviceMark mk;
+      if (mk.cur() < smem) { cudaFuncSetAttribute(enc_attention_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mk.cur() = smem; }
       enc_attention_rows_kernel<32><<<n_blk, 192, smem, st>>>(qkv, out, blk, d_model, n_head, so);
     } else {
-      static bool a = false;
-      if (!a) { cudaFuncSetAttribute(enc_attention_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+      static PerDeviceMark mk;
+      if (mk.cur() < smem) { cudaFuncSetAttribute(enc_attention_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mk.cur() = smem; }
       enc_attention_rows_kernel<64><<<n_blk, 192, smem, st>>>(qkv, out, blk, d_model, n_head, so);
     }
     SCB_LAUNCH_CHECK();

@@ -315,13 +315,13 @@ int launch_ffn_fused_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
   if (tc_get_map(W2, FF_D, F, F, 128, &mw2)) return -1;
   if (tc_get_map_f32(C, M, FF_D, ldc, 32, &mc)) return -1;
   constexpr size_t smem = 1024 + (size_t)(4 + 4) * FF_BOX + (size_t)FF_RING * FF_STAGE + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceMark attr_mk;
+  if (!attr_mk.cur()) {
     if (cudaFuncSetAttribute(ffn_fused_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(ffn_fused, smem=%zu) failed", smem);
       return -1;
     }
-    attr_set = true;
+    attr_mk.cur() = 1;
   }
   FfnParams p{b1, b2, M, F, accumulate, n_rows_dev, dbg};
   launch_k(ffn_fused_bf16_kernel, dim3(cdiv(M, TC_BM), splits), dim3(FF_THREADS), smem, st, ma, mw1, mw2, mc, p);

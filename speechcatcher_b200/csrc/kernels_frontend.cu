@@ -11,33 +11,31 @@ namespace scb {
 
 constexpr int NFFT = 512, HOPS = 160, WINL = 400, NBIN = 257, NMEL = 80;
 
-__constant__ float c_window[NFFT];        // hann(400) zero-padded to 512 (offset 56)
-__constant__ float2 c_twiddle[NFFT / 2];  // exp(-2*pi*i*k/512)
-__constant__ int2 c_melrange[NMEL];       // [k_lo, k_hi) of the non-zero taps of every (triangular) mel filter
-static float* g_melfb = nullptr;          // [257][80] device copy (owned by the library, 82 KB)
-
-int frontend_upload_tables(const float* window400, const float* mel_fb) {
-  float w[NFFT];
-  for (int i = 0; i < NFFT; ++i) w[i] = 0.f;
-  for (int i = 0; i < WINL; ++i) w[(NFFT - WINL) / 2 + i] = window400[i];
-  SCB_CUDA_CHECK(cudaMemcpyToSymbol(c_window, w, sizeof(w)));
-  float2 tw[NFFT / 2];
+// The constant tables live in the engine's caller-owned workspace (one copy per engine, hence per device): the library
+// allocates no device memory and keeps no device-side global state.
+//   window[512]  hann(400) zero-padded to 512 (offset 56)        twiddle[256]  exp(-2 pi i k / 512)
+//   melrange[80] [k_lo, k_hi) of the non-zero taps of every (triangular) mel filter        melfb[257][80]
+int frontend_upload_tables(FrontendTables* dev, const float* window400, const float* mel_fb) {
+  static_assert(sizeof(FrontendTables) == sizeof(float) * NFFT + sizeof(float2) * (NFFT / 2) + sizeof(int2) * NMEL +
+                                              sizeof(float) * NBIN * NMEL, "FrontendTables layout");
+  FrontendTables* h = new FrontendTables;
+  for (int i = 0; i < NFFT; ++i) h->window[i] = 0.f;
+  for (int i = 0; i < WINL; ++i) h->window[(NFFT - WINL) / 2 + i] = window400[i];
   for (int k = 0; k < NFFT / 2; ++k) {
     double a = -2.0 * M_PI * (double)k / (double)NFFT;
-    tw[k] = make_float2((float)cos(a), (float)sin(a));
+    h->twiddle[k] = make_float2((float)cos(a), (float)sin(a));
   }
-  SCB_CUDA_CHECK(cudaMemcpyToSymbol(c_twiddle, tw, sizeof(tw)));
-  int2 rng[NMEL];
   for (int m = 0; m < NMEL; ++m) {
     int lo = NBIN, hi = 0;
     for (int k = 0; k < NBIN; ++k)
       if (mel_fb[k * NMEL + m] != 0.f) { if (k < lo) lo = k; hi = k + 1; }
     if (lo >= hi) { lo = 0; hi = 0; }
-    rng[m] = make_int2(lo, hi);
+    h->melrange[m] = make_int2(lo, hi);
   }
-  SCB_CUDA_CHECK(cudaMemcpyToSymbol(c_melrange, rng, sizeof(rng)));
-  if (!g_melfb) SCB_CUDA_CHECK(cudaMalloc(&g_melfb, sizeof(float) * NBIN * NMEL));
-  SCB_CUDA_CHECK(cudaMemcpy(g_melfb, mel_fb, sizeof(float) * NBIN * NMEL, cudaMemcpyHostToDevice));
+  for (int i = 0; i < NBIN * NMEL; ++i) h->melfb[i] = mel_fb[i];
+  const cudaError_t e = cudaMemcpy(dev, h, sizeof(FrontendTables), cudaMemcpyHostToDevice);
+  delete h;
+  if (e != cudaSuccess) { set_last_error("frontend tables upload failed: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }
 
@@ -46,7 +44,7 @@ __device__ __forceinline__ int bitrev9(int i) { return (int)(__brev((unsigned)i)
 // blockDim = 128 (4 warps = 4 frames).  Dynamic smem: 4 * 512 float2.
 __global__ void __launch_bounds__(128) frontend_kernel(
     const float* __restrict__ wave_in, int ld_wave, const float* __restrict__ wbuf, int ld_wbuf,
-    const FrontendDesc* __restrict__ desc, int n_desc, int total_frames, const float* __restrict__ melfb,
+    const FrontendDesc* __restrict__ desc, int n_desc, int total_frames, const FrontendTables* __restrict__ tab,
     const double* __restrict__ mean, const double* __restrict__ std_, float* __restrict__ featbuf,
     int feat_cap) {
   __shared__ float2 sm[4][NFFT];
@@ -75,7 +73,7 @@ __global__ void __launch_bounds__(128) frontend_kernel(
     float v = 0.f;
     if (idx < d.n_prev) v = wb[idx];
     else if (idx < have) v = wi[idx - d.n_prev];   // beyond `have`: zero padding of a short final slab
-    x[bitrev9(i)] = make_float2(v * c_window[i], 0.f);
+    x[bitrev9(i)] = make_float2(v * __ldg(&tab->window[i]), 0.f);
   }
   __syncwarp();
   // radix-2 decimation-in-time FFT, 9 stages, 256 butterflies per stage
@@ -87,7 +85,7 @@ __global__ void __launch_bounds__(128) frontend_kernel(
       int j = bfly & (half - 1);
       int i0 = ((bfly >> (s - 1)) << s) + j;
       int i1 = i0 + half;
-      float2 w = c_twiddle[j * tstep];
+      float2 w = __ldg(&tab->twiddle[j * tstep]);
       float2 a = x[i0], b = x[i1];
       float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
       x[i0] = make_float2(a.x + t.x, a.y + t.y);
@@ -102,21 +100,21 @@ __global__ void __launch_bounds__(128) frontend_kernel(
   for (int m = lane; m < NMEL; m += 32) {
     // taps outside [k_lo, k_hi) are exactly zero, and fma(p, 0, acc) == acc, so skipping them is bit-identical
     float acc = 0.f;
-    const int2 rg = c_melrange[m];
-    for (int k = rg.x; k < rg.y; ++k) acc = fmaf(p[k], melfb[k * NMEL + m], acc);
+    const int2 rg = __ldg(&tab->melrange[m]);
+    for (int k = rg.x; k < rg.y; ++k) acc = fmaf(p[k], __ldg(&tab->melfb[k * NMEL + m]), acc);
     float lg = logf(fmaxf(acc, 1e-10f));
     if (mean) lg = (float)(((double)lg - mean[m]) / std_[m]);   // numpy fp64 round trip, :355-358
     out[m] = lg;
   }
 }
 
-int launch_frontend(const float* wave_in, int ld_wave, const float* wbuf, int ld_wbuf, const FrontendDesc* desc,
-                    int n_desc, int total_frames, const double* mean, const double* std_, float* featbuf,
-                    int feat_cap, cudaStream_t st) {
+int launch_frontend(const FrontendTables* tab, const float* wave_in, int ld_wave, const float* wbuf, int ld_wbuf,
+                    const FrontendDesc* desc, int n_desc, int total_frames, const double* mean, const double* std_,
+                    float* featbuf, int feat_cap, cudaStream_t st) {
   if (total_frames <= 0) return 0;
-  if (!g_melfb) { set_last_error("frontend tables not uploaded"); return -1; }
+  if (!tab) { set_last_error("frontend tables not uploaded"); return -1; }
   frontend_kernel<<<cdiv(total_frames, 4), 128, 0, st>>>(wave_in, ld_wave, wbuf, ld_wbuf, desc, n_desc,
-                                                        total_frames, g_melfb, mean, std_, featbuf, feat_cap);
+                                                        total_frames, tab, mean, std_, featbuf, feat_cap);
   SCB_LAUNCH_CHECK();
   return 0;
 }

@@ -349,13 +349,13 @@ int tc_get_map_f32(const void* ptr, int rows, int cols, int ld, int box_rows, CU
 template <int BN, int TC_STAGES, bool LNA = false>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = 1024 + TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceMark attr_mk;
+  if (!attr_mk.cur()) {
     if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TC_STAGES, LNA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(smem=%zu) failed", smem);
       return -1;
     }
-    attr_set = true;
+    attr_mk.cur() = 1;
   }
   dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
   launch_k(gemm_bf16_tc_kernel<BN, TC_STAGES, LNA>, grid, dim3(TC_THREADS), smem, st, ma, mb, p);

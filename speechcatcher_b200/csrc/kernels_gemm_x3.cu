@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
     if (row_ok) {
       if (p.C) crow = p.c_row_off ? p.C + p.c_row_off[m] : p.C + (size_t)m * p.ldc;
       if (p.R) rrow = p.R + (size_t)m * p.ldr;
-      if (p.C2) c2row = p.C2 + (size_t)m * p.ldc2;
+      // split-plane rows; with a row-offset table (given in fp32 elements of a [hi | lo] row, e.g. the K|V cache rows) the
+      // planes of a row are adjacent: hi at 2 * offset, lo c2_plane elements further
+      if (p.C2) c2row = p.c_row_off ? p.C2 + 2 * p.c_row_off[m] : p.C2 + (size_t)m * p.ldc2;
     }
     float4 rn[4];
     if (rrow) {
@@ -304,13 +306,13 @@ template <int BN, int STAGES, int J, bool A_TMA>
 static int x3_launch(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mah, const CUtensorMap& mal,
                      const X3Params& p, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (2 * TC_BM * TC_BK * 2 + 2 * BN * TC_BK * 2) + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceMark attr_mk;
+  if (!attr_mk.cur()) {
     if (cudaFuncSetAttribute(gemm_x3_kernel<BN, STAGES, J, A_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(gemm_x3, smem=%zu) failed", smem);
       return -1;
     }
-    attr_set = true;
+    attr_mk.cur() = 1;
   }
   dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
   launch_k(gemm_x3_kernel<BN, STAGES, J, A_TMA>, grid, dim3(X3_THREADS), smem, st, mh, ml, mah, mal, p);

@@ -397,12 +397,12 @@ static int launch_cross_t(const SearchBuffers& sb, int layer, const float* q, in
   const int tile = 4096 / dk;
   const size_t smem = sizeof(float) * ((size_t)tile * (dk + 4) + (size_t)tile * dk + (size_t)AMAXB * tile + AMAXB * dk + 3 * AMAXB);
   if (dk == 32) {
-    static bool a = false;
-    if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+    static PerDeviceMark mk;
+    if (mk.cur() < smem) { cudaFuncSetAttribute(dec_cross_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mk.cur() = smem; }
     launch_k(dec_cross_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16, so);
   } else if (dk == 64) {
-    static bool a = false;
-    if (!a) { cudaFuncSetAttribute(dec_cross_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = true; }
+    static PerDeviceMark mk;
+    if (mk.cur() < smem) { cudaFuncSetAttribute(dec_cross_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mk.cur() = smem; }
     launch_k(dec_cross_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, q, ldq, out, out16, so);
   } else { set_last_error("cross attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
@@ -657,12 +657,12 @@ static int launch_self_t(const SearchBuffers& sb, int layer, const float* qkv, i
   const size_t smem = sizeof(float) * ((size_t)tile * (dk + 4) + (size_t)tile * dk + (size_t)AMAXB * tile + AMAXB * dk + 3 * AMAXB) +
                       16 + (size_t)AMAXB * sb.Lcap;
   if (dk == 32) {
-    static size_t a = 0;
-    if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
+    static PerDeviceMark mk;
+    if (mk.cur() < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<32, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mk.cur() = smem; }
     launch_k(dec_self_attn_kernel<32, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16, so);
   } else if (dk == 64) {
-    static size_t a = 0;
-    if (a < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a = smem; }
+    static PerDeviceMark mk;
+    if (mk.cur() < smem) { cudaFuncSetAttribute(dec_self_attn_kernel<64, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); mk.cur() = smem; }
     launch_k(dec_self_attn_kernel<64, KVT>, grid, dim3(128), smem, st, sb, base, qkv, ldq, out, out16, so);
   } else { set_last_error("self attention: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
@@ -846,6 +846,34 @@ __global__ void __launch_bounds__(64) ctc_prefix_kernel(SearchBuffers sb) {
 
 int launch_ctc_prefix(const SearchBuffers& sb, cudaStream_t st) {
   launch_k(ctc_prefix_kernel, dim3(sb.S * sb.B), dim3(64), 0, st, sb);
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
+// The same recursion as a stand-alone operator over explicit tensors (C ABI sc_ctc_prefix_step; direct parity tests of
+// SURVEY.md row K7 against oracle/ctc_prefix.py): one CTA per hypothesis, thread k < 40 = candidate k.
+__global__ void __launch_bounds__(64) ctc_prefix_op_kernel(const float* __restrict__ x, int T, int V,
+                                                           const float* __restrict__ r_prev, const int* __restrict__ last_tok,
+                                                           int L, const int* __restrict__ ids, float* __restrict__ psi,
+                                                           float* __restrict__ psi_eos, float* __restrict__ r_new) {
+  const int h = blockIdx.x, k = threadIdx.x;
+  const float* rp = r_prev + (size_t)h * T * 2;
+  if (k < kPreBeam) {
+    const int tok = ids[(size_t)h * kPreBeam + k];
+    float* ro = r_new ? r_new + ((size_t)h * kPreBeam + k) * T * 2 : nullptr;
+    float ps;
+    ctc_forward_column(x, V, rp, T, L, tok, tok == last_tok[h], ro, ps);
+    psi[(size_t)h * kPreBeam + k] = ps;
+  } else if (k == kPreBeam) {
+    psi_eos[h] = lse2(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);
+  }
+}
+
+int launch_ctc_prefix_op(const float* x, int T, int V, const float* r_prev, const int* last_tok, int L, const int* ids,
+                         int n_hyp, float* psi, float* psi_eos, float* r_new, cudaStream_t st) {
+  if (n_hyp <= 0) return 0;
+  if (T < 1 || V < 2 || L < 0) { set_last_error("ctc_prefix_op: bad shape T=%d V=%d L=%d", T, V, L); return -1; }
+  ctc_prefix_op_kernel<<<n_hyp, 64, 0, st>>>(x, T, V, r_prev, last_tok, L, ids, psi, psi_eos, r_new);
   SCB_LAUNCH_CHECK();
   return 0;
 }

@@ -24,7 +24,7 @@ constexpr int SEG_NFFT = 512, SEG_WIN = 400, SEG_HOP = 160, SEG_NBIN = 257, SEG_
 constexpr int SEG_MAX_RADIUS = 200;
 
 __constant__ double2 c_tw64[SEG_NFFT / 2];   // exp(-2 pi i k / 512) in fp64
-static bool g_tw64_ready = false;
+static PerDeviceMark g_tw64_ready;     // the __constant__ twiddle table exists once per device
 
 struct SegBins { double b[SEG_NFILT + 2]; };
 struct SegGauss { int radius; double w[2 * SEG_MAX_RADIUS + 1]; };
@@ -123,14 +123,14 @@ __global__ void __launch_bounds__(256) seg_smooth_kernel(const double* __restric
 }
 
 static int ensure_tw64() {
-  if (g_tw64_ready) return 0;
+  if (g_tw64_ready.cur()) return 0;
   double2 tw[SEG_NFFT / 2];
   for (int k = 0; k < SEG_NFFT / 2; ++k) {
     const double a = -2.0 * M_PI * (double)k / (double)SEG_NFFT;
     tw[k] = make_double2(cos(a), sin(a));
   }
   SCB_CUDA_CHECK(cudaMemcpyToSymbol(c_tw64, tw, sizeof(tw)));
-  g_tw64_ready = true;
+  g_tw64_ready.cur() = 1;
   return 0;
 }
 
