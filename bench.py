@@ -200,6 +200,9 @@ def main():
                     help="split the GPU's streams into this many concurrently driven groups (own CUDA stream + host thread)")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("SCB_BENCH_GRAPH", "0")),
                     help="CUDA-graph replay (experimental, off by default): 1 = search iteration, 2 = encoder stack, 3 = both")
+    ap.add_argument("--enc-sms", type=int, default=int(os.environ.get("SCB_BENCH_ENC_SMS", "0")),
+                    help="SM partition of the encoder stream (green context): the frontend + encoder kernels of a push run on "
+                         "~N SMs, the rest stays free for the search chain; 0 = no partition")
     ap.add_argument("--lazy", type=int, default=int(os.environ.get("SCB_BENCH_LAZY", "-1")),
                     help="deferred-decode threshold (streams); 0 = strict per-push decoding; -1 = streams - streams/32")
     args = ap.parse_args()
@@ -285,9 +288,13 @@ def main():
             for g in shards:
                 g.set_option("graph_decode", args.graph & 1)
                 g.set_option("graph_encoder", (args.graph >> 1) & 1)
+        if args.enc_sms:
+            for g in shards:
+                g.set_option("encoder_sms", args.enc_sms)
         return sg_, shards
 
     sg, groups = make_groups(args.dtype)
+    groups_enc_sms = groups[0].counter("encoder_sms")      # SMs the driver really provisioned for the encoder stream (0 = none)
     grp = groups[0]                                   # kernel timing / roofline are taken on shard 0
     resident = host.to(dev)                           # inputs resident in HBM for `value`
     # e2e inputs: what a caller hands over per push -- one pinned [streams, chunk] buffer per chunk
@@ -452,9 +459,10 @@ def main():
     # per-kernel rooflines without cross-shard interference: one dedicated group holding all S streams, one full pass
     # per kernel with CUDA-event pairs around every launch of that kernel (same workload, same deferred scheduling)
     extra_roof = None
+    sync_latency = None
     if not args.no_extra_rooflines and rank == 0:
         g1 = StreamGroup(md, n_streams=S, beam_size=args.beam, ctc_weight=0.3, device=dev, dtype=args.dtype, use_bbd=False,
-                         max_chunk=CHUNK, max_seconds=args.seconds + 1.0)
+                         max_chunk=CHUNK, max_seconds=args.seconds + 1.0, own_stream=True)
         g1.set_option("lazy_threshold", max(1, S - S // 32))
         ids1 = np.arange(S, dtype=np.int32)
         lens1 = [np.full(S, int(l[0]), np.int32) for l in lens_all]
@@ -462,18 +470,40 @@ def main():
 
         def pass1():
             g1.reset()
+            blocks = 0
             for c in range(n_chunks):
-                g1.push_device(ids1, resident, lens1[c], fin1[c], col_offset=c * CHUNK)
+                blocks += g1.push_device(ids1, resident, lens1[c], fin1[c], col_offset=c * CHUNK).n_encoder_blocks
+            return blocks
 
         pass1()
+        # one pass with CUDA-event pairs around EVERY kernel launch (no sampling): launches and time per kernel
+        g1.profile_begin("all", max_launches=600000, stride=1)
+        n_blocks1 = pass1()
+        torch.cuda.synchronize()
+        raw1 = g1.profile_end("all")
+        cnt1 = raw1.pop("_counters")
+        Dm, Fm, Le = g1.cfg.d_model, g1.cfg.ffn, g1.cfg.enc_layers
+        enc_flops = {"enc_ffn1": 2.0 * 41 * n_blocks1 * Le * Fm * Dm, "enc_ffn2": 2.0 * 41 * n_blocks1 * Le * Fm * Dm,
+                     "enc_qkv": 2.0 * 41 * n_blocks1 * Le * 3 * Dm * Dm, "enc_o": 2.0 * 41 * n_blocks1 * Le * Dm * Dm}
         extra_roof = []
-        for kname in ("ctc_prefix", "dec_cross_attn", "dec_self_attn", "enc_ffn1", "enc_ffn2"):
-            tag = g1.profile_begin(kname)
-            pass1()
-            torch.cuda.synchronize()
-            r_ = g1.profile_end(tag)
-            if r_["launches"] > 0:                     # e.g. enc_ffn1 does not exist as a kernel when the FFN is fused
-                extra_roof.append(r_)
+        for kname in ("ctc_prefix", "dec_cross_attn", "dec_self_attn", "enc_ffn1", "enc_ffn2", "enc_qkv", "dec_ffn1"):
+            if kname in raw1 and raw1[kname][0] > 0:   # e.g. enc_ffn1 does not exist as a kernel when the FFN is fused
+                extra_roof.append(g1.roofline_of(kname, raw1[kname][0], raw1[kname][1], cnt1, enc_flops.get(kname)))
+        # synchronous per-chunk latency (what BASELINE's metric puts beside the CPU's per-call latency): strict mode
+        # (every push fully decodes its blocks like the reference), host buffers in, results of EVERY chunk read back
+        g1.set_option("lazy_threshold", 0)
+        g1.reset()
+        lat1 = []
+        for c in range(n_chunks):
+            t1 = time.perf_counter()
+            g1.push_batch(ids1, host_chunks[c], lens1[c], fin1[c])
+            fin_c = bool(fin1[c][0])
+            g1.results_all(fin_c, fin_c)
+            lat1.append(1000.0 * (time.perf_counter() - t1))
+        sync_latency = {"p50_chunk_ms": float(statistics.median(lat1)), "p95_chunk_ms": float(np.percentile(lat1, 95)),
+                        "max_chunk_ms": float(max(lat1)), "streams_per_call": S,
+                        "what": "wall time of one synchronous call for all streams of the GPU: pinned host chunk in, every "
+                                "block decoded (strict mode), beams of all streams read back"}
         g1.close()
         del g1
         torch.cuda.empty_cache()
@@ -551,12 +581,14 @@ def main():
                                     "float32": "float32 (engine default fp32 GEMM)",
                                     "bfloat16": "bfloat16: bf16 tcgen05 GEMMs / attention, bf16 KV caches"}[args.dtype],
                            "shards_per_gpu": G, "cuda_graphs": args.graph,
+                           "encoder_sm_partition": groups_enc_sms,
                            "decode_scheduling": ("strict: every push drains its decode blocks" if lazy == 0 else
                                                  f"deferred: a push stops iterating below {lazy} active streams; final calls drain"),
                            "decode_steps_per_pass": timed_stats["steps"] // max(1, args.steps),
                            "encoder_blocks_per_pass": timed_stats["blocks"] // max(1, args.steps)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": timed_stats["launches"],
-                "roofline": roof, "parity": parity, "roofline_single_group": extra_roof, "cpu_baseline": cpu_base,
+                "roofline": roof, "parity": parity, "sync_latency": sync_latency, "roofline_single_group": extra_roof,
+                "cpu_baseline": cpu_base,
                 "fp32_mode": fp32_mode,
                 "kernel_breakdown_sampled": breakdown}
         print(json.dumps(line))

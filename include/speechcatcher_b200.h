@@ -122,6 +122,9 @@ int sc_engine_buffer(void* handle, const char* name, void** ptr, size_t* n_elem)
  * fuller search iterations.  0 (default) = strict: every push fully decodes its blocks like the reference.
  * "overlap" = 0/1 (default 1): in deferred mode run a push's frontend/encoder on a second CUDA stream while the
  * caller's stream keeps iterating the search for blocks queued by earlier pushes.
+ * "encoder_sms" = n (default 0 = off): run the frontend + encoder part of every push in a green context that owns ~n SMs
+ * (CUDA partition granularity: 8), leaving the other SMs to the search chain; counter "encoder_sms" tells what was
+ * provisioned (0 when the driver refused and the plain stream is used).
  * "mma_attention" = 0/1/2: CUDA-core or tensor-core attention in the bf16 mode (1: beam <= 16; 2: also beam 17..32 with
  * the hypotheses tiled over two m16 tiles -- not yet run on a device).  "pdl" = 0/1: programmatic dependent
  * launch of the decode-step kernel chain (process-wide).  "fuse_layernorm" = 0/1: experimental LN-in-epilogue GEMMs.

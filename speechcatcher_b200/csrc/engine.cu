@@ -3,6 +3,7 @@
 //
 // Replaces (batched, on device): speechcatcher/speech2text_streaming.py:402-464 (__call__),
 //   speechcatcher/beam_search/beam_search.py:507-653 (process_block) and everything below them.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -106,6 +107,7 @@ struct Engine {
   int launches = 0;
   bool attn_f32_rows = true;        // fp32 modes: warp-per-head decoder attention (kernels_attn_f32.cu) instead of the
                                     // first CTA-per-(stream, head) kernels (SCB_ATTN=cta / option "attn_f32_rows")
+  bool enc_attn_x3 = true;          // precise mode: encoder block attention on tensor cores (split fp16, kernels_attn_x3.cu)
   bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
   bool mma_enc = false;             // bf16 mode: tensor-core encoder block attention
   // bf16 mode, experimental: fuse every LayerNorm into the epilogue of the GEMM producing its input (BN = 256 tiles).
@@ -131,6 +133,11 @@ struct Engine {
   // iterating the search for blocks queued by earlier pushes (they touch disjoint rows of the append-only buffers)
   bool overlap = true;
   cudaStream_t st_enc = nullptr;
+  // optional SM partition of the encoder stream (option "encoder_sms" / SCB_ENC_SMS): the frontend + encoder kernels of
+  // a push run inside a green context that owns only that many SMs, so the remaining SMs are always free for the
+  // search chain's small dependent kernels (otherwise each of them first waits for a wave of encoder GEMM CTAs to drain)
+  CUgreenCtx enc_gctx = nullptr;
+  int enc_sms = 0;                   // SMs of the partition actually provisioned (0 = no partition)
   cudaEvent_t ev_in = nullptr, ev_wave = nullptr, ev_enc = nullptr;
   bool enc_pending = false;
   std::vector<int> pending_bound;   // host upper bound of queued blocks per stream
@@ -165,6 +172,39 @@ struct Engine {
 
   explicit Engine(const ScConfig& c) : cfg(c), cap(make_caps(c)), planner(c.n_streams), pending_bound(c.n_streams, 0), last_plan(c.n_streams) {}
 };
+
+// ---------------------------------------------------------------- encoder stream (optionally SM-partitioned)
+// (Re)creates e.st_enc.  want_sms > 0: a stream of a green context holding ~want_sms SMs (CUDA rounds to its partition
+// granularity, 8 SMs on sm_90+); any failure falls back to a plain lowest-priority stream of the primary context.
+static void make_encoder_stream(Engine& e, int want_sms) {
+  if (e.st_enc) { cudaStreamSynchronize(e.st_enc); cudaStreamDestroy(e.st_enc); e.st_enc = nullptr; }
+  if (e.enc_gctx) { cuGreenCtxDestroy(e.enc_gctx); e.enc_gctx = nullptr; }
+  e.enc_sms = 0;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (want_sms > 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    CUdevice cudev;
+    CUdevResource all, part, rest;
+    unsigned int n_groups = 1;
+    CUdevResourceDesc desc = nullptr;
+    CUstream cs = nullptr;
+    bool ok = cuDeviceGet(&cudev, dev) == CUDA_SUCCESS &&
+              cuDeviceGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+              (unsigned)want_sms < all.sm.smCount &&
+              cuDevSmResourceSplitByCount(&part, &n_groups, &all, &rest, 0, (unsigned)want_sms) == CUDA_SUCCESS && n_groups == 1 &&
+              cuDevResourceGenerateDesc(&desc, &part, 1) == CUDA_SUCCESS &&
+              cuGreenCtxCreate(&e.enc_gctx, desc, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+              cuGreenCtxStreamCreate(&cs, e.enc_gctx, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS;
+    if (ok) { e.st_enc = (cudaStream_t)cs; e.enc_sms = (int)part.sm.smCount; return; }
+    if (e.enc_gctx) { cuGreenCtxDestroy(e.enc_gctx); e.enc_gctx = nullptr; }
+    cudaGetLastError();
+  }
+  // lowest priority, so that the search chain (small dependent kernels on the caller's stream, which callers create
+  // with a higher priority) is never queued behind a wave of encoder GEMM CTAs
+  cudaStreamCreateWithPriority(&e.st_enc, cudaStreamNonBlocking, lo);
+}
 
 // ---------------------------------------------------------------- workspace carving
 struct Carver {
@@ -385,7 +425,8 @@ static int run_encoder_layers_x3(Engine& e, int n_blk, cudaStream_t st) {
     PE(T_ENC_LN, launch_layernorm_split(e.X, D, w.ln1w, w.ln1b, nrm.base, nrm.plane, D, rows, D, nullptr, st));
     if (e.prof_tag == T_ENC_QKV) e.prof_flops += 2.0 * n_blk * 41 * 3.0 * D * D;
     PE(T_ENC_QKV, x3_linear(e, nrm, D, w.qkvw, w.qkvb, nullptr, e.QKV, 3 * D, nullptr, rows, 3 * D, 0, nullptr, st));
-    PE(T_ENC_ATTN, launch_enc_attention(e.QKV, nullptr, nullptr, e.d_blk, n_blk, c.enc_heads, D, st, split_out(att, D)));
+    if (e.enc_attn_x3) PE(T_ENC_ATTN, launch_enc_attention_x3(e.QKV, nullptr, e.d_blk, n_blk, c.enc_heads, D, split_out(att, D), st));
+    else PE(T_ENC_ATTN, launch_enc_attention(e.QKV, nullptr, nullptr, e.d_blk, n_blk, c.enc_heads, D, st, split_out(att, D)));
     PE(T_ENC_O, x3_linear(e, att, D, w.ow, w.ob, e.X, e.X, D, nullptr, rows, D, 0, nullptr, st));
     PE(T_ENC_LN, launch_layernorm_split(e.X, D, w.ln2w, w.ln2b, nrm.base, nrm.plane, D, rows, D, nullptr, st));
     // algorithmic FLOPs of the roofline: 41 useful rows per block; 42 are executed
@@ -713,11 +754,8 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
   cudaEventCreateWithFlags(&e->ev[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev[1], cudaEventDisableTiming);
   {
-    // frontend + encoder stream: lowest priority, so that the search chain (small dependent kernels on the caller's
-    // stream, which callers create with a higher priority) is never queued behind a wave of encoder GEMM CTAs
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    cudaStreamCreateWithPriority(&e->st_enc, cudaStreamNonBlocking, lo);
+    const char* es = getenv("SCB_ENC_SMS");
+    make_encoder_stream(*e, es ? atoi(es) : 0);
   }
   cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_wave, cudaEventDisableTiming);
@@ -730,6 +768,7 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     e->mma_attn = cfg->precision == 1 && cfg->beam <= mma_beam && !(a && strcmp(a, "simt") == 0);
     e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
     e->attn_f32_rows = !(a && strcmp(a, "cta") == 0);
+    e->enc_attn_x3 = !(a && (strcmp(a, "rows") == 0 || strcmp(a, "cta") == 0));
     const char* lp = getenv("SCB_LN_PROLOGUE");
     // measured slower than a separate LayerNorm kernel (every N-tile CTA re-normalises its 128 rows): opt-in only
     e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && lp && strcmp(lp, "1") == 0;
@@ -763,6 +802,7 @@ int sc_engine_destroy(void* handle) {
   if (e->h_flag) cudaFreeHost(e->h_flag);
   cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
   if (e->st_enc) { cudaStreamSynchronize(e->st_enc); cudaStreamDestroy(e->st_enc); }
+  if (e->enc_gctx) cuGreenCtxDestroy(e->enc_gctx);
   if (e->ev_in) { cudaEventDestroy(e->ev_in); cudaEventDestroy(e->ev_wave); cudaEventDestroy(e->ev_enc); }
   delete e;
   return SC_OK;
@@ -1305,6 +1345,7 @@ int sc_engine_counter(void* handle, const char* name, int64_t* value) {
   if (strcmp(name, "graphs_replayed") == 0) { *value = e->graphs_replayed; return SC_OK; }
   if (strcmp(name, "trace_steps") == 0) { *value = e->trace_used; return SC_OK; }
   if (strcmp(name, "graph_failed") == 0) { *value = e->graph_failed ? 1 : 0; return SC_OK; }
+  if (strcmp(name, "encoder_sms") == 0) { *value = e->enc_sms; return SC_OK; }
   set_last_error("unknown counter %s", name);
   return SC_ERR_ARG;
 }
@@ -1314,6 +1355,12 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (!e || !name) { set_last_error("set_option: null argument"); return SC_ERR_ARG; }
   if (strcmp(name, "lazy_threshold") == 0) { e->lazy_threshold = value < 0 ? 0 : value; return SC_OK; }
   if (strcmp(name, "overlap") == 0) { e->overlap = value != 0; return SC_OK; }
+  if (strcmp(name, "encoder_sms") == 0) {
+    if (e->enc_pending) { cudaEventSynchronize(e->ev_enc); e->enc_pending = false; }
+    drop_graphs(*e);
+    make_encoder_stream(*e, value);
+    return SC_OK;
+  }
   drop_graphs(*e);     // everything below changes which kernels a step launches: captured graphs are stale
   if (strcmp(name, "graph_decode") == 0) { e->graph_decode = value != 0; return SC_OK; }
   if (strcmp(name, "graph_encoder") == 0) { e->graph_encoder = value != 0; return SC_OK; }

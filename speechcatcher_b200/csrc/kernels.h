@@ -126,6 +126,9 @@ int launch_enc_attention(const float* qkv, float* out, __nv_bfloat16* out16, con
                          int n_head, int d_model, cudaStream_t st, SplitOut so = SplitOut());
 int launch_enc_attention_mma(const __nv_bfloat16* qkv16, float* out, __nv_bfloat16* out16, const BlockDesc* blk, int n_blk,
                              int n_head, int d_model, cudaStream_t st);
+// precise mode: block attention on tensor cores with split-fp16 operands (kernels_attn_x3.cu); fp32 QKV in
+int launch_enc_attention_x3(const float* qkv, float* out, const BlockDesc* blk, int n_blk, int n_head, int d_model,
+                            SplitOut so, cudaStream_t st);
 int launch_ctx_handover(float* X, float* enc_ctx, int layer, int n_layers, const BlockDesc* blk, int n_blk,
                         int D, const float* ln_w, const float* ln_b, __nv_bfloat16* nrm16, cudaStream_t st);
 int launch_stitch_norm(const float* X, const BlockDesc* blk, int n_blk, const float* w, const float* b,

@@ -324,6 +324,166 @@ __global__ void __launch_bounds__(128) dec_attn_x3_kernel(SearchBuffers sb, __ha
   }
 }
 
+
+// ---------------------------------------------------------------- encoder block attention, same arithmetic
+// One CTA (3 warps) per (block, head): the 42 block rows padded to 48 = three m16 query tiles, one per warp; Q, K, V of
+// the head are read as fp32 from the fused QKV rows, split once into fp16 hi / lo planes in shared memory, and both
+// products run as three HMMAs each.  Mask as in the CUDA-core kernels: rows 1..41 attend keys 0..40 (short path:
+// rows / keys < n_rows, no mask); rows outside the query range get 0.  (structure: enc_attn_mma_kernel of the bf16 mode)
+template <int DK>
+__global__ void __launch_bounds__(96) enc_attn_x3_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                         const BlockDesc* __restrict__ blk, int D, SplitOut so) {
+  const BlockDesc b = blk[blockIdx.x];
+  const int head = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int RS = DK + 8, CPR = DK / 8, KSTEPS = DK / 16, NDT = DK / 8, ROWS = 48;
+  __shared__ __align__(16) __half sm_all[6 * ROWS * RS];      // Q hi, Q lo, K hi, K lo, V hi, V lo
+  __half* Qh = sm_all;
+  __half* Ql = Qh + ROWS * RS;
+  __half* Kh = Ql + ROWS * RS;
+  __half* Kl = Kh + ROWS * RS;
+  __half* Vh = Kl + ROWS * RS;
+  __half* Vl = Vh + ROWS * RS;
+  const float* base = qkv + (size_t)blockIdx.x * kSlots * 3 * D + head * DK;
+  for (int idx = tid; idx < 3 * ROWS * CPR; idx += 96) {
+    const int which = idx / (ROWS * CPR), rem = idx % (ROWS * CPR), r = rem / CPR, ch = rem % CPR;
+    uint4 uh = make_uint4(0, 0, 0, 0), ul = uh;
+    if (r < kSlots) {
+      const float4* src = reinterpret_cast<const float4*>(base + (size_t)r * 3 * D + which * D + ch * 8);
+      const float4 a = src[0], c = src[1];
+      const float x[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      x3_split8(x, uh, ul);
+    }
+    __half* dh = sm_all + (size_t)(2 * which) * ROWS * RS + r * RS + ch * 8;
+    *reinterpret_cast<uint4*>(dh) = uh;
+    *reinterpret_cast<uint4*>(dh + ROWS * RS) = ul;
+  }
+  __syncthreads();
+  const int q_lo = b.short_path ? 0 : 1, q_hi = b.short_path ? b.n_rows : kSlots;
+  const int k_hi = b.short_path ? b.n_rows : kBlock + 1;
+  uint32_t qah[KSTEPS][4], qal[KSTEPS][4];
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const int off = (16 * warp + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 16 * ks + 8 * (lane >> 4);
+    xldsm_x4(qah[ks], Qh + off);
+    xldsm_x4(qal[ks], Ql + off);
+  }
+  float sacc[6][4];
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt) {
+    float smn[4] = {0.f, 0.f, 0.f, 0.f}, scr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k2 = 0; k2 < KSTEPS / 2; ++k2) {
+      uint32_t bh[4], bl[4];
+      const int off = (8 * nt + (lane & 7)) * RS + 32 * k2 + 8 * (lane >> 3);
+      xldsm_x4(bh, Kh + off);
+      xldsm_x4(bl, Kl + off);
+      mma_f16(smn, qah[2 * k2], bh);
+      mma_f16(smn, qah[2 * k2 + 1], bh + 2);
+      mma_f16(scr, qah[2 * k2], bl);
+      mma_f16(scr, qah[2 * k2 + 1], bl + 2);
+      mma_f16(scr, qal[2 * k2], bh);
+      mma_f16(scr, qal[2 * k2 + 1], bh + 2);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sacc[nt][e] = fmaf(scr[e], X3_INV_SCALE, smn[e]);
+  }
+  const float sqrt_dk = sqrtf((float)DK);
+  const int r0 = 16 * warp + (lane >> 2), r1 = r0 + 8, qd = lane & 3;
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int key = 8 * nt + 2 * qd + (e & 1);
+      const int row = (e & 2) ? r1 : r0;
+      const bool vis = row >= q_lo && row < q_hi && key < k_hi;
+      const float v = vis ? sacc[nt][e] / sqrt_dk : -INFINITY;
+      sacc[nt][e] = v;
+      mx[e >> 1] = fmaxf(mx[e >> 1], v);
+    }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+  }
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float m = mx[e >> 1];
+      const float p = (m == -INFINITY) ? 0.f : expf(sacc[nt][e] - m);
+      sacc[nt][e] = p;
+      sum[e >> 1] += p;
+    }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 2);
+  }
+  uint32_t pah[3][4], pal[3][4];
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt) {
+    const float p0 = sum[0] > 0.f ? sacc[nt][0] / sum[0] : 0.f, p1 = sum[0] > 0.f ? sacc[nt][1] / sum[0] : 0.f;
+    const float p2 = sum[1] > 0.f ? sacc[nt][2] / sum[1] : 0.f, p3 = sum[1] > 0.f ? sacc[nt][3] / sum[1] : 0.f;
+    split_pair(p0, p1, pah[nt >> 1][(nt & 1) * 2 + 0], pal[nt >> 1][(nt & 1) * 2 + 0]);
+    split_pair(p2, p3, pah[nt >> 1][(nt & 1) * 2 + 1], pal[nt >> 1][(nt & 1) * 2 + 1]);
+  }
+#pragma unroll
+  for (int n2 = 0; n2 < NDT / 2; ++n2) {
+    float om[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, oc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      uint32_t bh[4], bl[4];
+      const int off = (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 16 * n2 + 8 * (lane >> 4);
+      xldsm_x4_trans(bh, Vh + off);
+      xldsm_x4_trans(bl, Vl + off);
+      mma_f16(om[0], pah[kk], bh);
+      mma_f16(om[1], pah[kk], bh + 2);
+      mma_f16(oc[0], pah[kk], bl);
+      mma_f16(oc[1], pah[kk], bl + 2);
+      mma_f16(oc[0], pal[kk], bh);
+      mma_f16(oc[1], pal[kk], bh + 2);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = head * DK + 8 * (2 * n2 + j) + 2 * qd;
+      const float o0 = fmaf(oc[j][0], X3_INV_SCALE, om[j][0]), o1 = fmaf(oc[j][1], X3_INV_SCALE, om[j][1]);
+      const float o2 = fmaf(oc[j][2], X3_INV_SCALE, om[j][2]), o3 = fmaf(oc[j][3], X3_INV_SCALE, om[j][3]);
+      if (r0 < kSlots) {
+        const size_t row = (size_t)blockIdx.x * kSlots + r0;
+        if (so.base) {
+          uint32_t h2, l2;
+          split_pair(o0, o1, h2, l2);
+          *reinterpret_cast<uint32_t*>(so.base + row * so.ld + col) = h2;
+          *reinterpret_cast<uint32_t*>(so.base + so.plane + row * so.ld + col) = l2;
+        } else { out[row * D + col] = o0; out[row * D + col + 1] = o1; }
+      }
+      if (r1 < kSlots) {
+        const size_t row = (size_t)blockIdx.x * kSlots + r1;
+        if (so.base) {
+          uint32_t h2, l2;
+          split_pair(o2, o3, h2, l2);
+          *reinterpret_cast<uint32_t*>(so.base + row * so.ld + col) = h2;
+          *reinterpret_cast<uint32_t*>(so.base + so.plane + row * so.ld + col) = l2;
+        } else { out[row * D + col] = o2; out[row * D + col + 1] = o3; }
+      }
+    }
+  }
+}
+
+int launch_enc_attention_x3(const float* qkv, float* out, const BlockDesc* blk, int n_blk, int n_head, int d_model,
+                            SplitOut so, cudaStream_t st) {
+  if (n_blk <= 0) return 0;
+  dim3 grid(n_blk, n_head);
+  const int dk = d_model / n_head;
+  if (dk == 32) enc_attn_x3_kernel<32><<<grid, 96, 0, st>>>(qkv, out, blk, d_model, so);
+  else if (dk == 64) enc_attn_x3_kernel<64><<<grid, 96, 0, st>>>(qkv, out, blk, d_model, so);
+  else { set_last_error("enc_attn_x3: unsupported head dim %d", dk); return -1; }
+  SCB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int DK, int MODE>
 static int launch_x3_t(const SearchBuffers& sb, __half* kv_layer, const float* q, int ldq, float* out, SplitOut so,
                        cudaStream_t st) {

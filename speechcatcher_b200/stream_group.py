@@ -341,24 +341,44 @@ class StreamGroup:
             out["_counters"] = [int(x) for x in cnt]
             return out
         t = self.PROF_TAGS[kernel]
-        peaks_path = Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"
+        return self.roofline_of(kernel, int(n[t]), float(ms[t]), [int(x) for x in cnt], fl.value)
+
+    def roofline_of(self, kernel: str, launches: int, ms: float, cnt, flops: float = None) -> dict:
+        """Roofline object of one kernel from its launches / CUDA-event time and the device counters of the same pass:
+        algorithmic bytes (or FLOPs) / time against the measured peak in MEASURED_PEAKS.json (else the profiling
+        recipe's fallback).  `traffic` = DRAM bytes per launch of that kernel from the committed ncu capture
+        (profiles/r2_ncu_traffic.json), null when none exists."""
+        import json
+        root = Path(__file__).resolve().parent.parent
         peaks, src = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}, "fallback"
-        if peaks_path.exists():
-            peaks, src = json.load(open(peaks_path)), "measured"
+        if (root / "MEASURED_PEAKS.json").exists():
+            peaks, src = json.load(open(root / "MEASURED_PEAKS.json")), "measured"
         D, F = self.cfg.d_model, self.cfg.ffn
-        sec = max(ms[t], 1e-9) / 1e3
+        sec = max(ms, 1e-9) / 1e3
         hbm = {"ctc_prefix": cnt[0], "dec_cross_attn": cnt[2], "dec_self_attn": cnt[3]}
         if kernel in hbm:
             ach = hbm[kernel] / sec / 1e9
             peak = float(peaks["hbm_gbs"])
             out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
         else:
-            flops = fl.value if kernel in ("enc_ffn1", "enc_ffn2", "conv2") else 2.0 * cnt[1] * F * D
+            if flops is None or flops <= 0:
+                flops = 2.0 * cnt[1] * F * D              # decoder FFN GEMMs: active rows x 2 F D
             ach = flops / sec / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
             out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
-        out.update({"kernel": kernel, "launches": int(n[t]), "kernel_ms_total": float(ms[t]), "peak_source": src,
-                    "traffic": None, "search_iterations": int(cnt[4]), "active_rows_total": int(cnt[1])})
+            if self.precision == 2:
+                out["note"] = ("algorithmic FLOPs (2 M N K, 41 useful rows per encoder block) of a split-fp16 GEMM: the "
+                               "tensor cores execute 3 UMMAs per product, so frac <= 1/3 by construction; "
+                               "frac_of_3x_bound = 3 * frac")
+                out["frac_of_3x_bound"] = 3.0 * ach / peak
+        traffic = None
+        tpath = root / "profiles" / "r2_ncu_traffic.json"
+        if tpath.exists():
+            rec = json.load(open(tpath)).get(self.dtype, {}).get(kernel)
+            if rec:
+                traffic = rec
+        out.update({"kernel": kernel, "launches": launches, "kernel_ms_total": ms, "peak_source": src,
+                    "traffic": traffic, "search_iterations": int(cnt[4]), "active_rows_total": int(cnt[1])})
         return out
 
     def _read_all(self):

@@ -87,12 +87,14 @@ def test_ctc_prefix_step_matches_oracle(T, L, n_hyp, seed):
     want_psi = torch.gather(log_psi, 1, ids)
     real = want_psi > -1e9
     assert torch.isfinite(psi).all()
-    assert (psi.cpu()[real] - want_psi[real]).abs().max().item() <= 1e-3
+    if real.any():                                                             # T <= L: every prefix score is logzero
+        assert (psi.cpu()[real] - want_psi[real]).abs().max().item() <= 1e-3
     assert ((psi.cpu()[~real] - want_psi[~real]).abs() <= 2048).all()          # logzero entries (fp32 spacing at 1e10)
     assert (psi_eos.cpu() - log_psi[:, V - 1]).abs().max().item() <= 1e-3
     # forward variables: the reference's r is (T, 2, n_hyp, K)
     want_r = r_ref.permute(2, 3, 0, 1)
     got_r = r_new.cpu()
     big = want_r < -1e9
-    assert (got_r[~big] - want_r[~big]).abs().max().item() <= 1e-3
+    if (~big).any():
+        assert (got_r[~big] - want_r[~big]).abs().max().item() <= 1e-3
     assert (got_r[big] < -1e9).all()
