@@ -24,7 +24,10 @@
 
 namespace scb {
 
-constexpr int X_KPW = 32;          // keys per warp per step
+// Keys per warp per step.  ncu (profiles/r2_ncu_dec_attn_x3.txt) showed the first version (32 keys, 85 KB of stages per
+// CTA, two CTAs = 8 warps per SM) at 12 % warp occupancy and ~1.2 TB/s: latency-bound.  16 keys per warp-step halve
+// the stages (44 KB per CTA, five CTAs = 20 warps per SM).
+constexpr int X_KPW = 16;
 constexpr int X_STEP = 4 * X_KPW;  // keys per CTA step
 constexpr int X_NT = X_KPW / 8;    // score n-tiles per warp
 constexpr int X_KK = X_KPW / 16;   // k-steps of the P*V product per warp
@@ -59,7 +62,7 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
 }
 
 template <int DK, int MODE>
-__global__ void __launch_bounds__(128) dec_attn_x3_kernel(SearchBuffers sb, __half* kv_layer, const float* __restrict__ q,
+__global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, __half* kv_layer, const float* __restrict__ q,
                                                           int ldq, float* __restrict__ out, SplitOut so) {
   pdl_sync();
   if ((int)blockIdx.x >= *sb.n_active) return;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(128) dec_attn_x3_kernel(SearchBuffers sb, __ha
       // ---- mask: only where one can exist
       if (MODE == 0) {
         const signed char* ob = ownw + buf * X_KPW;
-        if (!__all_sync(0xffffffffu, ob[lane] == -1)) {       // step touches the divergent tail (or padding)
+        if (!__all_sync(0xffffffffu, ob[lane & (X_KPW - 1)] == -1)) {       // step touches the divergent tail (or padding)
 #pragma unroll
           for (int nt = 0; nt < X_NT; ++nt) {
             const int o0 = ob[8 * nt + 2 * qd], o1 = ob[8 * nt + 2 * qd + 1];
