@@ -226,10 +226,12 @@ int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, co
 /* The engine's own form of that GEMM: the activation arrives as split fp16 planes written by its producer
  * (x_planes_f16: hi plane [x_rows][k], lo plane x_plane_elems further, x_rows = row capacity >= m) and is staged by
  * TMA like the weights; the result is written as fp32 rows (y, may be NULL) and / or as split planes for the next
- * Linear (y_planes_f16, may be NULL). */
+ * Linear (y_planes_f16, may be NULL).  kernel: 0 = the engine's choice (the persistent A-resident kernel of
+ * kernels_gemm_x3p.cu for dense products with n % 128 == 0, k = 256 or k % 128 == 0 >= 384, one output form and an
+ * in-place residual; the per-tile kernel otherwise), 1 = per-tile kernel, 2 = persistent kernel (error if ineligible). */
 int sc_linear_x3_planes(const void* x_planes_f16, int64_t x_plane_elems, int32_t x_rows, const void* w_planes_f16,
                         const float* bias, const float* residual, float* y, void* y_planes_f16, int64_t y_plane_elems,
-                        int32_t m, int32_t n, int32_t k, int32_t relu, void* stream);
+                        int32_t m, int32_t n, int32_t k, int32_t relu, int32_t kernel, void* stream);
 /* LayerNorm eps=1e-12 whose result is written as split fp16 planes (hi [rows][d], lo y_plane_elems further) */
 int sc_layernorm_split(const float* x, const float* w, const float* b, void* y_planes_f16, int64_t y_plane_elems,
                        int32_t rows, int32_t d, void* stream);

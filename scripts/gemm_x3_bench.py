@@ -59,7 +59,11 @@ def main():
         t = {}
         t["x3_planes"] = timeit(lambda: _lib.check(lib.sc_linear_x3_planes(
             a2.data_ptr(), M * K, M, w2.data_ptr(), bias.data_ptr(), r, None if out_planes else y.data_ptr(),
-            yp.data_ptr() if out_planes else None, M * N, M, N, K, relu, None)), flush)
+            yp.data_ptr() if out_planes else None, M * N, M, N, K, relu, 1, None)), flush)
+        if N % 128 == 0 and K % 128 == 0 and K >= 256:
+            t["x3_persistent"] = timeit(lambda: _lib.check(lib.sc_linear_x3_planes(
+                a2.data_ptr(), M * K, M, w2.data_ptr(), bias.data_ptr(), r, None if out_planes else y.data_ptr(),
+                yp.data_ptr() if out_planes else None, M * N, M, N, K, relu, 2, None)), flush)
         t["x3_convert"] = timeit(lambda: _lib.check(lib.sc_linear_x3(a.data_ptr(), w2.data_ptr(), bias.data_ptr(), r, y.data_ptr(),
                                                                      M, N, K, relu, None)), flush)
         t["f32_simt"] = timeit(lambda: _lib.check(lib.sc_linear_f32(a.data_ptr(), w.data_ptr(), bias.data_ptr(), r, y.data_ptr(),

@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libscb200.so"
-SOURCES = ["kernels_gemm.cu", "kernels_gemm_tc.cu", "kernels_gemm_x3.cu", "kernels_frontend.cu", "kernels_encoder.cu",
+SOURCES = ["kernels_gemm.cu", "kernels_gemm_tc.cu", "kernels_gemm_x3.cu", "kernels_gemm_x3p.cu", "kernels_frontend.cu", "kernels_encoder.cu",
            "kernels_search.cu", "kernels_attn_mma.cu", "kernels_attn_f32.cu", "kernels_attn_x3.cu", "kernels_ffn_fused.cu", "segmenter.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", str(OUT), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-lcudart", "-lcuda"]
+           "-lcudart"]          # the driver API is resolved at run time (cudaGetDriverEntryPoint): no libcuda dependency
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -176,13 +176,45 @@ struct Engine {
 // ---------------------------------------------------------------- encoder stream (optionally SM-partitioned)
 // (Re)creates e.st_enc.  want_sms > 0: a stream of a green context holding ~want_sms SMs (CUDA rounds to its partition
 // granularity, 8 SMs on sm_90+); any failure falls back to a plain lowest-priority stream of the primary context.
+// The driver API is reached through cudaGetDriverEntryPoint (no link-time dependency on libcuda: the library must load
+// on a host without a driver, where only the symbol table and the host-side planner are exercised).
+struct DriverApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  bool ok = false;
+};
+static const DriverApi& driver_api() {
+  static const DriverApi api = [] {
+    DriverApi a;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      *fn = nullptr;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn != nullptr;
+    };
+    a.ok = get("cuDeviceGet", (void**)&a.DeviceGet) && get("cuDeviceGetDevResource", (void**)&a.DeviceGetDevResource) &&
+           get("cuDevSmResourceSplitByCount", (void**)&a.DevSmResourceSplitByCount) &&
+           get("cuDevResourceGenerateDesc", (void**)&a.DevResourceGenerateDesc) && get("cuGreenCtxCreate", (void**)&a.GreenCtxCreate) &&
+           get("cuGreenCtxDestroy", (void**)&a.GreenCtxDestroy) && get("cuGreenCtxStreamCreate", (void**)&a.GreenCtxStreamCreate);
+    if (!a.ok) cudaGetLastError();
+    return a;
+  }();
+  return api;
+}
+static void destroy_green_ctx(Engine& e);
+
 static void make_encoder_stream(Engine& e, int want_sms) {
   if (e.st_enc) { cudaStreamSynchronize(e.st_enc); cudaStreamDestroy(e.st_enc); e.st_enc = nullptr; }
-  if (e.enc_gctx) { cuGreenCtxDestroy(e.enc_gctx); e.enc_gctx = nullptr; }
+  destroy_green_ctx(e);
   e.enc_sms = 0;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  if (want_sms > 0) {
+  const DriverApi& d = driver_api();
+  if (want_sms > 0 && d.ok) {
     int dev = 0;
     cudaGetDevice(&dev);
     CUdevice cudev;
@@ -190,20 +222,25 @@ static void make_encoder_stream(Engine& e, int want_sms) {
     unsigned int n_groups = 1;
     CUdevResourceDesc desc = nullptr;
     CUstream cs = nullptr;
-    bool ok = cuDeviceGet(&cudev, dev) == CUDA_SUCCESS &&
-              cuDeviceGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+    bool ok = d.DeviceGet(&cudev, dev) == CUDA_SUCCESS &&
+              d.DeviceGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
               (unsigned)want_sms < all.sm.smCount &&
-              cuDevSmResourceSplitByCount(&part, &n_groups, &all, &rest, 0, (unsigned)want_sms) == CUDA_SUCCESS && n_groups == 1 &&
-              cuDevResourceGenerateDesc(&desc, &part, 1) == CUDA_SUCCESS &&
-              cuGreenCtxCreate(&e.enc_gctx, desc, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
-              cuGreenCtxStreamCreate(&cs, e.enc_gctx, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS;
+              d.DevSmResourceSplitByCount(&part, &n_groups, &all, &rest, 0, (unsigned)want_sms) == CUDA_SUCCESS && n_groups == 1 &&
+              d.DevResourceGenerateDesc(&desc, &part, 1) == CUDA_SUCCESS &&
+              d.GreenCtxCreate(&e.enc_gctx, desc, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+              d.GreenCtxStreamCreate(&cs, e.enc_gctx, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS;
     if (ok) { e.st_enc = (cudaStream_t)cs; e.enc_sms = (int)part.sm.smCount; return; }
-    if (e.enc_gctx) { cuGreenCtxDestroy(e.enc_gctx); e.enc_gctx = nullptr; }
+    destroy_green_ctx(e);
     cudaGetLastError();
   }
   // lowest priority, so that the search chain (small dependent kernels on the caller's stream, which callers create
   // with a higher priority) is never queued behind a wave of encoder GEMM CTAs
   cudaStreamCreateWithPriority(&e.st_enc, cudaStreamNonBlocking, lo);
+}
+
+static void destroy_green_ctx(Engine& e) {
+  if (e.enc_gctx && driver_api().GreenCtxDestroy) driver_api().GreenCtxDestroy(e.enc_gctx);
+  e.enc_gctx = nullptr;
 }
 
 // ---------------------------------------------------------------- workspace carving
@@ -802,7 +839,7 @@ int sc_engine_destroy(void* handle) {
   if (e->h_flag) cudaFreeHost(e->h_flag);
   cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
   if (e->st_enc) { cudaStreamSynchronize(e->st_enc); cudaStreamDestroy(e->st_enc); }
-  if (e->enc_gctx) cuGreenCtxDestroy(e->enc_gctx);
+  destroy_green_ctx(*e);
   if (e->ev_in) { cudaEventDestroy(e->ev_in); cudaEventDestroy(e->ev_wave); cudaEventDestroy(e->ev_enc); }
   delete e;
   return SC_OK;
@@ -1499,12 +1536,12 @@ int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, co
 }
 int sc_linear_x3_planes(const void* x_planes_f16, int64_t x_plane_elems, int32_t x_rows, const void* w_planes_f16,
                         const float* bias, const float* residual, float* y, void* y_planes_f16, int64_t y_plane_elems,
-                        int32_t m, int32_t n, int32_t k, int32_t relu, void* stream) {
+                        int32_t m, int32_t n, int32_t k, int32_t relu, int32_t kernel, void* stream) {
   GemmArgs g;
   g.lda = k; g.bias = bias; g.R = residual; g.ldr = n; g.C = y; g.ldc = n; g.M = m; g.N = n; g.K = k; g.relu = relu;
   X3Extra x;
   x.A2 = x_planes_f16; x.a2_plane = (size_t)x_plane_elems; x.a2_rows = x_rows;
-  x.C2 = y_planes_f16; x.c2_plane = (size_t)y_plane_elems; x.ldc2 = n;
+  x.C2 = y_planes_f16; x.c2_plane = (size_t)y_plane_elems; x.ldc2 = n; x.kernel = kernel;
   return launch_gemm_x3(g, x, w_planes_f16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }
 int sc_layernorm_split(const float* x, const float* w, const float* b, void* y_planes_f16, int64_t y_plane_elems,

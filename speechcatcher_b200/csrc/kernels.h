@@ -79,8 +79,12 @@ struct X3Extra {
   void* C2 = nullptr;         // output as planes, dense rows of leading dimension ldc2; lo plane at + c2_plane elements
   size_t c2_plane = 0;
   int ldc2 = 0;
+  int kernel = 0;             // 0: pick (persistent kernel where eligible), 1: per-tile kernel, 2: persistent kernel or error
 };
 int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);
+// persistent A-resident / chunk-accumulating form for encoder-sized products (kernels_gemm_x3p.cu)
+bool gemm_x3p_eligible(const GemmArgs& g, const X3Extra& x);
+int launch_gemm_x3p(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);
 // LayerNorm (eps 1e-12, same arithmetic as launch_layernorm) whose result is written as split fp16 planes
 int launch_layernorm_split(const float* x, int ldx, const float* w, const float* b, void* y2, size_t plane, int ldy,
                            int rows, int D, const int* n_rows_dev, cudaStream_t st);

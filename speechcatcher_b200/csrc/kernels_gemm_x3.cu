@@ -326,6 +326,10 @@ static int x3_launch(const CUtensorMap& mh, const CUtensorMap& ml, const CUtenso
 // Output: fp32 rows (g.C, optional when x.C2 is given) and / or split planes (x.C2).
 int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
+  // encoder-sized products with plane operands: the persistent kernel (SCB_X3_PERSIST_MIN_M rows and up; 0 disables)
+  static const int persist_min_m = [] { const char* v = getenv("SCB_X3_PERSIST_MIN_M"); return v ? atoi(v) : 1; }();
+  if (x.kernel == 2 || (x.kernel == 0 && persist_min_m > 0 && g.M >= persist_min_m && gemm_x3p_eligible(g, x)))
+    return launch_gemm_x3p(g, x, W2, st);
   const bool a_tma = x.A2 != nullptr;
   if (g.K % TC_BK != 0 || g.N % 64 != 0 || (g.a_seg_off && g.seg_len % TC_BK != 0) || (!g.a_row_off && g.lda % 8 != 0) || !W2 ||
       (!g.C && !x.C2) || (a_tma && (g.a_row_off || x.a2_rows < g.M)) || (x.C2 && x.ldc2 % 8 != 0)) {

@@ -116,7 +116,7 @@ def test_linear_x3_planes_in_equals_converter_path(M, N, K, relu, res):
     yp = torch.zeros(2, M, N, dtype=torch.float16, device="cuda")
     _lib.check(lib.sc_linear_x3_planes(a2.data_ptr(), cap * K, cap, w2.data_ptr(), bias.data_ptr(),
                                        y1.data_ptr() if res else None, y1.data_ptr(), yp.data_ptr(), M * N,
-                                       M, N, K, relu, None), "x3_planes")
+                                       M, N, K, relu, 1, None), "x3_planes")
     torch.cuda.synchronize()
     assert torch.equal(y0, y1)
     # the plane output represents the fp32 result to 2^-22 relative (2^-36 absolute for tiny values)
@@ -126,9 +126,68 @@ def test_linear_x3_planes_in_equals_converter_path(M, N, K, relu, res):
     if not res:
         yp2 = torch.zeros_like(yp)
         _lib.check(lib.sc_linear_x3_planes(a2.data_ptr(), cap * K, cap, w2.data_ptr(), bias.data_ptr(), None, None,
-                                           yp2.data_ptr(), M * N, M, N, K, relu, None), "x3_planes_only")
+                                           yp2.data_ptr(), M * N, M, N, K, relu, 1, None), "x3_planes_only")
         torch.cuda.synchronize()
         assert torch.equal(yp, yp2)
+
+
+PERSISTENT_SHAPES = [
+    # (M, N, K, relu, out) -- out: "f32" store, "res" in-place residual (fp32 add at the L2), "planes"
+    (10752, 768, 256, 0, "f32"),      # encoder QKV: 84 x 6 tiles, A-resident, several tiles per CTA
+    (8610, 2048, 256, 1, "planes"),   # encoder FFN1 (ragged M: 205 blocks x 42 rows), planes out
+    (8610, 256, 256, 0, "res"),       # encoder O-projection, residual in place
+    (8610, 256, 2048, 0, "res"),      # encoder FFN2: streamed A, 16 accumulator chunks
+    (126, 768, 256, 0, "f32"),        # three blocks of one stream: one row tile
+    (42, 2048, 256, 1, "planes"),
+    (42, 256, 2048, 0, "res"),
+    (1000, 128, 384, 0, "f32"),       # odd chunk count (3), one column tile
+    (40000, 256, 256, 0, "res"),      # more row tiles than SMs: a CTA walks several row tiles (A refill behind the MMAs)
+    (20000, 512, 256, 1, "planes"),
+]
+
+
+@pytest.mark.parametrize("M,N,K,relu,out", PERSISTENT_SHAPES)
+def test_linear_x3_persistent_kernel(M, N, K, relu, out):
+    """The persistent kernel (kernels_gemm_x3p.cu) against an fp64 reference and against the per-tile kernel on the same
+    plane operands: same products, a different (chunked, round-to-nearest) accumulation order, so the two agree to
+    fp32 rounding level, and both carry fp32-class error."""
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * K)
+    a = torch.randn(M, K, generator=g, device="cuda") * 1.3 + 0.05
+    w = torch.randn(N, K, generator=g, device="cuda") / K ** 0.5
+    bias = torch.randn(N, generator=g, device="cuda")
+    r = torch.randn(M, N, generator=g, device="cuda")
+    w2, a2 = _planes(w), _act_planes(a)
+    a_rec = a2[0].double() + a2[1].double() / 2048.0          # what the planes represent
+    w_rec = w2.view(2, N, K)[0].double() + w2.view(2, N, K)[1].double() / 2048.0
+    want = a_rec @ w_rec.t() + bias.double()
+    if relu:
+        want = want.relu()
+    if out == "res":
+        want = want + r.double()
+    outs = []
+    for kernel in (1, 2):
+        y = r.clone() if out == "res" else torch.full((M, N), float("nan"), device="cuda")
+        yp = torch.full((2, M + 3, N), 7.0, dtype=torch.float16, device="cuda")     # 3 guard rows behind the last one
+        planes = out == "planes"
+        _lib.check(lib.sc_linear_x3_planes(a2.data_ptr(), M * K, M, w2.data_ptr(), bias.data_ptr(),
+                                           y.data_ptr() if out == "res" else None, None if planes else y.data_ptr(),
+                                           yp.data_ptr() if planes else None, (M + 3) * N, M, N, K, relu, kernel, None),
+                   f"x3_planes kernel {kernel}")
+        torch.cuda.synchronize()
+        if planes:
+            assert (yp[:, M:] == 7.0).all()                   # rows beyond M are clipped
+            y = yp[0, :M].float() + yp[1, :M].float() / 2048.0
+        assert torch.isfinite(y).all()
+        outs.append(y.double())
+    scale = want.abs().max().item()
+    err_tile, err_pers = (outs[0] - want).abs(), (outs[1] - want).abs()
+    tol_planes = 2.0 ** -21 * scale if out == "planes" else 0.0
+    assert err_pers.max().item() <= 2.0 * err_tile.max().item() + 2.0 ** -22 * scale + tol_planes, \
+        f"persistent max err {err_pers.max().item():.3e} vs per-tile {err_tile.max().item():.3e} (scale {scale:.2f})"
+    assert err_pers.pow(2).mean().sqrt().item() <= 2.0 * err_tile.pow(2).mean().sqrt().item() + 2.0 ** -24 * scale
+    assert (outs[0] - outs[1]).abs().max().item() <= 2.0 ** -20 * scale
 
 
 def test_layernorm_split_planes():
