@@ -232,6 +232,14 @@ int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, co
 int sc_linear_x3_planes(const void* x_planes_f16, int64_t x_plane_elems, int32_t x_rows, const void* w_planes_f16,
                         const float* bias, const float* residual, float* y, void* y_planes_f16, int64_t y_plane_elems,
                         int32_t m, int32_t n, int32_t k, int32_t relu, int32_t kernel, void* stream);
+/* y = act(LayerNorm(x) W^T + bias) for fp32 rows x [m][256]: the LayerNorm (eps 1e-12, the arithmetic of
+ * sc_layernorm_split) is computed in the prologue of the persistent GEMM, which builds its resident A tile from it;
+ * output as fp32 rows (y) or as split planes (y_planes_f16), exactly one of them.  n_rows_dev (may be NULL): device-side
+ * count of active rows <= m (the decode step's compact row list); only row tiles holding active rows are computed.
+ * Replaces normalization.py:23 + torch.nn.functional.linear (decoder_layer.py:80-132, contextual_block_encoder_layer.py). */
+int sc_linear_x3_ln(const float* x, const float* ln_w, const float* ln_b, const void* w_planes_f16, const float* bias,
+                    float* y, void* y_planes_f16, int64_t y_plane_elems, int32_t m, int32_t n, int32_t relu,
+                    const int32_t* n_rows_dev, void* stream);
 /* LayerNorm eps=1e-12 whose result is written as split fp16 planes (hi [rows][d], lo y_plane_elems further) */
 int sc_layernorm_split(const float* x, const float* w, const float* b, void* y_planes_f16, int64_t y_plane_elems,
                        int32_t rows, int32_t d, void* stream);

@@ -75,6 +75,7 @@ SYMBOLS = {
     "sc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "sc_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "sc_linear_x3": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "sc_linear_x3_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i32, _i32, _i32, _vp, _vp]),
     "sc_linear_x3_planes": (C.c_int, [_vp, C.c_int64, _i32, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "sc_layernorm_split": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _i32, _i32, _vp]),
     "sc_linear_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

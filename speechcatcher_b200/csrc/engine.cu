@@ -108,6 +108,11 @@ struct Engine {
   bool attn_f32_rows = true;        // fp32 modes: warp-per-head decoder attention (kernels_attn_f32.cu) instead of the
                                     // first CTA-per-(stream, head) kernels (SCB_ATTN=cta / option "attn_f32_rows")
   bool enc_attn_x3 = true;          // precise mode: encoder block attention on tensor cores (split fp16, kernels_attn_x3.cu)
+  // precise mode: LayerNorm computed in the prologue of the persistent GEMM that consumes it (kernels_gemm_x3p.cu) instead
+  // of a LayerNorm kernel writing planes (SCB_X3_LN_FUSED = "0" / "enc" / "dec" / "1"; options "x3_ln_fused_encoder/_decoder")
+  bool x3_ln_fused_enc = false;     // measured slower: the eight epilogue warps build A, so every row-tile switch stalls the MMAs
+  bool x3_ln_fused_dec = false;     // measured slower too: the 225 KB CTAs keep the next kernels of the chain from becoming resident
+  int x3_dec_persist = 0;           // decode-step projections with plane operands on the persistent kernel: 1 = K 256, 2 = also FFN2
   bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
   bool mma_enc = false;             // bf16 mode: tensor-core encoder block attention
   // bf16 mode, experimental: fuse every LayerNorm into the epilogue of the GEMM producing its input (BN = 256 tiles).
@@ -376,8 +381,16 @@ static int x3_linear(Engine& e, const Planes& a, int K, const float* W, const fl
   X3Extra x;
   x.A2 = a.base; x.a2_plane = a.plane; x.a2_rows = a.rows;
   if (c2) { x.C2 = c2->base; x.c2_plane = c2->plane; x.ldc2 = N; }
+  if (n_rows_dev && !c_row_off && ((e.x3_dec_persist >= 1 && K == 256) || e.x3_dec_persist >= 2) && gemm_x3p_eligible(g, x)) x.kernel = 2;
   return gemm_fp32(e, g, st, x);
 }
+
+// C and / or C2 = act(LayerNorm(X) * W^T + bias), K = d_model = 256: one launch of the persistent kernel with the
+// LayerNorm computed in its prologue (x3_ln_fused), else LayerNorm kernel -> planes `scratch` -> GEMM (two launches,
+// the LayerNorm under ln_tag).  persistent: which GEMM kernel the two-launch form uses with a device-side row count.
+static int x3_ln_linear(Engine& e, int ln_tag, int gemm_tag, bool dec, const float* X, int ldx, const float* ln_w,
+                        const float* ln_b, const Planes& scratch, const float* W, const float* bias, float* C, int ldc,
+                        const Planes* c2, int M, int N, int relu, const int* n_rows_dev, cudaStream_t st);
 
 static int linear(Engine& e, const Lin& l, cudaStream_t st) {
   e.launches++;
@@ -453,25 +466,44 @@ static int ffn_auto_splits(const Engine& e, int rows, int F) {
   return s;
 }
 
+static int x3_ln_linear(Engine& e, int ln_tag, int gemm_tag, bool dec, const float* X, int ldx, const float* ln_w,
+                        const float* ln_b, const Planes& scratch, const float* W, const float* bias, float* C, int ldc,
+                        const Planes* c2, int M, int N, int relu, const int* n_rows_dev, cudaStream_t st) {
+  const int K = e.cfg.d_model;
+  const bool fuse = dec ? e.x3_ln_fused_dec : e.x3_ln_fused_enc;
+  if (fuse && K == 256 && N % 128 == 0) {
+    e.launches++;
+    GemmArgs g;
+    g.lda = K; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc; g.ldr = ldc; g.M = M; g.N = N; g.K = K; g.relu = relu; g.n_rows_dev = n_rows_dev;
+    X3Extra x;
+    x.lnX = X; x.ldx = ldx; x.ln_w = ln_w; x.ln_b = ln_b;
+    if (c2) { x.C2 = c2->base; x.c2_plane = c2->plane; x.ldc2 = N; }
+    PROFX(gemm_tag, dec, gemm_fp32(e, g, st, x));
+    return 0;
+  }
+  e.launches++;
+  PROFX(ln_tag, dec, launch_layernorm_split(X, ldx, ln_w, ln_b, scratch.base, scratch.plane, K, M, K, n_rows_dev, st));
+  PROFX(gemm_tag, dec, x3_linear(e, scratch, K, W, bias, nullptr, C, ldc, c2, M, N, relu, n_rows_dev, st));
+  return 0;
+}
+
 // ---------------------------------------------------------------- encoder layers over all blocks of the push
 static int run_encoder_layers_x3(Engine& e, int n_blk, cudaStream_t st) {
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, rows = n_blk * kSlots, cap = e.cap.rows_max;
   const Planes nrm{e.Nrm, (size_t)cap * D, cap}, att{e.Att, (size_t)cap * D, cap}, ff{e.FF, (size_t)cap * F, cap};
   for (int l = 0; l < c.enc_layers; ++l) {
     const EncLayerW& w = e.enc[l];
-    PE(T_ENC_LN, launch_layernorm_split(e.X, D, w.ln1w, w.ln1b, nrm.base, nrm.plane, D, rows, D, nullptr, st));
     if (e.prof_tag == T_ENC_QKV) e.prof_flops += 2.0 * n_blk * 41 * 3.0 * D * D;
-    PE(T_ENC_QKV, x3_linear(e, nrm, D, w.qkvw, w.qkvb, nullptr, e.QKV, 3 * D, nullptr, rows, 3 * D, 0, nullptr, st));
+    TRY(x3_ln_linear(e, T_ENC_LN, T_ENC_QKV, false, e.X, D, w.ln1w, w.ln1b, nrm, w.qkvw, w.qkvb, e.QKV, 3 * D, nullptr, rows, 3 * D, 0, nullptr, st));
     if (e.enc_attn_x3) PE(T_ENC_ATTN, launch_enc_attention_x3(e.QKV, nullptr, e.d_blk, n_blk, c.enc_heads, D, split_out(att, D), st));
     else PE(T_ENC_ATTN, launch_enc_attention(e.QKV, nullptr, nullptr, e.d_blk, n_blk, c.enc_heads, D, st, split_out(att, D)));
     PE(T_ENC_O, x3_linear(e, att, D, w.ow, w.ob, e.X, e.X, D, nullptr, rows, D, 0, nullptr, st));
-    PE(T_ENC_LN, launch_layernorm_split(e.X, D, w.ln2w, w.ln2b, nrm.base, nrm.plane, D, rows, D, nullptr, st));
     // algorithmic FLOPs of the roofline: 41 useful rows per block; 42 are executed
     if (e.prof_tag == T_ENC_FFN1 || e.prof_tag == T_ENC_FFN2) e.prof_flops += 2.0 * n_blk * 41 * (double)F * D;
-    PE(T_ENC_FFN1, x3_linear(e, nrm, D, w.f1w, w.f1b, nullptr, nullptr, F, &ff, rows, F, 1, nullptr, st));
+    TRY(x3_ln_linear(e, T_ENC_LN, T_ENC_FFN1, false, e.X, D, w.ln2w, w.ln2b, nrm, w.f1w, w.f1b, nullptr, F, &ff, rows, F, 1, nullptr, st));
     PE(T_ENC_FFN2, x3_linear(e, ff, F, w.f2w, w.f2b, e.X, e.X, D, nullptr, rows, D, 0, nullptr, st));
     PE(T_ENC_HANDOVER, launch_ctx_handover(e.X, e.enc_ctx, l, c.enc_layers, e.d_blk, n_blk, D, nullptr, nullptr, nullptr, st));
-    e.launches += 4;
+    e.launches += 2;
   }
   return 0;
 }
@@ -565,26 +597,21 @@ static int run_decode_step_x3(Engine& e, cudaStream_t st) {
   if (e.attn_f32_rows || sb.kv_split) { PD(T_DEC_EMBED, launch_build_self_keys(sb, st)); e.launches++; }
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerW& w = e.dec[l];
-    PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln1w, w.ln1b, dn.base, dn.plane, D, R, D, nr, st));
-    PD(T_DEC_QKV, x3_linear(e, dn, D, w.sqkvw, w.sqkvb, nullptr, e.dqkv, 3 * D, nullptr, R, 3 * D, 0, nr, st));
+    TRY(x3_ln_linear(e, T_DEC_LN, T_DEC_QKV, true, e.dx, D, w.ln1w, w.ln1b, dn, w.sqkvw, w.sqkvb, e.dqkv, 3 * D, nullptr, R, 3 * D, 0, nr, st));
     if (sb.kv_split) PD(T_DEC_SELF_ATTN, launch_dec_attention_x3(sb, 0, l, e.dqkv, 3 * D, nullptr, split_out(da, D), st));
     else if (e.attn_f32_rows) PD(T_DEC_SELF_ATTN, launch_dec_attention_f32(sb, 0, l, e.dqkv, 3 * D, nullptr, split_out(da, D), st));
     else PD(T_DEC_SELF_ATTN, launch_dec_self_attention(sb, l, e.dqkv, 3 * D, nullptr, nullptr, st, split_out(da, D)));
     PD(T_DEC_SO, x3_linear(e, da, D, w.sow, w.sob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
-    PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln2w, w.ln2b, dn.base, dn.plane, D, R, D, nr, st));
-    PD(T_DEC_CQ, x3_linear(e, dn, D, w.cqw, w.cqb, nullptr, e.dq, D, nullptr, R, D, 0, nr, st));
+    TRY(x3_ln_linear(e, T_DEC_LN, T_DEC_CQ, true, e.dx, D, w.ln2w, w.ln2b, dn, w.cqw, w.cqb, e.dq, D, nullptr, R, D, 0, nr, st));
     if (sb.kv_split) PD(T_DEC_CROSS_ATTN, launch_dec_attention_x3(sb, 1, l, e.dq, D, nullptr, split_out(da, D), st));
     else if (e.attn_f32_rows) PD(T_DEC_CROSS_ATTN, launch_dec_attention_f32(sb, 1, l, e.dq, D, nullptr, split_out(da, D), st));
     else PD(T_DEC_CROSS_ATTN, launch_dec_cross_attention(sb, l, e.dq, D, nullptr, nullptr, st, split_out(da, D)));
     PD(T_DEC_CO, x3_linear(e, da, D, w.cow, w.cob, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
-    PD(T_DEC_LN, launch_layernorm_split(e.dx, D, w.ln3w, w.ln3b, dn.base, dn.plane, D, R, D, nr, st));
-    PD(T_DEC_FFN1, x3_linear(e, dn, D, w.f1w, w.f1b, nullptr, nullptr, F, &df, R, F, 1, nr, st));
+    TRY(x3_ln_linear(e, T_DEC_LN, T_DEC_FFN1, true, e.dx, D, w.ln3w, w.ln3b, dn, w.f1w, w.f1b, nullptr, F, &df, R, F, 1, nr, st));
     PD(T_DEC_FFN2, x3_linear(e, df, F, w.f2w, w.f2b, e.dx, e.dx, D, nullptr, R, D, 0, nr, st));
-    e.launches += 5;
+    e.launches += 2;
   }
-  PD(T_DEC_LN, launch_layernorm_split(e.dx, D, e.daw, e.dab, dn.base, dn.plane, D, R, D, nr, st));
-  PD(T_DEC_OUT, x3_linear(e, dn, D, e.doutw, e.doutb, nullptr, e.dlogp, V, nullptr, R, V, 0, nr, st));
-  e.launches += 2;
+  TRY(x3_ln_linear(e, T_DEC_LN, T_DEC_OUT, true, e.dx, D, e.daw, e.dab, dn, e.doutw, e.doutb, e.dlogp, V, nullptr, R, V, 0, nr, st));
   return decode_tail(e, st);
 }
 
@@ -806,6 +833,11 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     e->mma_enc = cfg->precision == 1 && !(a && strcmp(a, "simt") == 0);
     e->attn_f32_rows = !(a && strcmp(a, "cta") == 0);
     e->enc_attn_x3 = !(a && (strcmp(a, "rows") == 0 || strcmp(a, "cta") == 0));
+    if (const char* xd = getenv("SCB_X3_DEC_PERSIST")) e->x3_dec_persist = atoi(xd);
+    if (const char* xl = getenv("SCB_X3_LN_FUSED")) {
+      e->x3_ln_fused_enc = strcmp(xl, "1") == 0 || strcmp(xl, "enc") == 0;
+      e->x3_ln_fused_dec = strcmp(xl, "1") == 0 || strcmp(xl, "dec") == 0;
+    }
     const char* lp = getenv("SCB_LN_PROLOGUE");
     // measured slower than a separate LayerNorm kernel (every N-tile CTA re-normalises its 128 rows): opt-in only
     e->ln_prologue = cfg->precision == 1 && cfg->d_model == 256 && lp && strcmp(lp, "1") == 0;
@@ -1402,6 +1434,8 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (strcmp(name, "graph_decode") == 0) { e->graph_decode = value != 0; return SC_OK; }
   if (strcmp(name, "graph_encoder") == 0) { e->graph_encoder = value != 0; return SC_OK; }
   if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
+  if (strcmp(name, "x3_ln_fused_encoder") == 0) { e->x3_ln_fused_enc = value != 0; drop_graphs(*e); return SC_OK; }
+  if (strcmp(name, "x3_ln_fused_decoder") == 0) { e->x3_ln_fused_dec = value != 0; drop_graphs(*e); return SC_OK; }
   if (strcmp(name, "ln_prologue") == 0) { e->ln_prologue = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
   if (strcmp(name, "ln_prologue_decoder") == 0) { e->ln_prologue_dec = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }
   if (strcmp(name, "fused_ffn") == 0) {
@@ -1543,6 +1577,16 @@ int sc_linear_x3_planes(const void* x_planes_f16, int64_t x_plane_elems, int32_t
   x.A2 = x_planes_f16; x.a2_plane = (size_t)x_plane_elems; x.a2_rows = x_rows;
   x.C2 = y_planes_f16; x.c2_plane = (size_t)y_plane_elems; x.ldc2 = n; x.kernel = kernel;
   return launch_gemm_x3(g, x, w_planes_f16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
+}
+int sc_linear_x3_ln(const float* x, const float* ln_w, const float* ln_b, const void* w_planes_f16, const float* bias, float* y,
+                    void* y_planes_f16, int64_t y_plane_elems, int32_t m, int32_t n, int32_t relu, const int32_t* n_rows_dev,
+                    void* stream) {
+  GemmArgs g;
+  g.lda = 256; g.bias = bias; g.C = y; g.ldc = n; g.ldr = n; g.M = m; g.N = n; g.K = 256; g.relu = relu; g.n_rows_dev = n_rows_dev;
+  X3Extra ex;
+  ex.lnX = x; ex.ldx = 256; ex.ln_w = ln_w; ex.ln_b = ln_b;
+  ex.C2 = y_planes_f16; ex.c2_plane = (size_t)y_plane_elems; ex.ldc2 = n;
+  return launch_gemm_x3(g, ex, w_planes_f16, (cudaStream_t)stream) ? SC_ERR_CUDA : SC_OK;
 }
 int sc_layernorm_split(const float* x, const float* w, const float* b, void* y_planes_f16, int64_t y_plane_elems,
                        int32_t rows, int32_t d, void* stream) {

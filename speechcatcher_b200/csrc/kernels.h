@@ -79,6 +79,10 @@ struct X3Extra {
   void* C2 = nullptr;         // output as planes, dense rows of leading dimension ldc2; lo plane at + c2_plane elements
   size_t c2_plane = 0;
   int ldc2 = 0;
+  const float* lnX = nullptr; // persistent kernel only: A = LayerNorm(lnX rows [M][256], leading dimension ldx), eps 1e-12,
+  int ldx = 0;                // computed inside the GEMM (replaces launch_layernorm_split + the plane round trip)
+  const float* ln_w = nullptr;
+  const float* ln_b = nullptr;
   int kernel = 0;             // 0: pick (persistent kernel where eligible), 1: per-tile kernel, 2: persistent kernel or error
 };
 int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);

@@ -62,8 +62,8 @@ constexpr int x3_tmem_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 
 
 // A_TMA: the A operand already exists as split planes in global memory (written by the producing kernel) and is staged
 // by TMA like the weights; otherwise the converter warps build the planes from fp32 rows (gathered A: conv2).
-template <int BN, int STAGES, int J, bool A_TMA>
-__global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_constant__ CUtensorMap map_wh,
+template <int BN, int STAGES, int J, bool A_TMA, int MINB = 1>
+__global__ void __launch_bounds__(X3_THREADS, MINB) gemm_x3_kernel(const __grid_constant__ CUtensorMap map_wh,
                                                                 const __grid_constant__ CUtensorMap map_wl,
                                                                 const __grid_constant__ CUtensorMap map_ah,
                                                                 const __grid_constant__ CUtensorMap map_al,
@@ -302,20 +302,20 @@ __global__ void __launch_bounds__(X3_THREADS, 1) gemm_x3_kernel(const __grid_con
   }
 }
 
-template <int BN, int STAGES, int J, bool A_TMA>
+template <int BN, int STAGES, int J, bool A_TMA, int MINB = 1>
 static int x3_launch(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mah, const CUtensorMap& mal,
                      const X3Params& p, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (2 * TC_BM * TC_BK * 2 + 2 * BN * TC_BK * 2) + 256;
   static PerDeviceMark attr_mk;
   if (!attr_mk.cur()) {
-    if (cudaFuncSetAttribute(gemm_x3_kernel<BN, STAGES, J, A_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_x3_kernel<BN, STAGES, J, A_TMA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(gemm_x3, smem=%zu) failed", smem);
       return -1;
     }
     attr_mk.cur() = 1;
   }
   dim3 grid(p.N / BN, cdiv(p.M, TC_BM));
-  launch_k(gemm_x3_kernel<BN, STAGES, J, A_TMA>, grid, dim3(X3_THREADS), smem, st, mh, ml, mah, mal, p);
+  launch_k(gemm_x3_kernel<BN, STAGES, J, A_TMA, MINB>, grid, dim3(X3_THREADS), smem, st, mh, ml, mah, mal, p);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -328,7 +328,8 @@ int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStre
   if (g.M <= 0 || g.N <= 0) return 0;
   // encoder-sized products with plane operands: the persistent kernel (SCB_X3_PERSIST_MIN_M rows and up; 0 disables)
   static const int persist_min_m = [] { const char* v = getenv("SCB_X3_PERSIST_MIN_M"); return v ? atoi(v) : 1; }();
-  if (x.kernel == 2 || (x.kernel == 0 && persist_min_m > 0 && g.M >= persist_min_m && gemm_x3p_eligible(g, x)))
+  if (x.kernel == 2 || x.lnX ||
+      (x.kernel == 0 && !g.n_rows_dev && persist_min_m > 0 && g.M >= persist_min_m && gemm_x3p_eligible(g, x)))
     return launch_gemm_x3p(g, x, W2, st);
   const bool a_tma = x.A2 != nullptr;
   if (g.K % TC_BK != 0 || g.N % 64 != 0 || (g.a_seg_off && g.seg_len % TC_BK != 0) || (!g.a_row_off && g.lda % 8 != 0) || !W2 ||
@@ -355,6 +356,12 @@ int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStre
   X3Params p{g.A, g.lda, g.a_row_off, g.a_seg_off, g.seg_len, g.bias, g.R, g.ldr, g.C, g.ldc, g.c_row_off,
              g.M, g.N, g.K, g.relu, g.n_rows_dev, (__half*)x.C2, x.c2_plane, x.ldc2};
   // stage = 32 KB (A hi + lo) + 2 * BN * 128 B (W hi + lo): BN 128 -> 64 KB (3 stages), BN 64 -> 48 KB (4 stages)
+  // decode-step projections (device-side row count, K = 256: four K blocks): a two-stage ring and two main accumulators
+  // (8 instructions each, like the 128-wide tiles) make the CTA small enough -- 97 KB of shared memory, 256 TMEM columns
+  // -- for two per SM, so that one CTA's epilogue overlaps the other's loads and the next kernel of the chain can
+  // become resident early (SCB_X3_DEC2=0 keeps the four-stage form)
+  static const bool dec2 = [] { const char* v = getenv("SCB_X3_DEC2"); return v && v[0] == '1'; }();
+  if (a_tma && dec2 && g.n_rows_dev && g.K == 256 && small) return x3_launch<64, 2, 2, true, 2>(mh, ml, mah, mal, p, st);
   if (a_tma) {
     if (long_k) return x3_launch<64, 4, 7, true>(mh, ml, mah, mal, p, st);
     return small ? x3_launch<64, 4, 4, true>(mh, ml, mah, mal, p, st) : x3_launch<128, 3, 2, true>(mh, ml, mah, mal, p, st);

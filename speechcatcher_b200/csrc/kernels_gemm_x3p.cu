@@ -39,6 +39,9 @@ struct XpParams {
   const float* bias;
   int M, N, K, relu, out_mode;                   // out_mode 0: fp32 store, 1: fp32 add into C, 2: split planes
   int m_tiles, n_tiles;
+  const int* n_rows_dev;                         // optional device-side row count (decode step: active rows)
+  const float* X; int ldx; const float* ln_w; const float* ln_b;   // LN form: A = LayerNorm(X rows), built in the kernel
+  int dbg;                                       // SCB_XP_DBG (timing experiments only): 1 = no output, 2 = no TMEM drain
 };
 
 __device__ __forceinline__ void xp_umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
@@ -62,7 +65,7 @@ __device__ __forceinline__ void xp_ld32_nowait(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void xp_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-template <bool A_RES>
+template <bool A_RES, bool LN>
 __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_constant__ CUtensorMap map_wh,
                                                                  const __grid_constant__ CUtensorMap map_wl,
                                                                  const __grid_constant__ CUtensorMap map_ah,
@@ -88,15 +91,13 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.K / TC_BK, n_chunks = nkb / 2;
-  const long T = (long)p.m_tiles * p.n_tiles;
-  const int t0 = (int)((long)blockIdx.x * T / gridDim.x), t1 = (int)((long)(blockIdx.x + 1) * T / gridDim.x);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
-    for (int i = 0; i < 4; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&a_full[i], LN ? 8 : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -110,13 +111,17 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   pdl_sync();                                // the producing kernel's writes (A planes, C for the residual add) are visible
+  int M = p.M;
+  if (p.n_rows_dev) M = min(M, *p.n_rows_dev);
+  const long T = (long)((M + TC_BM - 1) / TC_BM) * p.n_tiles;          // row tiles that hold active rows only
+  const int t0 = (int)((long)blockIdx.x * T / gridDim.x), t1 = (int)((long)(blockIdx.x + 1) * T / gridDim.x);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int it = 0, a_gen = 0, prev_m = -1;
     for (int t = t0; t < t1; ++t) {
       const int m = t / p.n_tiles, n = t - m * p.n_tiles;
-      if (A_RES && m != prev_m) {            // new row tile: refill the resident A, K block by K block as they are released
+      if (A_RES && !LN && m != prev_m) {     // new row tile: refill the resident A, K block by K block as they are released
         for (int kb = 0; kb < 4; ++kb) {
           mbar_wait(&a_empty[kb], (a_gen & 1) ^ 1);
           if (elect_one_sync()) {
@@ -198,9 +203,84 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
     unsigned char* stg = s_out + (warp - 2) * 4096;             // [32 rows][128 B], 128-byte swizzle (1 KB aligned)
     unsigned char* my_row = stg + lane * 128;
     const int sw = lane & 7;
-    int chunk = 0;
+    int chunk = 0, a_gen = 0, prev_m = -1;
     for (int t = t0; t < t1; ++t) {
       const int m = t / p.n_tiles, n = t - m * p.n_tiles;
+      if (LN && m != prev_m) {
+        // ---- LayerNorm prologue: these eight warps build the resident A tile of a new row tile from the fp32 rows
+        // (one warp per row; statistics exactly as layernorm_kernel, kernels_gemm.cu: element lane + 32 i per lane, the
+        // row re-read in 16-byte chunk order for the normalise / split / swizzled store).  Rows beyond M are zero.
+        mbar_wait(&a_empty[3], (a_gen & 1) ^ 1);                // the MMAs of the previous row tile have read all of A
+        const int kb = lane >> 3, ch = lane & 7;                // columns 8 lane .. 8 lane + 7 = chunk ch of K block kb
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ln_w) + 2 * lane), w1 = __ldg(reinterpret_cast<const float4*>(p.ln_w) + 2 * lane + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 2 * lane), b1 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 2 * lane + 1);
+        // 16 rows per warp in two batches of eight: all loads of a batch are in flight together and the eight rows'
+        // shuffle reductions interleave (row by row the build is a chain of L2 and shuffle latencies, ~10 us per tile)
+#pragma unroll 1
+        for (int jb = 0; jb < 2; ++jb) {
+          const int r_first = (warp - 2) + 64 * jb;             // rows r_first + 8 j, j = 0..7
+          float v[8][8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = m * TC_BM + r_first + 8 * j;
+            const float* xr = p.X + (size_t)row * p.ldx;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] = row < M ? xr[lane + 32 * i] : 0.f;
+          }
+          float mean[8], rstd[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum += v[j][i];
+            mean[j] = sum;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mean[j] += __shfl_xor_sync(0xffffffffu, mean[j], o);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            mean[j] = mean[j] / 256.0f;
+            float qq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean[j]; qq += d * d; }
+            rstd[j] = qq;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rstd[j] += __shfl_xor_sync(0xffffffffu, rstd[j], o);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            rstd[j] = 1.0f / sqrtf(rstd[j] / 256.0f + 1e-12f);
+            const int r = r_first + 8 * j, row = m * TC_BM + r;
+            uint4 uh = make_uint4(0, 0, 0, 0), ul = uh;
+            if (row < M) {
+              const float* xr = p.X + (size_t)row * p.ldx;
+              const float4 x0 = *reinterpret_cast<const float4*>(xr + 8 * lane), x1 = *reinterpret_cast<const float4*>(xr + 8 * lane + 4);
+              const float mu = mean[j], rs = rstd[j];
+              const float o8[8] = {(x0.x - mu) * rs * w0.x + b0.x, (x0.y - mu) * rs * w0.y + b0.y,
+                                   (x0.z - mu) * rs * w0.z + b0.z, (x0.w - mu) * rs * w0.w + b0.w,
+                                   (x1.x - mu) * rs * w1.x + b1.x, (x1.y - mu) * rs * w1.y + b1.y,
+                                   (x1.z - mu) * rs * w1.z + b1.z, (x1.w - mu) * rs * w1.w + b1.w};
+              x3_split8(o8, uh, ul);
+            }
+            unsigned char* dst = smem + kb * A_KB_BYTES + r * 128 + ((ch ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = uh;
+            *reinterpret_cast<uint4*>(dst + XP_PLANE) = ul;
+          }
+        }
+        fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_full[k4])) : "memory");
+        }
+        ++a_gen; prev_m = m;
+      }
       float acc[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = 0.f;
@@ -209,6 +289,7 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
         mbar_wait(&tmem_full[as], (chunk >> 1) & 1);
         tc_fence_after();
         const uint32_t tb = lane_base + (uint32_t)(as * 256);
+        if (!(p.dbg & 2)) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint32_t vm[32], vc[32];
@@ -218,6 +299,7 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             acc[g * 32 + j] += fmaf(__uint_as_float(vc[j]), X3_INV_SCALE, __uint_as_float(vm[j]));
+        }
         }
         tc_fence_before();
         __syncwarp();
@@ -236,7 +318,7 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = fmaxf(acc[j], 0.f);
       }
-      if (row0 < p.M) {
+      if (row0 < M && !(p.dbg & 1)) {
         if (p.out_mode == 2) {
           uint4 ul[8];
           if (lane == 0) xp_store_wait_read();                 // the previous tile's copy has read the staging rows
@@ -287,30 +369,35 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
   }
 }
 
-template <bool A_RES>
+template <bool A_RES, bool LN>
 static int xp_launch(const CUtensorMap* maps, const XpParams& p, cudaStream_t st) {
   static PerDeviceMark attr_mk;
   if (!attr_mk.cur()) {
-    if (cudaFuncSetAttribute(gemm_x3p_kernel<A_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XP_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_x3p_kernel<A_RES, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XP_SMEM) != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(gemm_x3p, smem=%zu) failed", XP_SMEM);
       return -1;
     }
     attr_mk.cur() = 1;
   }
+  // SCB_XP_MAX_CTAS: leave some SMs to the concurrently running search chain (experiments)
+  static const int max_ctas = [] { const char* v = getenv("SCB_XP_MAX_CTAS"); const int n = v ? atoi(v) : 0; return n > 0 && n < kNumSMs ? n : kNumSMs; }();
   const long tiles = (long)p.m_tiles * p.n_tiles;
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  launch_k(gemm_x3p_kernel<A_RES>, dim3(grid), dim3(XP_THREADS), XP_SMEM, st, maps[0], maps[1], maps[2], maps[3], maps[4],
+  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+  launch_k(gemm_x3p_kernel<A_RES, LN>, dim3(grid), dim3(XP_THREADS), XP_SMEM, st, maps[0], maps[1], maps[2], maps[3], maps[4],
            maps[5], maps[6], p);
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
-// Shapes the persistent kernel takes: A as split planes (dense rows), dense output rows, M known on the host, N a
-// multiple of 128, K = 256 (A-resident) or a multiple of 128 from 384 up (streamed), exactly one output form, and a
-// residual only as the in-place add (R == C).
+// Shapes the persistent kernel takes: A as split planes (dense rows) or as LayerNorm(X) of fp32 rows (K = 256), dense
+// output rows, N a multiple of 128, K = 256 (A-resident) or a multiple of 128 from 384 up (streamed), exactly one
+// output form, and a residual only as the in-place add (R == C).  With a device-side row count (n_rows_dev) only the row
+// tiles holding active rows are computed; rows of the last such tile beyond the count are written too (stale or zero
+// operands -> values nobody reads), so the output buffers must hold M rows.
 bool gemm_x3p_eligible(const GemmArgs& g, const X3Extra& x) {
-  if (!x.A2 || g.a_row_off || g.a_seg_off || g.c_row_off || g.n_rows_dev) return false;
-  if (g.M <= 0 || g.N % XP_BN != 0 || g.K % 128 != 0 || g.K < 256 || g.lda % 8 != 0) return false;
+  if ((!x.A2 && !x.lnX) || g.a_row_off || g.a_seg_off || g.c_row_off) return false;
+  if (g.M <= 0 || g.N % XP_BN != 0 || g.K % 128 != 0 || g.K < 256 || (x.A2 && g.lda % 8 != 0)) return false;
+  if (x.lnX && (g.K != 256 || x.ldx % 4 != 0 || !x.ln_w || !x.ln_b)) return false;
   if ((g.C != nullptr) == (x.C2 != nullptr)) return false;
   if (g.C && g.ldc % 4 != 0) return false;
   if (x.C2 && x.ldc2 % 8 != 0) return false;
@@ -325,8 +412,11 @@ int launch_gemm_x3p(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStr
   CUtensorMap maps[7];
   if (tc_get_map(wh, g.N, g.K, g.K, XP_BN, &maps[0])) return -1;
   if (tc_get_map(wh + (size_t)g.N * g.K, g.N, g.K, g.K, XP_BN, &maps[1])) return -1;
-  if (tc_get_map(ah, g.M, g.K, g.lda, TC_BM, &maps[2])) return -1;             // rows = M: the tail tile is zero-filled
-  if (tc_get_map(ah + x.a2_plane, g.M, g.K, g.lda, TC_BM, &maps[3])) return -1;
+  if (x.lnX) { maps[2] = maps[0]; maps[3] = maps[1]; }                         // A is built in the kernel
+  else {
+    if (tc_get_map(ah, g.M, g.K, g.lda, TC_BM, &maps[2])) return -1;           // rows = M: the tail tile is zero-filled
+    if (tc_get_map(ah + x.a2_plane, g.M, g.K, g.lda, TC_BM, &maps[3])) return -1;
+  }
   if (g.C) {
     if (tc_get_map_f32(g.C, g.M, g.N, g.ldc, 32, &maps[4])) return -1;
     maps[5] = maps[4]; maps[6] = maps[4];
@@ -336,8 +426,11 @@ int launch_gemm_x3p(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStr
     if (tc_get_map(ch + x.c2_plane, g.M, g.N, x.ldc2, 32, &maps[6])) return -1;
     maps[4] = maps[5];
   }
-  XpParams p{g.bias, g.M, g.N, g.K, g.relu, g.C ? (g.R ? 1 : 0) : 2, cdiv(g.M, TC_BM), g.N / XP_BN};
-  return g.K == 256 ? xp_launch<true>(maps, p, st) : xp_launch<false>(maps, p, st);
+  static const int dbg = [] { const char* v = getenv("SCB_XP_DBG"); return v ? atoi(v) : 0; }();
+  XpParams p{g.bias, g.M, g.N, g.K, g.relu, g.C ? (g.R ? 1 : 0) : 2, cdiv(g.M, TC_BM), g.N / XP_BN, g.n_rows_dev,
+             x.lnX, x.ldx, x.ln_w, x.ln_b, dbg};
+  if (x.lnX) return xp_launch<true, true>(maps, p, st);
+  return g.K == 256 ? xp_launch<true, false>(maps, p, st) : xp_launch<false, false>(maps, p, st);
 }
 
 }  // namespace scb

@@ -190,6 +190,54 @@ def test_linear_x3_persistent_kernel(M, N, K, relu, out):
     assert (outs[0] - outs[1]).abs().max().item() <= 2.0 ** -20 * scale
 
 
+@pytest.mark.parametrize("M,N,relu,out,n_rows", [(8610, 768, 0, "f32", None), (8610, 2048, 1, "planes", None),
+                                                 (2560, 768, 0, "f32", 2480), (2560, 256, 0, "f32", 130),
+                                                 (2560, 2048, 1, "planes", 2333), (2560, 1024, 0, "f32", 1),
+                                                 (42, 768, 0, "f32", None), (40000, 256, 0, "f32", None)])
+def test_linear_x3_layernorm_prologue(M, N, relu, out, n_rows):
+    """LayerNorm in the prologue of the persistent GEMM == sc_layernorm_split followed by the persistent GEMM on the
+    planes (bit for bit: same LayerNorm arithmetic, same split, same instruction sequence); with a device-side row count
+    only rows below it are defined."""
+    from speechcatcher_b200 import _lib
+    lib = _lib.load()
+    K = 256
+    g = torch.Generator(device="cuda").manual_seed(M + N + (n_rows or 0))
+    x = torch.randn(M, K, generator=g, device="cuda") * 2.5 + 0.3
+    lw = 1.0 + 0.1 * torch.randn(K, generator=g, device="cuda")
+    lb = 0.1 * torch.randn(K, generator=g, device="cuda")
+    w = torch.randn(N, K, generator=g, device="cuda") / K ** 0.5
+    bias = torch.randn(N, generator=g, device="cuda")
+    w2 = _planes(w)
+    nr = torch.tensor([n_rows], dtype=torch.int32, device="cuda") if n_rows is not None else None
+    planes = out == "planes"
+    xp = torch.zeros(2, M, K, dtype=torch.float16, device="cuda")
+    _lib.check(lib.sc_layernorm_split(x.data_ptr(), lw.data_ptr(), lb.data_ptr(), xp.data_ptr(), M * K, M, K, None), "ln_split")
+    y0 = torch.full((M, N), float("nan"), device="cuda")
+    yp0 = torch.zeros(2, M, N, dtype=torch.float16, device="cuda")
+    _lib.check(lib.sc_linear_x3_planes(xp.data_ptr(), M * K, M, w2.data_ptr(), bias.data_ptr(), None,
+                                       None if planes else y0.data_ptr(), yp0.data_ptr() if planes else None, M * N,
+                                       M, N, K, relu, 2, None), "x3_planes persistent")
+    y1 = torch.full((M, N), float("nan"), device="cuda")
+    yp1 = torch.zeros(2, M, N, dtype=torch.float16, device="cuda")
+    _lib.check(lib.sc_linear_x3_ln(x.data_ptr(), lw.data_ptr(), lb.data_ptr(), w2.data_ptr(), bias.data_ptr(),
+                                   None if planes else y1.data_ptr(), yp1.data_ptr() if planes else None, M * N,
+                                   M, N, relu, nr.data_ptr() if nr is not None else None, None), "x3_ln")
+    torch.cuda.synchronize()
+    rows = M if n_rows is None else n_rows
+    if planes:
+        assert torch.equal(yp0[:, :rows], yp1[:, :rows])
+    else:
+        assert torch.isfinite(y1[:rows]).all()
+        assert torch.equal(y0[:rows], y1[:rows])
+    # against fp64
+    xn = torch.nn.functional.layer_norm(x.double(), (K,), lw.double(), lb.double(), eps=1e-12)
+    want = xn @ w.double().t() + bias.double()
+    if relu:
+        want = want.relu()
+    got = (yp1[0].double() + yp1[1].double() / 2048.0) if planes else y1.double()
+    assert (got[:rows] - want[:rows]).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
 def test_layernorm_split_planes():
     from speechcatcher_b200 import _lib
     lib = _lib.load()
