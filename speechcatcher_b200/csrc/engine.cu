@@ -112,6 +112,18 @@ struct Engine {
   // of a LayerNorm kernel writing planes (SCB_X3_LN_FUSED = "0" / "enc" / "dec" / "1"; options "x3_ln_fused_encoder/_decoder")
   bool x3_ln_fused_enc = false;     // measured slower: the eight epilogue warps build A, so every row-tile switch stalls the MMAs
   bool x3_ln_fused_dec = false;     // measured slower too: the 225 KB CTAs keep the next kernels of the chain from becoming resident
+  // precise mode: the row-local parts of the decode step as persistent chain kernels (kernels_chain_x3.cu): 2 launches per
+  // layer instead of 9.  Correct (the golden suite passes with it) but measured SLOWER (6 071 -> 4 787 audio-s/s): with
+  // programmatic dependent launch the separate kernels already cost only ~3-8 us each, while a chain pays a counter
+  // round trip and an exposed TMA latency per stage and its 225 KB CTAs block the SMs.  Opt-in: SCB_X3_CHAIN=1 / "x3_chain".
+  bool x3_chain = false;
+  bool chain_ready = false;
+  CUtensorMap* d_chain_maps = nullptr;      // workspace: tensor maps of the chains' operands
+  int* d_chain_ctr = nullptr;               // workspace: completion counters, one region per chain launch of a step
+  float* d_chain_part = nullptr;            // workspace: split-K partial products of FFN2 [4][Rp][D]
+  int chain_ctr_ints = 0, chain_rp = 0;
+  std::vector<ChainParams> chains;          // [0] LN1 -> QKV of layer 0; [1 + 2 l] after self-attention l; [2 + 2 l] after cross-attention l
+  std::vector<int> chain_items;
   int x3_dec_persist = 0;           // decode-step projections with plane operands on the persistent kernel: 1 = K 256, 2 = also FFN2
   bool mma_attn = false;            // bf16 mode: tensor-core (mma.sync) decoder attention
   bool mma_enc = false;             // bf16 mode: tensor-core encoder block attention
@@ -284,6 +296,14 @@ static void carve(Engine& e, Carver& cv) {
   e.dx = cv.take<float>(R * D); e.dn = cv.take<float>(R * D); e.dqkv = cv.take<float>(R * 3 * D);
   e.dq = cv.take<float>(R * D); e.dattn = cv.take<float>(R * D); e.dffn = cv.take<float>(R * F);
   e.dlogp = cv.take<float>(R * V); reg("dlogp", e.dlogp, R * V);
+  if (c.precision == 2) {
+    const size_t rt = (R + 127) / 128;
+    e.chain_rp = (int)(rt * 128);
+    e.chain_ctr_ints = (int)((1 + 2 * c.dec_layers) * 8 * rt * 4);
+    e.d_chain_maps = cv.take<CUtensorMap>(32 + 16 * (size_t)c.dec_layers);
+    e.d_chain_ctr = cv.take<int>(e.chain_ctr_ints);
+    e.d_chain_part = cv.take<float>(4 * rt * 128 * D);
+  }
   if (c.precision == 1) {
     e.Nrm16 = cv.take<__nv_bfloat16>((size_t)k.rows_max * D);
     e.Att16 = cv.take<__nv_bfloat16>((size_t)k.rows_max * D);
@@ -586,11 +606,155 @@ static int trace_step(Engine& e, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- one search iteration for all active streams
+
+// ---------------------------------------------------------------- decode-step chains (kernels_chain_x3.cu)
+// Built once per engine: every operand of the decode step lives at a fixed address (activation buffers of the
+// workspace, weight planes), so the tensor maps and the stage lists never change.
+static int build_decode_chains(Engine& e) {
+  const ScConfig& c = e.cfg;
+  const int D = c.d_model, F = c.ffn, V = c.vocab, R = e.cap.R, Ld = c.dec_layers;
+  e.chain_ready = false;
+  if (c.precision != 2 || D != 256 || F % 512 != 0 || V % 128 != 0 || !e.d_chain_maps) return 0;
+  std::vector<CUtensorMap> maps;
+  auto add_load = [&](const void* planes, size_t plane_elems, int rows, int cols, int ld) -> int {       // hi, lo: 64 x 128 boxes
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(planes);
+    CUtensorMap m0, m1;
+    if (tc_get_map(h, rows, cols, ld, 128, &m0) || tc_get_map(h + plane_elems, rows, cols, ld, 128, &m1)) return -1;
+    maps.push_back(m0); maps.push_back(m1);
+    return (int)maps.size() - 2;
+  };
+  auto add_out_planes = [&](void* planes, size_t plane_elems, int rows, int cols, int ld) -> int {       // hi, lo: 64 x 32 boxes
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(planes);
+    CUtensorMap m0, m1;
+    if (tc_get_map(h, rows, cols, ld, 32, &m0) || tc_get_map(h + plane_elems, rows, cols, ld, 32, &m1)) return -1;
+    maps.push_back(m0); maps.push_back(m1);
+    return (int)maps.size() - 2;
+  };
+  auto add_out_f32 = [&](float* ptr, int rows, int cols, int ld) -> int {
+    CUtensorMap m0;
+    if (tc_get_map_f32(ptr, rows, cols, ld, 32, &m0)) return -1;
+    maps.push_back(m0);
+    return (int)maps.size() - 1;
+  };
+  auto wplanes = [&](const float* w) -> const void* { auto it = e.x3map.find(w); return it == e.x3map.end() ? nullptr : it->second; };
+  // activations
+  const int a_dn = add_load(e.dn, (size_t)R * D, R, D, D), a_da = add_load(e.dattn, (size_t)R * D, R, D, D);
+  const int a_df = add_load(e.dffn, (size_t)R * F, R, F, F);
+  const int o_df = add_out_planes(e.dffn, (size_t)R * F, R, F, F);
+  const int o_dx = add_out_f32(e.dx, R, D, D), o_qkv = add_out_f32(e.dqkv, R, 3 * D, 3 * D), o_dq = add_out_f32(e.dq, R, D, D);
+  const int o_logp = add_out_f32(e.dlogp, R, V, V), o_part = add_out_f32(e.d_chain_part, 4 * e.chain_rp, D, D);
+  if (a_dn < 0 || a_da < 0 || a_df < 0 || o_df < 0 || o_dx < 0 || o_qkv < 0 || o_dq < 0 || o_logp < 0 || o_part < 0) return -1;
+  struct LW { int qkv, so, cq, co, f1, f2; };
+  std::vector<LW> lw(Ld);
+  for (int l = 0; l < Ld; ++l) {
+    const DecLayerW& w = e.dec[l];
+    const void *pq = wplanes(w.sqkvw), *ps = wplanes(w.sow), *pc = wplanes(w.cqw), *po = wplanes(w.cow), *p1 = wplanes(w.f1w), *p2 = wplanes(w.f2w);
+    if (!pq || !ps || !pc || !po || !p1 || !p2) return 0;
+    lw[l].qkv = add_load(pq, (size_t)3 * D * D, 3 * D, D, D); lw[l].so = add_load(ps, (size_t)D * D, D, D, D);
+    lw[l].cq = add_load(pc, (size_t)D * D, D, D, D); lw[l].co = add_load(po, (size_t)D * D, D, D, D);
+    lw[l].f1 = add_load(p1, (size_t)F * D, F, D, D); lw[l].f2 = add_load(p2, (size_t)D * F, D, F, F);
+    if (lw[l].qkv < 0 || lw[l].so < 0 || lw[l].cq < 0 || lw[l].co < 0 || lw[l].f1 < 0 || lw[l].f2 < 0) return -1;
+  }
+  const void* pout = wplanes(e.doutw);
+  if (!pout) return 0;
+  const int w_out = add_load(pout, (size_t)V * D, V, D, D);
+  if (w_out < 0) return -1;
+  if (maps.size() > 32 + 16 * (size_t)Ld) { set_last_error("decode chains: %zu tensor maps exceed the carved table", maps.size()); return -1; }
+  SCB_CUDA_CHECK(cudaMemcpy(e.d_chain_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+
+  const int RT = (R + 127) / 128, region = 8 * RT * 4;                 // counters per chain launch: 8 groups of RT * 4
+  auto gemm = [&](int map_a, int map_w, int map_o, int n_ct, int n_ks, int kb_item, int out_mode, int relu, const float* bias) {
+    ChainStage g{};
+    g.type = 0; g.n_ct = n_ct; g.n_ks = n_ks; g.kb_item = kb_item; g.map_a = map_a; g.map_w = map_w; g.map_o = map_o;
+    g.out_mode = out_mode; g.relu = relu; g.bias = bias; g.wait_base = -1; g.sig_base = -1; g.sig_div = 1 << 20; g.sig_stride = 1; g.wait_stride = 1;
+    return g;
+  };
+  auto lnorm = [&](const float* w, const float* b, int n_part, const float* pbias) {
+    ChainStage g{};
+    g.type = 1; g.ln_w = w; g.ln_b = b; g.x = e.dx; g.n_part = n_part; g.part = e.d_chain_part; g.pbias = pbias;
+    g.out_hi = reinterpret_cast<__half*>(e.dn); g.out_plane = (size_t)R * D; g.wait_base = -1; g.sig_base = -1; g.sig_div = 1 << 20;
+    g.sig_stride = 1; g.wait_stride = 1;
+    return g;
+  };
+  // stage i signals counter group i (stride 1 per row tile unless stated), stage i + 1 waits for it
+  auto link = [&](ChainStage& prod, ChainStage& cons, int group, int target_items) {
+    prod.sig_base = group * RT * 4; prod.sig_stride = 1;
+    cons.wait_base = group * RT * 4; cons.wait_stride = 1; cons.wait_ks = 0; cons.wait_target = 8 * target_items;
+  };
+  e.chains.assign(1 + 2 * Ld, ChainParams{});
+  e.chain_items.assign(1 + 2 * Ld, 0);
+  auto finish = [&](int idx, std::vector<ChainStage>& st) {
+    ChainParams& cp = e.chains[idx];
+    cp.n_stages = (int)st.size();
+    int items = 0;
+    for (size_t i = 0; i < st.size(); ++i) { cp.st[i] = st[i]; items += RT * (st[i].type == 0 ? st[i].n_ct * st[i].n_ks : 1); }
+    cp.maps = e.d_chain_maps; cp.ctr = e.d_chain_ctr + (size_t)idx * region; cp.n_rows_dev = e.sb.n_rows; cp.M = R;
+    cp.part_stride_rows = e.chain_rp;
+    e.chain_items[idx] = items;
+  };
+  {                                                                    // chain 0: LayerNorm1 -> QKV of layer 0
+    std::vector<ChainStage> st{lnorm(e.dec[0].ln1w, e.dec[0].ln1b, 0, nullptr),
+                               gemm(a_dn, lw[0].qkv, o_qkv, 3 * D / 128, 1, D / 64, 0, 0, e.dec[0].sqkvb)};
+    link(st[0], st[1], 0, 1);
+    finish(0, st);
+  }
+  for (int l = 0; l < Ld; ++l) {
+    const DecLayerW& w = e.dec[l];
+    {                                                                  // after self-attention: O (+x) -> LayerNorm2 -> cross-Q
+      std::vector<ChainStage> st{gemm(a_da, lw[l].so, o_dx, D / 128, 1, D / 64, 1, 0, w.sob), lnorm(w.ln2w, w.ln2b, 0, nullptr),
+                                 gemm(a_dn, lw[l].cq, o_dq, D / 128, 1, D / 64, 0, 0, w.cqb)};
+      link(st[0], st[1], 0, D / 128);
+      link(st[1], st[2], 1, 1);
+      finish(1 + 2 * l, st);
+    }
+    {   // after cross-attention: O (+x) -> LayerNorm3 -> FFN1 -> FFN2 (4 K splits) -> fold + next LayerNorm -> next projection
+      const bool last = l + 1 == Ld;
+      std::vector<ChainStage> st{gemm(a_da, lw[l].co, o_dx, D / 128, 1, D / 64, 1, 0, w.cob), lnorm(w.ln3w, w.ln3b, 0, nullptr),
+                                 gemm(a_dn, lw[l].f1, o_df, F / 128, 1, D / 64, 2, 1, w.f1b),
+                                 gemm(a_df, lw[l].f2, o_part, D / 128, 4, F / 4 / 64, 3, 0, nullptr),
+                                 last ? lnorm(e.daw, e.dab, 4, w.f2b) : lnorm(e.dec[l + 1].ln1w, e.dec[l + 1].ln1b, 4, w.f2b),
+                                 last ? gemm(a_dn, w_out, o_logp, V / 128, 1, D / 64, 0, 0, e.doutb)
+                                      : gemm(a_dn, lw[l + 1].qkv, o_qkv, 3 * D / 128, 1, D / 64, 0, 0, e.dec[l + 1].sqkvb)};
+      link(st[0], st[1], 0, D / 128);
+      link(st[1], st[2], 1, 1);
+      // FFN1 column tiles of 128 -> the K split of FFN2 that consumes them (F / 4 hidden units = F / 512 column tiles each)
+      st[2].sig_base = 2 * RT * 4; st[2].sig_stride = 4; st[2].sig_div = F / 4 / 128;
+      st[3].wait_base = 2 * RT * 4; st[3].wait_stride = 4; st[3].wait_ks = 1; st[3].wait_target = 8 * (F / 4 / 128);
+      link(st[3], st[4], 3, (D / 128) * 4);
+      link(st[4], st[5], 4, 1);
+      finish(2 + 2 * l, st);
+    }
+  }
+  e.chain_ready = true;
+  return 0;
+}
+
 static int decode_tail(Engine& e, cudaStream_t st);
+
+// one search iteration with the row-local chains: embed, [LN1 -> QKV], then per layer self-attention, chain, cross-attention, chain
+static int run_decode_step_x3_chain(Engine& e, cudaStream_t st) {
+  const ScConfig& c = e.cfg; const int D = c.d_model, R = e.cap.R;
+  const SearchBuffers& sb = e.sb;
+  const Planes da{e.dattn, (size_t)R * D, R};
+  SCB_CUDA_CHECK(cudaMemsetAsync(e.d_chain_ctr, 0, (size_t)e.chain_ctr_ints * sizeof(int), st));
+  PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, nullptr, nullptr, nullptr, st));
+  PD(T_DEC_EMBED, launch_build_self_keys(sb, st));
+  PD(T_DEC_QKV, launch_chain_x3(e.chains[0], e.chain_items[0], st));
+  e.launches += 3;
+  for (int l = 0; l < c.dec_layers; ++l) {
+    PD(T_DEC_SELF_ATTN, launch_dec_attention_x3(sb, 0, l, e.dqkv, 3 * D, nullptr, split_out(da, D), st));
+    PD(T_DEC_SO, launch_chain_x3(e.chains[1 + 2 * l], e.chain_items[1 + 2 * l], st));
+    PD(T_DEC_CROSS_ATTN, launch_dec_attention_x3(sb, 1, l, e.dq, D, nullptr, split_out(da, D), st));
+    PD(T_DEC_FFN1, launch_chain_x3(e.chains[2 + 2 * l], e.chain_items[2 + 2 * l], st));
+    e.launches += 4;
+  }
+  return decode_tail(e, st);
+}
 
 static int run_decode_step_x3(Engine& e, cudaStream_t st) {
   const ScConfig& c = e.cfg; const int D = c.d_model, F = c.ffn, V = c.vocab, R = e.cap.R;
   const SearchBuffers& sb = e.sb;
+  if (e.x3_chain && e.chain_ready && sb.kv_split) return run_decode_step_x3_chain(e, st);
   const int* nr = sb.n_rows;
   const Planes dn{e.dn, (size_t)R * D, R}, da{e.dattn, (size_t)R * D, R}, df{e.dffn, (size_t)R * F, R};
   PD(T_DEC_EMBED, launch_dec_embed(sb, e.demb, e.pe, e.dx, nullptr, nullptr, nullptr, st));
@@ -834,6 +998,7 @@ int sc_engine_create(const ScConfig* cfg, void* workspace, size_t bytes, void** 
     e->attn_f32_rows = !(a && strcmp(a, "cta") == 0);
     e->enc_attn_x3 = !(a && (strcmp(a, "rows") == 0 || strcmp(a, "cta") == 0));
     if (const char* xd = getenv("SCB_X3_DEC_PERSIST")) e->x3_dec_persist = atoi(xd);
+    if (const char* xc = getenv("SCB_X3_CHAIN")) e->x3_chain = atoi(xc) != 0;
     if (const char* xl = getenv("SCB_X3_LN_FUSED")) {
       e->x3_ln_fused_enc = strcmp(xl, "1") == 0 || strcmp(xl, "enc") == 0;
       e->x3_ln_fused_dec = strcmp(xl, "1") == 0 || strcmp(xl, "dec") == 0;
@@ -973,6 +1138,7 @@ int sc_engine_finalize(void* handle) {
   for (int i = 0; i < e->cfg.n_streams; ++i) all[i] = i;
   SCB_CUDA_CHECK(cudaMemcpy(e->d_reset, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (launch_search_reset(e->sb, e->d_reset, e->cfg.n_streams, 0)) return SC_ERR_CUDA;
+  if (build_decode_chains(*e)) return SC_ERR_CUDA;
   SCB_CUDA_CHECK(cudaDeviceSynchronize());
   e->finalized = true;
   return SC_OK;
@@ -1434,6 +1600,7 @@ int sc_engine_set_option(void* handle, const char* name, int32_t value) {
   if (strcmp(name, "graph_decode") == 0) { e->graph_decode = value != 0; return SC_OK; }
   if (strcmp(name, "graph_encoder") == 0) { e->graph_encoder = value != 0; return SC_OK; }
   if (strcmp(name, "pdl") == 0) { g_use_pdl = value != 0; return SC_OK; }
+  if (strcmp(name, "x3_chain") == 0) { e->x3_chain = value != 0; drop_graphs(*e); return SC_OK; }
   if (strcmp(name, "x3_ln_fused_encoder") == 0) { e->x3_ln_fused_enc = value != 0; drop_graphs(*e); return SC_OK; }
   if (strcmp(name, "x3_ln_fused_decoder") == 0) { e->x3_ln_fused_dec = value != 0; drop_graphs(*e); return SC_OK; }
   if (strcmp(name, "ln_prologue") == 0) { e->ln_prologue = value != 0 && e->cfg.precision == 1 && e->cfg.d_model == 256; return SC_OK; }

@@ -1,6 +1,8 @@
 // Launcher declarations for every CUDA kernel of the streaming decode path.
 // All launchers return 0 on success, -1 on failure (message via scb::get_last_error()).
 #pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "x3_split.cuh"
 
@@ -89,6 +91,37 @@ int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStre
 // persistent A-resident / chunk-accumulating form for encoder-sized products (kernels_gemm_x3p.cu)
 bool gemm_x3p_eligible(const GemmArgs& g, const X3Extra& x);
 int launch_gemm_x3p(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);
+// ---------------------------------------------------------------- row-local chains of the decode step (kernels_chain_x3.cu)
+struct ChainStage {
+  int type;                    // 0: GEMM stage, 1: LayerNorm stage (optionally folding split-K partial sums into x first)
+  int n_ct, n_ks, kb_item;     // GEMM: column tiles of 128, K splits, K blocks of 64 per item (even)
+  int map_a, map_w, map_o;     // indices into ChainParams::maps; hi plane, lo = + 1 (map_o: fp32 map, or planes hi / lo)
+  int out_mode, relu;          // 0: fp32 store, 1: fp32 add into the output (residual in place), 2: split planes,
+                               // 3: fp32 partial product of K split ks (row block ks * part_stride_rows)
+  int wait_base, wait_stride, wait_ks, wait_target;   // dependency: ctr[base + rt * stride (+ ks)] >= target; base < 0: none
+  int sig_base, sig_stride, sig_div;                  // completion: ctr[base + rt * stride + ct / div] += 1 per epilogue warp
+  int n_part;                  // LayerNorm: number of partial products to fold into x (0: none)
+  const float* bias;           // GEMM bias [N] or null
+  float* x;                    // LayerNorm: residual stream rows [M][256]
+  const float* part;           // LayerNorm: partial products [n_part][part_stride_rows][256]
+  const float* pbias;          // LayerNorm: bias added with the partials
+  const float* ln_w; const float* ln_b;
+  __half* out_hi; size_t out_plane;                   // LayerNorm: split planes [M][256], lo plane out_plane elements further
+};
+struct ChainParams {
+  ChainStage st[8];
+  int n_stages;
+  const CUtensorMap* maps;     // device array of tensor maps (64-byte aligned)
+  int* ctr;                    // completion counters of THIS launch, zero on entry
+  const int* n_rows_dev;       // device-side count of active rows (<= M)
+  int M;                       // row capacity
+  int part_stride_rows;        // rows between the partial products of consecutive K splits (multiple of 128)
+};
+int launch_chain_x3(const ChainParams& p, int max_items, cudaStream_t st);
+// cached tensor maps (kernels_gemm_tc.cu): 16-bit row-major matrix, 64-column x box_rows box; fp32 matrix, 32-column box
+int tc_get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out);
+int tc_get_map_f32(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out);
+
 // LayerNorm (eps 1e-12, same arithmetic as launch_layernorm) whose result is written as split fp16 planes
 int launch_layernorm_split(const float* x, int ldx, const float* w, const float* b, void* y2, size_t plane, int ldy,
                            int rows, int D, const int* n_rows_dev, cudaStream_t st);

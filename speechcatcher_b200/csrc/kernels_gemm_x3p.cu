@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
     // instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(XP_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int it = 0, a_gen = 0, prev_m = -1, chunk = 0;
+    long long w_full = 0, w_tmem = 0, w_afull = 0, t_begin = clock64();      // SCB_XP_DBG & 4: where the issuer waits
     for (int t = t0; t < t1; ++t) {
       const int m = t / p.n_tiles;
       const bool first_of_m = m != prev_m;
@@ -164,14 +165,20 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
       if (first_of_m) { a_ph = a_gen & 1; ++a_gen; prev_m = m; }
       for (int c = 0; c < n_chunks; ++c, ++chunk) {
         const int as = chunk & 1;
+        long long c0 = clock64();
         mbar_wait(&tmem_empty[as], ((chunk >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator stage
+        w_tmem += clock64() - c0;
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(as * 256), d_corr = d_main + 128;
         for (int kb2 = 0; kb2 < 2; ++kb2, ++it) {
           const int kb = 2 * c + kb2;
           const int s = it % NST, ph = (it / NST) & 1;
+          c0 = clock64();
           mbar_wait(&full_bar[s], ph);
+          w_full += clock64() - c0;
+          c0 = clock64();
           if (A_RES && first_of_m) mbar_wait(&a_full[kb], a_ph);
+          w_afull += clock64() - c0;
           tc_fence_after();
           if (elect_one_sync()) {
             unsigned char* st = ring + s * STAGE_BYTES;
@@ -195,6 +202,9 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
         }
       }
     }
+    if ((p.dbg & 4) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+      printf("x3p cta %d tiles %d K %d N %d: issuer total %lld clk, wait full %lld, wait a_full %lld, wait tmem_empty %lld\n",
+             (int)blockIdx.x, t1 - t0, p.K, p.N, clock64() - t_begin, w_full, w_afull, w_tmem);
   } else {
     // ===================== epilogue warps 2..9: thread <-> accumulator row; the two warps of a TMEM lane quarter
     // split the 128 columns
