@@ -228,7 +228,8 @@ int sc_linear_x3(const float* x, const void* w_planes_f16, const float* bias, co
  * TMA like the weights; the result is written as fp32 rows (y, may be NULL) and / or as split planes for the next
  * Linear (y_planes_f16, may be NULL).  kernel: 0 = the engine's choice (the persistent A-resident kernel of
  * kernels_gemm_x3p.cu for dense products with n % 128 == 0, k = 256 or k % 128 == 0 >= 384, one output form and an
- * in-place residual; the per-tile kernel otherwise), 1 = per-tile kernel, 2 = persistent kernel (error if ineligible). */
+ * in-place residual; the per-tile kernel otherwise), 1 = per-tile kernel, 2 = persistent kernel (error if ineligible; k = 256 without a
+ * residual takes the form with A in tensor memory, kernels_gemm_x3t.cu), 3 = persistent kernel, operands in shared memory. */
 int sc_linear_x3_planes(const void* x_planes_f16, int64_t x_plane_elems, int32_t x_rows, const void* w_planes_f16,
                         const float* bias, const float* residual, float* y, void* y_planes_f16, int64_t y_plane_elems,
                         int32_t m, int32_t n, int32_t k, int32_t relu, int32_t kernel, void* stream);

@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libscb200.so"
-SOURCES = ["kernels_gemm.cu", "kernels_gemm_tc.cu", "kernels_gemm_x3.cu", "kernels_gemm_x3p.cu", "kernels_chain_x3.cu", "kernels_frontend.cu", "kernels_encoder.cu",
+SOURCES = ["kernels_gemm.cu", "kernels_gemm_tc.cu", "kernels_gemm_x3.cu", "kernels_gemm_x3p.cu", "kernels_gemm_x3t.cu", "kernels_chain_x3.cu", "kernels_frontend.cu", "kernels_encoder.cu",
            "kernels_search.cu", "kernels_attn_mma.cu", "kernels_attn_f32.cu", "kernels_attn_x3.cu", "kernels_ffn_fused.cu", "segmenter.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -85,12 +85,16 @@ struct X3Extra {
   int ldx = 0;                // computed inside the GEMM (replaces launch_layernorm_split + the plane round trip)
   const float* ln_w = nullptr;
   const float* ln_b = nullptr;
-  int kernel = 0;             // 0: pick (persistent kernel where eligible), 1: per-tile kernel, 2: persistent kernel or error
+  int kernel = 0;             // 0: pick (persistent kernels where eligible), 1: per-tile kernel, 2: persistent kernel or error,
+                              // 3: persistent kernel with both operands in shared memory (never the A-in-TMEM form)
 };
 int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);
 // persistent A-resident / chunk-accumulating form for encoder-sized products (kernels_gemm_x3p.cu)
 bool gemm_x3p_eligible(const GemmArgs& g, const X3Extra& x);
 int launch_gemm_x3p(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);
+// persistent form with the A operand in tensor memory (K = 256, no residual; kernels_gemm_x3t.cu)
+bool gemm_x3t_eligible(const GemmArgs& g, const X3Extra& x);
+int launch_gemm_x3t(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStream_t st);
 // ---------------------------------------------------------------- row-local chains of the decode step (kernels_chain_x3.cu)
 struct ChainStage {
   int type;                    // 0: GEMM stage, 1: LayerNorm stage (optionally folding split-K partial sums into x first)

@@ -69,8 +69,13 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
   const int s = sb.act_streams[blockIdx.x];
   const int head = blockIdx.y;
   const StreamCtl& c = sb.ctl[s];
-  const int nb = c.n_hyp;
-  const int row0 = sb.row_base[s], D = sb.D, B = sb.B;
+  // beam 17..32: two m16 tiles of hypotheses per (stream, head), one CTA each (blockIdx.z); a tile reads every key but
+  // appends, scores and writes only its own rows h0 .. h0 + nb - 1 (a hypothesis' new token is visible to itself only,
+  // so the other tile's concurrent appends are always masked; the caches are zero-initialised, so masked values are finite)
+  const int h0 = blockIdx.z * 16;
+  const int nb = min(16, c.n_hyp - h0);
+  if (nb <= 0) return;
+  const int row0 = sb.row_base[s] + h0, D = sb.D, B = sb.B;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int RS = DK + 8;                 // padded smem row (fp16 elements): conflict-free ldmatrix
   constexpr int CPR = DK / 8;                // 16-byte chunks per row slice
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
       const float v = q[(size_t)(row0 + b) * ldq + D + which * D + head * DK + cc];
       __half h, l;
       x3_split(v, h, l);
-      __half* dst = base + ((size_t)(len - 1) * B + b) * row_stride + which * D + cc;
+      __half* dst = base + ((size_t)(len - 1) * B + h0 + b) * row_stride + which * D + cc;
       dst[0] = h;
       dst[2 * D] = l;
     }
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
     for (int i = tid; i < n_keys && i < X_KEYS_SMEM; i += 128) keys_s[i] = keys[i];
   } else {
     n_keys = c.Tb;
-    if (tid == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 4));
+    if (tid == 0 && h0 == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 4));
   }
   __syncthreads();                      // Q planes, key list staged; appended rows visible to the loads below
   const int n_steps = (n_keys + X_STEP - 1) / X_STEP;
@@ -218,10 +223,10 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
 #pragma unroll
           for (int nt = 0; nt < X_NT; ++nt) {
             const int o0 = ob[8 * nt + 2 * qd], o1 = ob[8 * nt + 2 * qd + 1];
-            if (!(o0 == -1 || o0 == r0)) sacc[nt][0] = -INFINITY;
-            if (!(o1 == -1 || o1 == r0)) sacc[nt][1] = -INFINITY;
-            if (!(o0 == -1 || o0 == r1)) sacc[nt][2] = -INFINITY;
-            if (!(o1 == -1 || o1 == r1)) sacc[nt][3] = -INFINITY;
+            if (!(o0 == -1 || o0 == h0 + r0)) sacc[nt][0] = -INFINITY;
+            if (!(o1 == -1 || o1 == h0 + r0)) sacc[nt][1] = -INFINITY;
+            if (!(o0 == -1 || o0 == h0 + r1)) sacc[nt][2] = -INFINITY;
+            if (!(o1 == -1 || o1 == h0 + r1)) sacc[nt][3] = -INFINITY;
           }
         }
       } else if (u0 + X_KPW > n_keys) {                        // cross: zero-filled rows past the last frame
@@ -503,16 +508,16 @@ static int launch_x3_t(const SearchBuffers& sb, __half* kv_layer, const float* q
     }
     attr = smem;
   }
-  launch_k(dec_attn_x3_kernel<DK, MODE>, dim3(sb.S, sb.H), dim3(128), smem, st, sb, kv_layer, q, ldq, out, so);
+  launch_k(dec_attn_x3_kernel<DK, MODE>, dim3(sb.S, sb.H, (sb.B + 15) / 16), dim3(128), smem, st, sb, kv_layer, q, ldq, out, so);
   SCB_LAUNCH_CHECK();
   return 0;
 }
 
 // mode 0: self attention (q = fused QKV GEMM output, row stride ldq = 3D; K|V of the new token at +D / +2D), needs
-// launch_build_self_keys earlier in the step; mode 1: cross attention.  Requires split-plane K|V caches and beam <= 16.
+// launch_build_self_keys earlier in the step; mode 1: cross attention.  Requires split-plane K|V caches and beam <= 32.
 int launch_dec_attention_x3(const SearchBuffers& sb, int mode, int layer, const float* q, int ldq, float* out,
                             SplitOut so, cudaStream_t st) {
-  if (!sb.kv_split || sb.B > 16) { set_last_error("attn_x3: needs split-plane KV caches and beam <= 16"); return -1; }
+  if (!sb.kv_split || sb.B > 32) { set_last_error("attn_x3: needs split-plane KV caches and beam <= 32"); return -1; }
   const int dk = sb.D / sb.H;
   __half* kv = mode == 0
       ? reinterpret_cast<__half*>(sb.skv) + (size_t)layer * sb.S * sb.Lcap * sb.B * 4 * sb.D

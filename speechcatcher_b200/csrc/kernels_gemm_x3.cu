@@ -328,9 +328,16 @@ int launch_gemm_x3(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStre
   if (g.M <= 0 || g.N <= 0) return 0;
   // encoder-sized products with plane operands: the persistent kernel (SCB_X3_PERSIST_MIN_M rows and up; 0 disables)
   static const int persist_min_m = [] { const char* v = getenv("SCB_X3_PERSIST_MIN_M"); return v ? atoi(v) : 1; }();
-  if (x.kernel == 2 || x.lnX ||
-      (x.kernel == 0 && !g.n_rows_dev && persist_min_m > 0 && g.M >= persist_min_m && gemm_x3p_eligible(g, x)))
+  if (x.kernel == 2 || x.kernel == 3 || x.lnX ||
+      (x.kernel == 0 && !g.n_rows_dev && persist_min_m > 0 && g.M >= persist_min_m && gemm_x3p_eligible(g, x))) {
+    // K = 256 without a residual can take the form with A in tensor memory (kernels_gemm_x3t.cu).  Verified bit-identical to
+    // the shared-memory form but measured slower as it stands (QKV 20 -> 33 us, FFN1 41 -> 55 us: its thread-per-row A loader
+    // costs ~12 us per row tile and the direct-store epilogue is slower than the TMA one, while the UMMA rate only improves
+    // from one 128x128x16 per ~108 cycles to the equivalent of ~92): opt-in, SCB_X3T=1.
+    static const bool use_ts = [] { const char* v = getenv("SCB_X3T"); return v && v[0] == '1'; }();
+    if (x.kernel != 3 && use_ts && gemm_x3t_eligible(g, x)) return launch_gemm_x3t(g, x, W2, st);
     return launch_gemm_x3p(g, x, W2, st);
+  }
   const bool a_tma = x.A2 != nullptr;
   if (g.K % TC_BK != 0 || g.N % 64 != 0 || (g.a_seg_off && g.seg_len % TC_BK != 0) || (!g.a_row_off && g.lda % 8 != 0) || !W2 ||
       (!g.C && !x.C2) || (a_tma && (g.a_row_off || x.a2_rows < g.M)) || (x.C2 && x.ldc2 % 8 != 0)) {

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
                                                                  XpParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int NST = A_RES ? 2 : 3;                                   // ring stages
+  // ring stages (SCB_XP_DBG & 8, timing experiment with & 1: the output staging becomes a third W stage of the A-resident form)
+  const int NST = A_RES ? ((p.dbg & 9) == 9 ? 3 : 2) : 3;
   constexpr int STAGE_BYTES = A_RES ? 2 * XP_PLANE : 4 * XP_PLANE;     // W hi | W lo   or   A hi | A lo | W hi | W lo
   constexpr int A_KB_BYTES = 2 * XP_PLANE;                             // resident A: hi | lo per K block
   unsigned char* ring = smem + (A_RES ? 4 * A_KB_BYTES : 0);
