@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--breakdown", action="store_true", help="always run the all-kernel timing pass")
-    ap.add_argument("--shards", type=int, default=int(os.environ.get("SCB_BENCH_SHARDS", "4")),
+    ap.add_argument("--shards", type=int, default=int(os.environ.get("SCB_BENCH_SHARDS", "2")),
                     help="split the GPU's streams into this many concurrently driven groups (own CUDA stream + host thread)")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("SCB_BENCH_GRAPH", "0")),
                     help="CUDA-graph replay (experimental, off by default): 1 = search iteration, 2 = encoder stack, 3 = both")

@@ -42,6 +42,12 @@ struct XpParams {
   const int* n_rows_dev;                         // optional device-side row count (decode step: active rows)
   const float* X; int ldx; const float* ln_w; const float* ln_b;   // LN form: A = LayerNorm(X rows), built in the kernel
   int dbg;                                       // SCB_XP_DBG (timing experiments only): 1 = no output, 2 = no TMEM drain
+  // direct != 0 (SCB_XP_DIRECT=1, experiment): store / plane outputs go from registers straight to global memory (thread <->
+  // row, 16-byte stores) instead of through the shared-memory staging + TMA store.  The kernel is bound by shared-memory
+  // bandwidth -- every 128x128x16 UMMA with both operands in shared memory reads 8 KB, the W ring writes 2.7 KB per UMMA,
+  // staging writes + reads another 2.7 KB: 13.4 KB / 128 B per cycle = 105 cycles per UMMA, measured 106
+  // (profiles/r2_gemm_x3p_issuer_waits.txt) -- but the uncoalesced stores cost more than the staging saves (FFN1 40 -> 50 us)
+  int direct; float* C; int ldc; __half* C2; size_t c2_plane; int ldc2;
 };
 
 __device__ __forceinline__ void xp_umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
@@ -157,7 +163,6 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
     // instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(XP_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int it = 0, a_gen = 0, prev_m = -1, chunk = 0;
-    long long w_full = 0, w_tmem = 0, w_afull = 0, t_begin = clock64();      // SCB_XP_DBG & 4: where the issuer waits
     for (int t = t0; t < t1; ++t) {
       const int m = t / p.n_tiles;
       const bool first_of_m = m != prev_m;
@@ -166,20 +171,14 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
       if (first_of_m) { a_ph = a_gen & 1; ++a_gen; prev_m = m; }
       for (int c = 0; c < n_chunks; ++c, ++chunk) {
         const int as = chunk & 1;
-        long long c0 = clock64();
         mbar_wait(&tmem_empty[as], ((chunk >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator stage
-        w_tmem += clock64() - c0;
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(as * 256), d_corr = d_main + 128;
         for (int kb2 = 0; kb2 < 2; ++kb2, ++it) {
           const int kb = 2 * c + kb2;
           const int s = it % NST, ph = (it / NST) & 1;
-          c0 = clock64();
           mbar_wait(&full_bar[s], ph);
-          w_full += clock64() - c0;
-          c0 = clock64();
           if (A_RES && first_of_m) mbar_wait(&a_full[kb], a_ph);
-          w_afull += clock64() - c0;
           tc_fence_after();
           if (elect_one_sync()) {
             unsigned char* st = ring + s * STAGE_BYTES;
@@ -203,9 +202,6 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
         }
       }
     }
-    if ((p.dbg & 4) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-      printf("x3p cta %d tiles %d K %d N %d: issuer total %lld clk, wait full %lld, wait a_full %lld, wait tmem_empty %lld\n",
-             (int)blockIdx.x, t1 - t0, p.K, p.N, clock64() - t_begin, w_full, w_afull, w_tmem);
   } else {
     // ===================== epilogue warps 2..9: thread <-> accumulator row; the two warps of a TMEM lane quarter
     // split the 128 columns
@@ -329,7 +325,26 @@ __global__ void __launch_bounds__(XP_THREADS, 1) gemm_x3p_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = fmaxf(acc[j], 0.f);
       }
-      if (row0 < M && !(p.dbg & 1)) {
+      if (p.direct && p.out_mode != 1) {
+        const int row = row0 + lane;
+        if (row < M && !(p.dbg & 1)) {
+          if (p.out_mode == 2) {
+            __half* dh = p.C2 + (size_t)row * p.ldc2 + col0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 uh, ul;
+              x3_split8(acc + 8 * i, uh, ul);
+              *reinterpret_cast<uint4*>(dh + 8 * i) = uh;
+              *reinterpret_cast<uint4*>(dh + p.c2_plane + 8 * i) = ul;
+            }
+          } else {
+            float* d = p.C + (size_t)row * p.ldc + col0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              *reinterpret_cast<float4*>(d + 4 * i) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          }
+        }
+      } else if (row0 < M && !(p.dbg & 1)) {
         if (p.out_mode == 2) {
           uint4 ul[8];
           if (lane == 0) xp_store_wait_read();                 // the previous tile's copy has read the staging rows
@@ -438,8 +453,9 @@ int launch_gemm_x3p(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStr
     maps[4] = maps[5];
   }
   static const int dbg = [] { const char* v = getenv("SCB_XP_DBG"); return v ? atoi(v) : 0; }();
+  static const int direct = [] { const char* v = getenv("SCB_XP_DIRECT"); return v ? atoi(v) : 0; }();
   XpParams p{g.bias, g.M, g.N, g.K, g.relu, g.C ? (g.R ? 1 : 0) : 2, cdiv(g.M, TC_BM), g.N / XP_BN, g.n_rows_dev,
-             x.lnX, x.ldx, x.ln_w, x.ln_b, dbg};
+             x.lnX, x.ldx, x.ln_w, x.ln_b, dbg, direct, g.C, g.ldc, reinterpret_cast<__half*>(x.C2), x.c2_plane, x.ldc2};
   if (x.lnX) return xp_launch<true, true>(maps, p, st);
   return g.K == 256 ? xp_launch<true, false>(maps, p, st) : xp_launch<false, false>(maps, p, st);
 }

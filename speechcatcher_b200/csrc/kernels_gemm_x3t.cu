@@ -15,6 +15,11 @@
 //     K chunks of 128 drained into registers with round-to-nearest adds as in kernels_gemm_x3p.cu;
 //   * the eight epilogue warps (thread <-> row, 32 columns each) store straight to global memory (fp32 rows or split
 //     planes): no staging traffic in shared memory.
+// Status: bit-identical to the shared-memory form (tests/test_gpu_gemm_x3.py) but SLOWER as it stands (QKV 20 -> 33 us,
+// FFN1 41 -> 55 us on one push of 256 streams): the thread-per-row loader takes ~24 k cycles per row tile and is not
+// overlapped with the UMMAs of the previous row tile (no room for a second A in TMEM), the direct-store epilogue makes the
+// issuer wait ~1.3 k cycles per tile, and the UMMA rate itself only improves from ~106 cycles per 128x128x16 to the
+// equivalent of ~92 (profiles/r2_gemm_x3p_issuer_waits.txt).  Opt-in (SCB_X3T=1); the engine uses kernels_gemm_x3p.cu.
 // Replaces torch.nn.functional.linear of the encoder layers where K = d_model
 // (speechcatcher/model/attention/multi_head_attention.py:79-83, layers/feed_forward.py:50).
 #include <cuda.h>
@@ -40,7 +45,6 @@ struct XtParams {
   float* C; int ldc;                             // fp32 output rows, or
   __half* C2; size_t c2_plane; int ldc2;         // split-plane output
   int M, N, relu, m_tiles, n_tiles;
-  int dbg;                                       // SCB_XP_DBG & 4: print where the issuer waits (timing experiments)
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]^T
@@ -122,30 +126,23 @@ __global__ void __launch_bounds__(XT_THREADS, 1) gemm_x3t_kernel(const __grid_co
     const uint32_t idesc = (1u << 4) | ((uint32_t)(XT_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t a_hi = tmem_base, a_lo = tmem_base + 128;
     int it = 0, a_gen = 0, prev_m = -1, chunk = 0;
-    long long w_full = 0, w_tmem = 0, w_afull = 0, t_begin = clock64(), c0;
     for (int t = t0; t < t1; ++t) {
       const int m = t / p.n_tiles;
       const bool last_of_m = (t + 1 == t1) || ((t + 1) / p.n_tiles != m);
       if (m != prev_m) {                     // the loaders have stored this row tile's A planes
-        c0 = clock64();
         mbar_wait(a_full, a_gen & 1);
-        w_afull += clock64() - c0;
         tc_fence_after();
         ++a_gen; prev_m = m;
       }
       for (int c = 0; c < 2; ++c, ++chunk) {
         const int as = chunk & 1;
-        c0 = clock64();
         mbar_wait(&tmem_empty[as], ((chunk >> 1) & 1) ^ 1);
-        w_tmem += clock64() - c0;
         tc_fence_after();
         const uint32_t d_main = tmem_base + XT_ACC_COL + (uint32_t)(as * 128), d_corr = d_main + 64;
         for (int kb2 = 0; kb2 < 2; ++kb2, ++it) {
           const int kb = 2 * c + kb2;
           const int s = it % XT_NST, ph = (it / XT_NST) & 1;
-          c0 = clock64();
           mbar_wait(&full_bar[s], ph);
-          w_full += clock64() - c0;
           tc_fence_after();
           if (elect_one_sync()) {
             unsigned char* st = smem + s * XT_STAGE;
@@ -166,9 +163,6 @@ __global__ void __launch_bounds__(XT_THREADS, 1) gemm_x3t_kernel(const __grid_co
         }
       }
     }
-    if ((p.dbg & 4) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-      printf("x3t cta %d tiles(64) %d N %d: issuer total %lld clk, wait full %lld, wait a_full %lld, wait tmem_empty %lld\n",
-             (int)blockIdx.x, t1 - t0, p.N, clock64() - t_begin, w_full, w_afull, w_tmem);
   } else if (warp >= 10) {
     // ===================== A loaders (warps 10..13): thread <-> row of the TMEM lane quarter warp % 4 =====================
     const int q = warp & 3;
@@ -293,9 +287,7 @@ int launch_gemm_x3t(const GemmArgs& g, const X3Extra& x, const void* W2, cudaStr
     attr_mk.cur() = 1;
   }
   XtParams p{g.bias, reinterpret_cast<const __half*>(x.A2), x.a2_plane, g.lda, g.C, g.ldc, reinterpret_cast<__half*>(x.C2),
-             x.c2_plane, x.ldc2, g.M, g.N, g.relu, cdiv(g.M, TC_BM), g.N / XT_BN, 0};
-  static const int dbg = [] { const char* v = getenv("SCB_XP_DBG"); return v ? atoi(v) : 0; }();
-  p.dbg = dbg;
+             x.c2_plane, x.ldc2, g.M, g.N, g.relu, cdiv(g.M, TC_BM), g.N / XT_BN};
   const long tiles = (long)p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   launch_k(gemm_x3t_kernel, dim3(grid), dim3(XT_THREADS), XT_SMEM, st, mh, ml, p);
