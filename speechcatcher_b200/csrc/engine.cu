@@ -325,6 +325,7 @@ static void carve(Engine& e, Carver& cv) {
     // precise mode, beam <= 16: K|V caches as split fp16 planes for the tensor-core attention (kernels_attn_x3.cu);
     // SCB_ATTN = "rows" / "cta" keeps fp32 caches and the CUDA-core attention kernels
     const char* a = getenv("SCB_ATTN");
+    { const char* hm = getenv("SCB_ATTN_HEAD_MAJOR"); sb.attn_head_major = hm ? atoi(hm) : 1; }
     sb.kv_split = c.precision == 2 && c.beam <= 32 && !(a && (strcmp(a, "rows") == 0 || strcmp(a, "cta") == 0));
   }
   if (sb.kv_bf16) sb.xkv = reinterpret_cast<float*>(cv.take<__nv_bfloat16>((size_t)c.dec_layers * S * k.Tcap * 2 * D));

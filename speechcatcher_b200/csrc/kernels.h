@@ -207,6 +207,7 @@ struct SearchBuffers {
   float* xkv;             // [Ld][S][Tcap][2D]  cross-attention K|V (bf16 elements when kv_bf16)
   int kv_bf16;
   int kv_split;           // K|V caches hold split fp16 planes per row: [hi K|V][lo K|V] (kernels_attn_x3.cu)
+  int attn_head_major;    // x3 decoder attention: grid (head, stream) instead of (stream, head)
   float* skv;             // [Ld][S][Lcap][B][2D] self-attention K|V (tree storage)
   // beam (ping-pong)
   int* yseq;              // [2][S][B][Lcap]

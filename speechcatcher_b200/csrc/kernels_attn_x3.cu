@@ -20,6 +20,7 @@
 // Replaces the attention part of speechcatcher/model/decoder/decoder_layer.py:80-113
 // (speechcatcher/model/attention/multi_head_attention.py:92-133).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace scb {
@@ -65,9 +66,13 @@ template <int DK, int MODE>
 __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, __half* kv_layer, const float* __restrict__ q,
                                                           int ldq, float* __restrict__ out, SplitOut so) {
   pdl_sync();
-  if ((int)blockIdx.x >= *sb.n_active) return;
-  const int s = sb.act_streams[blockIdx.x];
-  const int head = blockIdx.y;
+  // head-major grid (SCB_ATTN_HEAD_MAJOR, default): the CTAs of the eight heads of a stream are neighbours in launch order,
+  // so the 64-byte head slices of one 2 KB cache row are fetched at about the same time (DRAM page / L2 locality)
+  // instead of in eight separate passes over the cache
+  const int bs = sb.attn_head_major ? blockIdx.y : blockIdx.x;
+  if (bs >= *sb.n_active) return;
+  const int s = sb.act_streams[bs];
+  const int head = sb.attn_head_major ? blockIdx.x : blockIdx.y;
   const StreamCtl& c = sb.ctl[s];
   // beam 17..32: two m16 tiles of hypotheses per (stream, head), one CTA each (blockIdx.z); a tile reads every key but
   // appends, scores and writes only its own rows h0 .. h0 + nb - 1 (a hypothesis' new token is visible to itself only,
@@ -340,9 +345,10 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
 // rows / keys < n_rows, no mask); rows outside the query range get 0.  (structure: enc_attn_mma_kernel of the bf16 mode)
 template <int DK>
 __global__ void __launch_bounds__(96) enc_attn_x3_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                         const BlockDesc* __restrict__ blk, int D, SplitOut so) {
-  const BlockDesc b = blk[blockIdx.x];
-  const int head = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+                                                         const BlockDesc* __restrict__ blk, int D, SplitOut so, int head_major) {
+  const int blk_i = head_major ? blockIdx.y : blockIdx.x;
+  const BlockDesc b = blk[blk_i];
+  const int head = head_major ? blockIdx.x : blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int RS = DK + 8, CPR = DK / 8, KSTEPS = DK / 16, NDT = DK / 8, ROWS = 48;
   __shared__ __align__(16) __half sm_all[6 * ROWS * RS];      // Q hi, Q lo, K hi, K lo, V hi, V lo
   __half* Qh = sm_all;
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(96) enc_attn_x3_kernel(const float* __restrict
   __half* Kl = Kh + ROWS * RS;
   __half* Vh = Kl + ROWS * RS;
   __half* Vl = Vh + ROWS * RS;
-  const float* base = qkv + (size_t)blockIdx.x * kSlots * 3 * D + head * DK;
+  const float* base = qkv + (size_t)blk_i * kSlots * 3 * D + head * DK;
   for (int idx = tid; idx < 3 * ROWS * CPR; idx += 96) {
     const int which = idx / (ROWS * CPR), rem = idx % (ROWS * CPR), r = rem / CPR, ch = rem % CPR;
     uint4 uh = make_uint4(0, 0, 0, 0), ul = uh;
@@ -459,7 +465,7 @@ __global__ void __launch_bounds__(96) enc_attn_x3_kernel(const float* __restrict
       const float o0 = fmaf(oc[j][0], X3_INV_SCALE, om[j][0]), o1 = fmaf(oc[j][1], X3_INV_SCALE, om[j][1]);
       const float o2 = fmaf(oc[j][2], X3_INV_SCALE, om[j][2]), o3 = fmaf(oc[j][3], X3_INV_SCALE, om[j][3]);
       if (r0 < kSlots) {
-        const size_t row = (size_t)blockIdx.x * kSlots + r0;
+        const size_t row = (size_t)blk_i * kSlots + r0;
         if (so.base) {
           uint32_t h2, l2;
           split_pair(o0, o1, h2, l2);
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(96) enc_attn_x3_kernel(const float* __restrict
         } else { out[row * D + col] = o0; out[row * D + col + 1] = o1; }
       }
       if (r1 < kSlots) {
-        const size_t row = (size_t)blockIdx.x * kSlots + r1;
+        const size_t row = (size_t)blk_i * kSlots + r1;
         if (so.base) {
           uint32_t h2, l2;
           split_pair(o2, o3, h2, l2);
@@ -483,10 +489,11 @@ __global__ void __launch_bounds__(96) enc_attn_x3_kernel(const float* __restrict
 int launch_enc_attention_x3(const float* qkv, float* out, const BlockDesc* blk, int n_blk, int n_head, int d_model,
                             SplitOut so, cudaStream_t st) {
   if (n_blk <= 0) return 0;
-  dim3 grid(n_blk, n_head);
+  static const int head_major = [] { const char* v = getenv("SCB_ATTN_HEAD_MAJOR"); return v ? atoi(v) : 1; }();
+  dim3 grid = head_major ? dim3(n_head, n_blk) : dim3(n_blk, n_head);
   const int dk = d_model / n_head;
-  if (dk == 32) enc_attn_x3_kernel<32><<<grid, 96, 0, st>>>(qkv, out, blk, d_model, so);
-  else if (dk == 64) enc_attn_x3_kernel<64><<<grid, 96, 0, st>>>(qkv, out, blk, d_model, so);
+  if (dk == 32) enc_attn_x3_kernel<32><<<grid, 96, 0, st>>>(qkv, out, blk, d_model, so, head_major);
+  else if (dk == 64) enc_attn_x3_kernel<64><<<grid, 96, 0, st>>>(qkv, out, blk, d_model, so, head_major);
   else { set_last_error("enc_attn_x3: unsupported head dim %d", dk); return -1; }
   SCB_LAUNCH_CHECK();
   return 0;
@@ -508,7 +515,8 @@ static int launch_x3_t(const SearchBuffers& sb, __half* kv_layer, const float* q
     }
     attr = smem;
   }
-  launch_k(dec_attn_x3_kernel<DK, MODE>, dim3(sb.S, sb.H, (sb.B + 15) / 16), dim3(128), smem, st, sb, kv_layer, q, ldq, out, so);
+  const dim3 grid = sb.attn_head_major ? dim3(sb.H, sb.S, (sb.B + 15) / 16) : dim3(sb.S, sb.H, (sb.B + 15) / 16);
+  launch_k(dec_attn_x3_kernel<DK, MODE>, grid, dim3(128), smem, st, sb, kv_layer, q, ldq, out, so);
   SCB_LAUNCH_CHECK();
   return 0;
 }
