@@ -62,17 +62,21 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
   lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
 }
 
-template <int DK, int MODE>
-__global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, __half* kv_layer, const float* __restrict__ q,
+// WH = false: one CTA (4 warps) per (stream, head), the four warps split the keys of a 64-key step and merge at the end.
+// WH = true ("warp = head", opt-in experiment): one CTA per stream with one warp per head; a warp walks ALL keys of its head in
+// 16-key steps, so there is no merge, the fixed cost of a CTA (Q split, append, key list, first round trip) is paid once
+// per stream instead of once per (stream, head) in ~3 waves, and the eight head slices of a cache row are fetched together.
+template <int DK, int MODE, bool WH>
+__global__ void __launch_bounds__(WH ? 256 : 128, WH ? 2 : 4) dec_attn_x3_kernel(SearchBuffers sb, __half* kv_layer, const float* __restrict__ q,
                                                           int ldq, float* __restrict__ out, SplitOut so) {
   pdl_sync();
   // head-major grid (SCB_ATTN_HEAD_MAJOR, default): the CTAs of the eight heads of a stream are neighbours in launch order,
   // so the 64-byte head slices of one 2 KB cache row are fetched at about the same time (DRAM page / L2 locality)
   // instead of in eight separate passes over the cache
-  const int bs = sb.attn_head_major ? blockIdx.y : blockIdx.x;
+  const int bs = WH ? blockIdx.x : (sb.attn_head_major ? blockIdx.y : blockIdx.x);
   if (bs >= *sb.n_active) return;
   const int s = sb.act_streams[bs];
-  const int head = sb.attn_head_major ? blockIdx.x : blockIdx.y;
+  const int head = WH ? (int)(threadIdx.x >> 5) : (sb.attn_head_major ? blockIdx.x : blockIdx.y);
   const StreamCtl& c = sb.ctl[s];
   // beam 17..32: two m16 tiles of hypotheses per (stream, head), one CTA each (blockIdx.z); a tile reads every key but
   // appends, scores and writes only its own rows h0 .. h0 + nb - 1 (a hypothesis' new token is visible to itself only,
@@ -88,14 +92,24 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
   constexpr int NDT = DK / 8;                // n-tiles of the output
   constexpr int RPP = 32 / CPR;              // rows one pass of the warp's 32 lanes covers
   constexpr int PASSES = X_KPW / RPP;
-  constexpr int ST_HALFS = 4 * X_KPW * RS;   // one stage: K hi, K lo, V hi, V lo
+  // K|V stages: unpadded rows with the 16-byte chunks XOR-swizzled by the row (conflict-free ldmatrix like the padding, but
+  // 4 KB instead of 5 KB per 16-key stage), three stages per warp: two loads stay in flight while a tile is being
+  // multiplied.  (A load-only probe with this kernel's grid and two stages reaches 4.4-6.2 TB/s, scripts/probes/
+  // kv_pattern_probe.cu; the arithmetic between a warp's loads is what the third stage hides.)
+  constexpr int RSK = DK;
+  constexpr int NS = 3;
+  constexpr int ST_HALFS = 4 * X_KPW * RSK;  // one stage: K hi, K lo, V hi, V lo
+  auto swz = [](int r) { return (r / (8 / CPR)) & (CPR - 1); };
 
+  const int NWARP = WH ? sb.H : 4;           // warps per CTA
+  const int nthr = NWARP * 32;
+  const int qsets = WH ? NWARP : 1;          // WH: every warp has its own Q tile (its head)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __half* Qh = reinterpret_cast<__half*>(smem_raw);                              // [16][RS]
+  __half* Qh = reinterpret_cast<__half*>(smem_raw) + (WH ? warp * 2 * 16 * RS : 0);   // [16][RS]
   __half* Ql = Qh + 16 * RS;                                                     // [16][RS]
-  __half* KV = Ql + 16 * RS;                                                     // [4 warps][2 stages][4][X_KPW][RS]
-  signed char* own = reinterpret_cast<signed char*>(KV + 4 * 2 * ST_HALFS);      // [4][2][X_KPW]
-  int* keys_s = reinterpret_cast<int*>(own + 4 * 2 * X_KPW);                     // self only: [X_KEYS_SMEM]
+  __half* KV = reinterpret_cast<__half*>(smem_raw) + qsets * 2 * 16 * RS;        // [warps][2 stages][4][X_KPW][RS]
+  signed char* own = reinterpret_cast<signed char*>(KV + NWARP * NS * ST_HALFS); // [warps][NS][X_KPW]
+  int* keys_s = reinterpret_cast<int*>(own + ((NWARP * NS * X_KPW + 15) & ~15));   // self only: [X_KEYS_SMEM]
   // merge scratch aliases the K|V stages after the main loop
   float* mrg_m = reinterpret_cast<float*>(KV);                                   // [4][16]
   float* mrg_l = mrg_m + 64;                                                     // [4][16]
@@ -108,7 +122,8 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
   else base = kv_layer + (size_t)s * sb.Lcap * B * row_stride + head * DK;
 
   // ---- Q tile as hi / lo planes (rows >= nb are zero), self: append K|V of the scored token as split rows
-  for (int i = tid; i < 16 * DK; i += 128) {
+  const int t0i = WH ? lane : tid, tstep = WH ? 32 : 128;      // WH: each warp prepares its own head
+  for (int i = t0i; i < 16 * DK; i += tstep) {
     const int r = i / DK, d = i % DK;
     const float v = r < nb ? q[(size_t)(row0 + r) * ldq + head * DK + d] : 0.f;
     __half h, l;
@@ -119,8 +134,8 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
   int n_keys;
   const int* keys = nullptr;
   if (MODE == 0) {
-    if (tid == 0) atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * 4));
-    for (int i = tid; i < nb * 2 * DK; i += 128) {        // [len-1][b]: K at +0 / V at +D of the hi half, lo half at +2D
+    if (t0i == 0) atomicAdd(&sb.prof[3], (unsigned long long)((long long)nb * 2ll * len * DK * 4));
+    for (int i = t0i; i < nb * 2 * DK; i += tstep) {      // [len-1][b]: K at +0 / V at +D of the hi half, lo half at +2D
       const int b = i / (2 * DK), rem = i % (2 * DK), which = rem / DK, cc = rem % DK;
       const float v = q[(size_t)(row0 + b) * ldq + D + which * D + head * DK + cc];
       __half h, l;
@@ -131,25 +146,27 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
     }
     n_keys = sb.self_nkeys[s];
     keys = sb.self_keys + (size_t)s * sb.key_cap;
-    for (int i = tid; i < n_keys && i < X_KEYS_SMEM; i += 128) keys_s[i] = keys[i];
+    for (int i = tid; i < n_keys && i < X_KEYS_SMEM; i += nthr) keys_s[i] = keys[i];
   } else {
     n_keys = c.Tb;
-    if (tid == 0 && h0 == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 4));
+    if (t0i == 0 && h0 == 0) atomicAdd(&sb.prof[2], (unsigned long long)(2ll * n_keys * DK * 4));
   }
   __syncthreads();                      // Q planes, key list staged; appended rows visible to the loads below
-  const int n_steps = (n_keys + X_STEP - 1) / X_STEP;
+  constexpr int STEP = WH ? X_KPW : X_STEP;                     // keys all warps of a CTA advance per step
+  const int wk = WH ? 0 : X_KPW * warp;                         // this warp's first key inside a step
+  const int n_steps = (n_keys + STEP - 1) / STEP;
 
-  __half* kw = KV + (size_t)warp * (2 * ST_HALFS);
-  signed char* ownw = own + warp * 2 * X_KPW;
+  __half* kw = KV + (size_t)warp * (NS * ST_HALFS);
+  signed char* ownw = own + warp * NS * X_KPW;
   const int lr = lane / CPR, ch8 = (lane % CPR) * 8;
 
   auto issue = [&](int t, int buf) {
-    const int u0 = t * X_STEP + X_KPW * warp;
-    __half* st = kw + (size_t)buf * ST_HALFS;           // K hi | K lo | V hi | V lo, [X_KPW][RS] each
+    const int u0 = t * STEP + wk;
+    __half* st = kw + (size_t)buf * ST_HALFS;           // K hi | K lo | V hi | V lo, [X_KPW][RSK] each
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) {
       const int r = lr + RPP * ps, u = u0 + r;
-      __half* d0 = st + r * RS + ch8;
+      __half* d0 = st + r * RSK + (((lane % CPR) ^ swz(r)) << 3);
       if (u < n_keys) {
         const __half* src;
         if (MODE == 1) src = base + (size_t)u * row_stride + ch8;
@@ -159,15 +176,15 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
           if (ch8 == 0) ownw[buf * X_KPW + r] = (signed char)((kd_ >> 24) - 1);
         }
         xcp16(d0, src);                                   // K hi
-        xcp16(d0 + X_KPW * RS, src + 2 * D);              // K lo
-        xcp16(d0 + 2 * X_KPW * RS, src + D);              // V hi
-        xcp16(d0 + 3 * X_KPW * RS, src + 3 * D);          // V lo
+        xcp16(d0 + X_KPW * RSK, src + 2 * D);             // K lo
+        xcp16(d0 + 2 * X_KPW * RSK, src + D);             // V hi
+        xcp16(d0 + 3 * X_KPW * RSK, src + 3 * D);         // V lo
       } else {
         const uint4 z = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(d0) = z;
-        *reinterpret_cast<uint4*>(d0 + X_KPW * RS) = z;
-        *reinterpret_cast<uint4*>(d0 + 2 * X_KPW * RS) = z;
-        *reinterpret_cast<uint4*>(d0 + 3 * X_KPW * RS) = z;
+        *reinterpret_cast<uint4*>(d0 + X_KPW * RSK) = z;
+        *reinterpret_cast<uint4*>(d0 + 2 * X_KPW * RSK) = z;
+        *reinterpret_cast<uint4*>(d0 + 3 * X_KPW * RSK) = z;
         if (MODE == 0 && ch8 == 0) ownw[buf * X_KPW + r] = (signed char)-2;      // invisible to everyone
       }
     }
@@ -175,6 +192,7 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
   };
 
   if (n_steps > 0) issue(0, 0);
+  if (n_steps > 1) issue(1, 1);
   uint32_t qah[KSTEPS][4], qal[KSTEPS][4];
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -191,15 +209,17 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
   for (int i = 0; i < NDT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
   for (int t = 0; t < n_steps; ++t) {
-    const int buf = t & 1;
-    if (t + 1 < n_steps) { issue(t + 1, buf ^ 1); xcp_wait<1>(); } else { xcp_wait<0>(); }
+    const int buf = t % NS;
+    if (t + 2 < n_steps) { issue(t + 2, (t + 2) % NS); xcp_wait<2>(); }
+    else if (t + 1 < n_steps) { xcp_wait<1>(); }
+    else { xcp_wait<0>(); }
     __syncwarp();                       // the other lanes' copies / zero fills of this stage are visible
-    const int u0 = t * X_STEP + X_KPW * warp;
+    const int u0 = t * STEP + wk;
     if (u0 < n_keys) {
       const __half* kh = kw + (size_t)buf * ST_HALFS;
-      const __half* kl = kh + X_KPW * RS;
-      const __half* vh = kl + X_KPW * RS;
-      const __half* vl = vh + X_KPW * RS;
+      const __half* kl = kh + X_KPW * RSK;
+      const __half* vh = kl + X_KPW * RSK;
+      const __half* vl = vh + X_KPW * RSK;
       // ---- S = Q K^T for this warp's keys (raw scores): main term and low-order terms (x 2^11) separately
       float sacc[X_NT][4];
 #pragma unroll
@@ -208,7 +228,8 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
 #pragma unroll
         for (int k2 = 0; k2 < KSTEPS / 2; ++k2) {
           uint32_t bh[4], bl[4];          // B fragments of two k-steps with one ldmatrix per plane
-          const int off = (8 * nt + (lane & 7)) * RS + 32 * k2 + 8 * (lane >> 3);
+          const int krow = 8 * nt + (lane & 7);
+          const int off = krow * RSK + (((4 * k2 + (lane >> 3)) ^ swz(krow)) << 3);
           xldsm_x4(bh, kh + off);
           xldsm_x4(bl, kl + off);
           mma_f16(sm, qah[2 * k2], bh);
@@ -283,7 +304,8 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
 #pragma unroll
         for (int kk = 0; kk < X_KK; ++kk) {
           uint32_t bh[4], bl[4];        // V fragments of two output n-tiles with one transposing ldmatrix per plane
-          const int off = (16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 16 * n2 + 8 * (lane >> 4);
+          const int vrow = 16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1);
+          const int off = vrow * RSK + (((2 * n2 + (lane >> 4)) ^ swz(vrow)) << 3);
           xldsm_x4_trans(bh, vh + off);
           xldsm_x4_trans(bl, vl + off);
           mma_f16(om[0], pah[kk], bh);
@@ -304,6 +326,34 @@ __global__ void __launch_bounds__(128, 4) dec_attn_x3_kernel(SearchBuffers sb, _
       }
     }
     __syncwarp();                       // stage fully consumed before this warp refills it
+  }
+  if (WH) {
+    // ---- one warp owns the head: normalise and write rows r0, r1 straight from the accumulators
+#pragma unroll
+    for (int nd = 0; nd < NDT; ++nd) {
+      const int col = head * DK + 8 * nd + 2 * qd;
+      if (r0 < nb) {
+        const float a0 = o[nd][0] / l_run[0], a1 = o[nd][1] / l_run[0];
+        const size_t row = (size_t)(row0 + r0);
+        if (so.base) {
+          uint32_t h2, l2;
+          split_pair(a0, a1, h2, l2);
+          *reinterpret_cast<uint32_t*>(so.base + row * so.ld + col) = h2;
+          *reinterpret_cast<uint32_t*>(so.base + so.plane + row * so.ld + col) = l2;
+        } else { out[row * D + col] = a0; out[row * D + col + 1] = a1; }
+      }
+      if (r1 < nb) {
+        const float a2 = o[nd][2] / l_run[1], a3 = o[nd][3] / l_run[1];
+        const size_t row = (size_t)(row0 + r1);
+        if (so.base) {
+          uint32_t h2, l2;
+          split_pair(a2, a3, h2, l2);
+          *reinterpret_cast<uint32_t*>(so.base + row * so.ld + col) = h2;
+          *reinterpret_cast<uint32_t*>(so.base + so.plane + row * so.ld + col) = l2;
+        } else { out[row * D + col] = a2; out[row * D + col + 1] = a3; }
+      }
+    }
+    return;
   }
   __syncthreads();                      // every warp is done with its stages: the merge scratch aliases them
   // ---- merge the four warps' partial (m, l, O)
@@ -499,24 +549,26 @@ int launch_enc_attention_x3(const float* qkv, float* out, const BlockDesc* blk, 
   return 0;
 }
 
-template <int DK, int MODE>
+template <int DK, int MODE, bool WH>
 static int launch_x3_t(const SearchBuffers& sb, __half* kv_layer, const float* q, int ldq, float* out, SplitOut so,
                        cudaStream_t st) {
   constexpr int RS = DK + 8;
-  const size_t stages = sizeof(__half) * 4 * 2 * 4 * (size_t)X_KPW * RS;       // [4 warps][2 stages][4 planes][X_KPW][RS]
-  size_t smem = sizeof(__half) * (size_t)2 * 16 * RS + stages + 4 * 2 * X_KPW + 16;
+  const int nw = WH ? sb.H : 4;
+  const size_t stages = sizeof(__half) * 4 * 3 * (size_t)nw * X_KPW * DK;      // [warps][3 stages][4 planes][X_KPW][DK]
+  size_t smem = sizeof(__half) * (size_t)(WH ? nw : 1) * 2 * 16 * RS + stages + (((size_t)nw * 3 * X_KPW + 15) & ~(size_t)15) + 16;
   if (MODE == 0) smem += sizeof(int) * X_KEYS_SMEM;
   static PerDeviceMark mk;
   size_t& attr = mk.cur();
   if (attr < smem) {
-    if (cudaFuncSetAttribute(dec_attn_x3_kernel<DK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(dec_attn_x3_kernel<DK, MODE, WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error("attn_x3: cudaFuncSetAttribute(%zu) failed", smem);
       return -1;
     }
     attr = smem;
   }
-  const dim3 grid = sb.attn_head_major ? dim3(sb.H, sb.S, (sb.B + 15) / 16) : dim3(sb.S, sb.H, (sb.B + 15) / 16);
-  launch_k(dec_attn_x3_kernel<DK, MODE>, grid, dim3(128), smem, st, sb, kv_layer, q, ldq, out, so);
+  const int tiles = (sb.B + 15) / 16;
+  const dim3 grid = WH ? dim3(sb.S, 1, tiles) : (sb.attn_head_major ? dim3(sb.H, sb.S, tiles) : dim3(sb.S, sb.H, tiles));
+  launch_k(dec_attn_x3_kernel<DK, MODE, WH>, grid, dim3(WH ? 32 * sb.H : 128), smem, st, sb, kv_layer, q, ldq, out, so);
   SCB_LAUNCH_CHECK();
   return 0;
 }
@@ -530,8 +582,18 @@ int launch_dec_attention_x3(const SearchBuffers& sb, int mode, int layer, const 
   __half* kv = mode == 0
       ? reinterpret_cast<__half*>(sb.skv) + (size_t)layer * sb.S * sb.Lcap * sb.B * 4 * sb.D
       : reinterpret_cast<__half*>(sb.xkv) + (size_t)layer * sb.S * sb.Tcap * 4 * sb.D;
-  if (dk == 32) return mode == 0 ? launch_x3_t<32, 0>(sb, kv, q, ldq, out, so, st) : launch_x3_t<32, 1>(sb, kv, q, ldq, out, so, st);
-  if (dk == 64) return mode == 0 ? launch_x3_t<64, 0>(sb, kv, q, ldq, out, so, st) : launch_x3_t<64, 1>(sb, kv, q, ldq, out, so, st);
+  // warp = head form: measured slower (a warp then walks four times as many 16-key steps, and the step latency is what
+  // bounds the kernel: self 49.6 -> 68.5 us, cross 44.3 -> 55.1 us per launch); opt-in, SCB_ATTN_WARP_HEAD=1; <= 8 heads
+  static const bool wh_env = [] { const char* v = getenv("SCB_ATTN_WARP_HEAD"); return v && v[0] == '1'; }();
+  const bool wh = wh_env && sb.H <= 8;
+  if (dk == 32) {
+    if (wh) return mode == 0 ? launch_x3_t<32, 0, true>(sb, kv, q, ldq, out, so, st) : launch_x3_t<32, 1, true>(sb, kv, q, ldq, out, so, st);
+    return mode == 0 ? launch_x3_t<32, 0, false>(sb, kv, q, ldq, out, so, st) : launch_x3_t<32, 1, false>(sb, kv, q, ldq, out, so, st);
+  }
+  if (dk == 64) {
+    if (wh) return mode == 0 ? launch_x3_t<64, 0, true>(sb, kv, q, ldq, out, so, st) : launch_x3_t<64, 1, true>(sb, kv, q, ldq, out, so, st);
+    return mode == 0 ? launch_x3_t<64, 0, false>(sb, kv, q, ldq, out, so, st) : launch_x3_t<64, 1, false>(sb, kv, q, ldq, out, so, st);
+  }
   set_last_error("attn_x3: unsupported head dim %d", dk);
   return -1;
 }
