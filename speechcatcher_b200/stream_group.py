@@ -362,7 +362,8 @@ class StreamGroup:
             out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
         else:
             if flops is None or flops <= 0:
-                flops = 2.0 * cnt[1] * F * D              # decoder FFN GEMMs: active rows x 2 F D
+                # decoder FFN GEMMs: 2 F D per active row and LAYER (cnt[1] counts active rows once per search iteration)
+                flops = 2.0 * cnt[1] * F * D * self.cfg.dec_layers
             ach = flops / sec / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
             out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
