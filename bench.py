@@ -564,7 +564,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample_s = args.cpu_sample_seconds or cpu_sample_seconds(args.warmup + args.steps)   # = the reference arm's
         cpu = CpuBaseline(md, args.beam, cores)
-        cpu.run(min(sample_s, 2.0))                     # warm-up: model load, thread pools
+        # warm-up with the SAME sample: the reference's per-chunk tensor shapes grow with the utterance, and the first pass
+        # over new shapes is ~2x slower (primitive / allocator caches) -- a 2 s warm-up left the timed pass cold (2.4 vs
+        # 4.8 audio-s/s for the reference arm, which times passes after a full-length warm-up)
+        cpu.run(sample_s)
         v, p50 = cpu.run(sample_s)
         cpu.close()
         cpu_base = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": cpu.kind, "sample": cpu.describe(sample_s),
