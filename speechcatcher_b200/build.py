@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src):
         obj = objdir / (src[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("SCB_NVCC_EXTRA", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -28,7 +28,17 @@ namespace scb {
 // Keys per warp per step.  ncu (profiles/r2_ncu_dec_attn_x3.txt) showed the first version (32 keys, 85 KB of stages per
 // CTA, two CTAs = 8 warps per SM) at 12 % warp occupancy and ~1.2 TB/s: latency-bound.  16 keys per warp-step halve
 // the stages (44 KB per CTA, five CTAs = 20 warps per SM).
-constexpr int X_KPW = 16;
+#ifndef SCB_X_KPW
+#define SCB_X_KPW 16
+#endif
+#ifndef SCB_X_NS
+#define SCB_X_NS 3
+#endif
+// compile-time knobs for tuning runs (SCB_NVCC_EXTRA="-DSCB_X_KPW=32 -DSCB_X_NS=2").  Measured on the bench workload, strict mode
+// (keys, stages) -> audio-s/s: (16, 2 padded) 3 893, (16, 3) 4 046, (16, 4) 3 972, (32, 2) 3 995, (32, 3) 3 805
+constexpr int X_KPW = SCB_X_KPW;
+constexpr int X_NSTAGES = SCB_X_NS;
+constexpr int X_MINB = (X_KPW * X_NSTAGES <= 48) ? 4 : (X_KPW * X_NSTAGES <= 64 ? 3 : 2);   // CTAs per SM the stages leave room for
 constexpr int X_STEP = 4 * X_KPW;  // keys per CTA step
 constexpr int X_NT = X_KPW / 8;    // score n-tiles per warp
 constexpr int X_KK = X_KPW / 16;   // k-steps of the P*V product per warp
@@ -67,7 +77,7 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
 // 16-key steps, so there is no merge, the fixed cost of a CTA (Q split, append, key list, first round trip) is paid once
 // per stream instead of once per (stream, head) in ~3 waves, and the eight head slices of a cache row are fetched together.
 template <int DK, int MODE, bool WH>
-__global__ void __launch_bounds__(WH ? 256 : 128, WH ? 2 : 4) dec_attn_x3_kernel(SearchBuffers sb, __half* kv_layer, const float* __restrict__ q,
+__global__ void __launch_bounds__(WH ? 256 : 128, WH ? 1 : X_MINB) dec_attn_x3_kernel(SearchBuffers sb, __half* kv_layer, const float* __restrict__ q,
                                                           int ldq, float* __restrict__ out, SplitOut so) {
   pdl_sync();
   // head-major grid (SCB_ATTN_HEAD_MAJOR, default): the CTAs of the eight heads of a stream are neighbours in launch order,
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(WH ? 256 : 128, WH ? 2 : 4) dec_attn_x3_kernel
   // multiplied.  (A load-only probe with this kernel's grid and two stages reaches 4.4-6.2 TB/s, scripts/probes/
   // kv_pattern_probe.cu; the arithmetic between a warp's loads is what the third stage hides.)
   constexpr int RSK = DK;
-  constexpr int NS = 3;
+  constexpr int NS = X_NSTAGES;
   constexpr int ST_HALFS = 4 * X_KPW * RSK;  // one stage: K hi, K lo, V hi, V lo
   auto swz = [](int r) { return (r / (8 / CPR)) & (CPR - 1); };
 
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(WH ? 256 : 128, WH ? 2 : 4) dec_attn_x3_kernel
   };
 
   if (n_steps > 0) issue(0, 0);
-  if (n_steps > 1) issue(1, 1);
+  if (NS > 2 && n_steps > 1) issue(1, 1);
   uint32_t qah[KSTEPS][4], qal[KSTEPS][4];
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -210,9 +220,13 @@ __global__ void __launch_bounds__(WH ? 256 : 128, WH ? 2 : 4) dec_attn_x3_kernel
 
   for (int t = 0; t < n_steps; ++t) {
     const int buf = t % NS;
-    if (t + 2 < n_steps) { issue(t + 2, (t + 2) % NS); xcp_wait<2>(); }
-    else if (t + 1 < n_steps) { xcp_wait<1>(); }
-    else { xcp_wait<0>(); }
+    if (NS > 2) {
+      if (t + 2 < n_steps) { issue(t + 2, (t + 2) % NS); xcp_wait<2>(); }
+      else if (t + 1 < n_steps) { xcp_wait<1>(); }
+      else { xcp_wait<0>(); }
+    } else {
+      if (t + 1 < n_steps) { issue(t + 1, (t + 1) % NS); xcp_wait<1>(); } else { xcp_wait<0>(); }
+    }
     __syncwarp();                       // the other lanes' copies / zero fills of this stage are visible
     const int u0 = t * STEP + wk;
     if (u0 < n_keys) {
@@ -554,8 +568,8 @@ static int launch_x3_t(const SearchBuffers& sb, __half* kv_layer, const float* q
                        cudaStream_t st) {
   constexpr int RS = DK + 8;
   const int nw = WH ? sb.H : 4;
-  const size_t stages = sizeof(__half) * 4 * 3 * (size_t)nw * X_KPW * DK;      // [warps][3 stages][4 planes][X_KPW][DK]
-  size_t smem = sizeof(__half) * (size_t)(WH ? nw : 1) * 2 * 16 * RS + stages + (((size_t)nw * 3 * X_KPW + 15) & ~(size_t)15) + 16;
+  const size_t stages = sizeof(__half) * 4 * X_NSTAGES * (size_t)nw * X_KPW * DK;   // [warps][stages][4 planes][X_KPW][DK]
+  size_t smem = sizeof(__half) * (size_t)(WH ? nw : 1) * 2 * 16 * RS + stages + (((size_t)nw * X_NSTAGES * X_KPW + 15) & ~(size_t)15) + 16;
   if (MODE == 0) smem += sizeof(int) * X_KEYS_SMEM;
   static PerDeviceMark mk;
   size_t& attr = mk.cur();
