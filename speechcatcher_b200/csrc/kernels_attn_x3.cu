@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(WH ? 256 : 128, WH ? 1 : X_MINB) dec_attn_x3_k
     }
     n_keys = sb.self_nkeys[s];
     keys = sb.self_keys + (size_t)s * sb.key_cap;
+    // bytes this kernel really reads: every key row of the list once per (stream, head, tile), 4 planes x DK fp16
+    if (t0i == 0) atomicAdd(&sb.prof[5], (unsigned long long)((long long)n_keys * 4 * DK * 2));
     for (int i = tid; i < n_keys && i < X_KEYS_SMEM; i += nthr) keys_s[i] = keys[i];
   } else {
     n_keys = c.Tb;

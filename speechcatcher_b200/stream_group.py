@@ -357,9 +357,16 @@ class StreamGroup:
         sec = max(ms, 1e-9) / 1e3
         hbm = {"ctc_prefix": cnt[0], "dec_cross_attn": cnt[2], "dec_self_attn": cnt[3]}
         if kernel in hbm:
-            ach = hbm[kernel] / sec / 1e9
+            nbytes, extra = hbm[kernel], {}
+            if kernel == "dec_self_attn" and cnt[5] > 0:
+                # the SURVEY formula (2 L D e bytes per HYPOTHESIS and layer) charges K|V once per hypothesis; the kernel reads
+                # the shared ancestor chain once per STREAM, so the roofline is stated against the bytes it moves
+                extra = {"bytes": "moved (key-list rows x 4 planes x d_k fp16 per stream, head and layer)",
+                         "survey_formula_GBs": cnt[3] / sec / 1e9}
+                nbytes = cnt[5]
+            ach = nbytes / sec / 1e9
             peak = float(peaks["hbm_gbs"])
-            out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+            out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, **extra}
         else:
             if flops is None or flops <= 0:
                 # decoder FFN GEMMs: 2 F D per active row and LAYER (cnt[1] counts active rows once per search iteration)
