@@ -49,6 +49,10 @@ CASES = {
     "m_d2_b5_60s": ("m_d2", 5, 60 * 16000, "noise", "A", False, 1.0, 0, 0.0, True),
     "xl_d4_b10_60s": ("xl_d4", 10, 60 * 16000, "noise", "A", False, 1.0, 0, 0.0, True),
     "xl_b10_20s": ("xl", 10, 20 * 16000, "noise", "A", False, 1.0, 0, 0.0, True),
+    # BASELINE.json configs[4] (beam 20: two hypothesis tiles in the tensor-core decoder attention) and configs[2]
+    # (the L architecture, full depth: 18 encoder / 8 decoder layers)
+    "xl_d4_b20_6s": ("xl_d4", 20, 6 * 16000 + 321, "noise", "A", False, 1.0, 2),
+    "l_b10_6s": ("l", 10, 6 * 16000, "tones", "A", False, 1.0, 0),
 }
 
 
